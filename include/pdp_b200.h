@@ -1,0 +1,98 @@
+/* pdp_b200.h -- C ABI of the B200-native batched PDP engine (libpdp_b200.so).
+ *
+ * The reference (wanxinjin/Pontryagin-Differentiable-Programming) has no FFI: its boundary is the
+ * Python class surface of PDP/PDP.py.  Each entry point below is what a binding of that surface
+ * calls for the hot path; the reference method it replaces is cited per function.
+ *
+ * Conventions
+ *   - every array pointer is a DEVICE pointer (float64, row-major, contiguous, batch-major) unless
+ *     the parameter name ends in _host (pinned or pageable host memory);
+ *   - the caller owns every buffer including workspaces; the library allocates nothing per call;
+ *   - launches are asynchronous on `stream`; no implicit device synchronisation;
+ *   - return value 0 = ok, <0 = error (pdp_last_error() gives a thread-local message); no exceptions,
+ *     no exit();
+ *   - status[b] (int32, optional, caller zero-initialises) collects per-trajectory flags:
+ *     bit 0 = non-finite value encountered, bit 1 = Quu not positive definite in the Riccati sweep.
+ *   - theta_stride = r for per-trajectory parameters, 0 when one parameter vector is shared.
+ */
+#ifndef PDP_B200_H
+#define PDP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pdp_system pdp_system_t;
+typedef void* pdp_stream_t; /* cudaStream_t */
+
+enum { PDP_OK = 0, PDP_ERR_ARG = -1, PDP_ERR_LOAD = -2, PDP_ERR_CUDA = -3, PDP_ERR_WORKSPACE = -4, PDP_ERR_UNSUPPORTED = -5 };
+enum { PDP_KIND_OC = 1, PDP_KIND_SYSID = 2, PDP_KIND_CP = 3, PDP_KIND_LQR = 4 };
+enum { PDP_OP_AUX_LQR = 1, PDP_OP_SWEEP = 2, PDP_OP_SWEEP_HOST = 3 };
+
+/* Load a generated system module (the product of OCSys.setDyn/setPathCost/setFinalCost + diffPMP,
+ * reference PDP/PDP.py:96-119,222-270: here "differentiate PMP" = code-generate + nvcc). */
+int pdp_load_system(const char* module_path, pdp_system_t** out);
+void pdp_free_system(pdp_system_t* sys);
+/* dims[0..3] = kind, n_state, n_control, n_auxvar */
+int pdp_system_dims(const pdp_system_t* sys, int* dims);
+const char* pdp_last_error(void);
+const char* pdp_version(void);
+
+/* Bytes of caller-provided workspace an operation needs (0 if none). */
+size_t pdp_workspace_bytes(const pdp_system_t* sys, int op, int B, int H);
+
+/* Forward rollout + cost + costate recursion at given controls; optional dH/du (adjoint gradient).
+ * Replaces the rollout/costate semantics of OCSys.ocSolver (PDP/PDP.py:158-175, 196-209) and, with
+ * dHu != NULL, ControlPlanning.recmat_step's gradient (PDP/PDP.py:1100-1114).
+ *   x0[B,n] theta[B|1,r] U[B,H,m] -> X[B,H+1,n] Lam[B,H,n] (Lam[t] = lambda_{t+1}) cost[B] dHu[B,H,m]
+ * Lam, cost, dHu may be NULL. */
+int pdp_rollout_costate(pdp_system_t* sys, int B, int H, const double* x0, const double* theta, int theta_stride,
+                        const double* U, double* X, double* Lam, double* cost, double* dHu, int* status,
+                        pdp_stream_t stream);
+
+/* Fused OCSys.getAuxSys (PDP/PDP.py:272-314) + LQR.lqrSolver (PDP/PDP.py:446-615).
+ *   X,U,Lam,theta as above; X0aux[B|1,n,r] initial condition of the auxiliary system (NULL = zeros,
+ *   x0aux_stride 0 = shared); outputs dXdtheta[B,H+1,n,r], dUdtheta[B,H,m,r] (either may be NULL).
+ *   Optional fused IRL loss/chain rule (Examples/IRL/quadrotor/uav_PDP.py:67-75): Xref[B,H+1,n],
+ *   Uref[B,H,m] -> loss_dp[B,r+1] = (loss_b, dp_b[0..r-1]) per trajectory (dp is 1/2 grad, like the
+ *   reference).  workspace: pdp_workspace_bytes(sys, PDP_OP_AUX_LQR, B, H). */
+int pdp_aux_lqr(pdp_system_t* sys, int B, int H, const double* X, const double* U, const double* Lam,
+                const double* theta, int theta_stride, const double* X0aux, int x0aux_stride,
+                double* dXdtheta, double* dUdtheta, const double* Xref, const double* Uref, double* loss_dp,
+                void* workspace, size_t ws_bytes, int* status, pdp_stream_t stream);
+
+/* One full PDP sweep = pdp_rollout_costate + pdp_aux_lqr on device buffers (the BASELINE metric's unit). */
+int pdp_sweep(pdp_system_t* sys, int B, int H, const double* x0, const double* theta, int theta_stride,
+              const double* U, double* X, double* Lam, double* cost, double* dXdtheta, double* dUdtheta,
+              const double* Xref, const double* Uref, double* loss_dp, void* workspace, size_t ws_bytes,
+              int* status, pdp_stream_t stream);
+
+/* Dense auxiliary matrices for the legacy OCSys.getAuxSys return value (PDP/PDP.py:303-313).
+ *   aux[B,H,NDENSE] with per-step layout [F n*n|G n*m|E n*r|Hxx|Hxu|Hxe|Hux m*n|Huu|Hue] row-major,
+ *   term[B, n*n + n*r] = [hxx|hxe]. */
+int pdp_aux_eval(pdp_system_t* sys, int B, int H, const double* X, const double* U, const double* Lam,
+                 const double* theta, int theta_stride, double* aux, double* term, pdp_stream_t stream);
+
+/* Forward-sensitivity sweeps (ControlPlanning.step PDP/PDP.py:850-878; SysID.step :1261-1296):
+ * kind SYSID: args = (x0[B,n], theta[B|1,r], inputs[B,H,m], Xobs[B,H+1,n] or NULL)
+ * kind CP   : args = (x0[B,n], theta[B|1,r])  (policy parameters), rollout under the policy.
+ * outputs X[B,H+1,n], Uout[B,H,m] (CP), dX[B,H+1,n,r], dU[B,H,m,r] (CP), loss_dp[B,r+1]; any may be NULL. */
+int pdp_sens_fwd(pdp_system_t* sys, int B, int H, const double* x0, const double* theta, int theta_stride,
+                 const double* inputs, const double* Xobs, double* X, double* Uout, double* dX, double* dU,
+                 double* loss_dp, int* status, pdp_stream_t stream);
+
+/* Host-buffer variant of pdp_sweep for end-to-end use: copies x0/theta/U (and Xref/Uref) from host,
+ * runs the sweep with the fused loss, copies loss_dp[B,r+1] (and cost[B] if cost_host != NULL) back.
+ * All device scratch comes from `workspace` (pdp_workspace_bytes(sys, PDP_OP_SWEEP_HOST, B, H)). */
+int pdp_sweep_host(pdp_system_t* sys, int B, int H, const double* x0_host, const double* theta_host,
+                   int theta_stride, const double* U_host, const double* Xref_host, const double* Uref_host,
+                   double* loss_dp_host, double* cost_host, int keep_dtraj, void* workspace, size_t ws_bytes,
+                   pdp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDP_B200_H */

@@ -1,0 +1,818 @@
+"""Expressions -> one sm_100a CUDA translation unit per (system, mode).
+
+This is the "diffPMP" step of the engine (reference ``PDP/PDP.py:222-270`` builds 14 CasADi
+``Function`` objects and ``getAuxSys`` :272-314 calls them per time step): here the same
+derivatives are taken symbolically ONCE and emitted as straight-line CUDA that is compiled into
+the kernels -- the auxiliary-system matrices never exist in HBM.
+
+Three module kinds are generated (see DESIGN.md for the kernel designs and rooflines):
+
+``oc``     OCSys path: ``pdp_k_rollout_costate`` (thread / trajectory), ``pdp_k_aux_lqr``
+           (warp / trajectory: chunked aux evaluation with lanes = time steps, structured-sparse
+           Riccati sweep in the stacked form, gain spill, aux forward pass), ``pdp_k_aux_eval``
+           (thread / (trajectory, step): dense aux matrices for the legacy ``getAuxSys`` API).
+``sysid``  SysID path: rollout + forward sensitivity + fused loss / gradient.
+``cp``     ControlPlanning path: policy rollout + forward sensitivity + fused chain rule, and the
+           adjoint gradient that replaces the reference's recovery matrix.
+
+The sparsity pattern of every derivative matrix is known at generation time, so all small-matrix
+products are emitted fully unrolled over structural non-zeros only; constants are folded into the
+instruction stream, shared expression nodes are stored once per step ("slots").
+"""
+from __future__ import annotations
+
+import hashlib
+from typing import Dict, List, Sequence, Tuple
+
+from . import symbolic as S
+from .symbolic import SX, Node
+
+WARP = 32
+
+
+# ---------------------------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------------------------
+
+def _lit(v: float) -> str:
+    return S._c_literal(float(v))
+
+
+class SlotTable:
+    """Distinct non-constant expression nodes that must be materialised per time step."""
+
+    def __init__(self):
+        self.nodes: List[Node] = []
+        self.index: Dict[int, int] = {}
+
+    def entry(self, node: Node):
+        """Classify a matrix entry: ('z',) | ('c', value) | ('v', slot, sign)."""
+        if node is S.ZERO:
+            return ("z",)
+        if node.op == "const":
+            return ("c", node.val)
+        sign = 1.0
+        if node.op == "neg":
+            sign, node = -1.0, node.args[0]
+        k = self.index.get(node.uid)
+        if k is None:
+            k = len(self.nodes)
+            self.index[node.uid] = k
+            self.nodes.append(node)
+        return ("v", k, sign)
+
+    def __len__(self):
+        return len(self.nodes)
+
+
+def _emit_function(name: str, inputs: Sequence[Tuple[str, SX]], outputs: Sequence[Node], out_expr,
+                   qualifiers="__device__ __forceinline__") -> str:
+    """``void name(const double* in0, ..., double* out)`` computing ``outputs``.
+
+    ``out_expr(i)`` gives the C lvalue for output ``i``.  Inputs are read into locals first so the
+    stores to ``out`` can never alias the loads."""
+    leaf: Dict[int, str] = {}
+    used = {n.uid for n in S.topo_order(outputs) if n.op == "sym"}
+    loads = []
+    for pname, sx in inputs:
+        for k, e in enumerate(sx.elements()):
+            if e.uid in used:
+                loads.append("  const double %s_%d = %s[%d];" % (pname, k, pname, k))
+                leaf[e.uid] = "%s_%d" % (pname, k)
+    lines, names = S.emit_c(outputs, leaf)
+    sig = ", ".join("const double* __restrict__ %s" % p for p, _ in inputs)
+    body = ["%s void %s(%s, double* __restrict__ out) {" % (qualifiers, name, sig)]
+    body += loads + lines
+    for i, nm in enumerate(names):
+        body.append("  %s = %s;" % (out_expr(i), nm))
+    body.append("}")
+    return "\n".join(body)
+
+
+class _Acc:
+    """Tracks first-touch of accumulator registers so products start with a mul, not 0 + fma."""
+
+    def __init__(self, prefix, n, lines, indent="      "):
+        self.prefix, self.n, self.lines, self.indent = prefix, n, lines, indent
+        self.touched = [False] * n
+
+    def name(self, j):
+        return "%s%d" % (self.prefix, j)
+
+    def add(self, j, a: str, ent, load):
+        """acc_j += a * entry, with entry classified by SlotTable.entry; ``load(slot)`` -> C name."""
+        if ent[0] == "z":
+            return
+        acc = self.name(j)
+        if ent[0] == "c":
+            c = ent[1]
+            if not self.touched[j]:
+                self.lines.append("%s%s = %s;" % (self.indent, acc, a if c == 1.0 else ("-%s" % a if c == -1.0 else "%s * %s" % (a, _lit(c)))))
+            elif c == 1.0:
+                self.lines.append("%s%s += %s;" % (self.indent, acc, a))
+            elif c == -1.0:
+                self.lines.append("%s%s -= %s;" % (self.indent, acc, a))
+            else:
+                self.lines.append("%s%s = fma(%s, %s, %s);" % (self.indent, acc, a, _lit(c), acc))
+        else:
+            s = load(ent[1])
+            neg = ent[2] < 0
+            if not self.touched[j]:
+                self.lines.append("%s%s = %s%s * %s;" % (self.indent, acc, "-" if neg else "", a, s))
+            else:
+                self.lines.append("%s%s = fma(%s%s, %s, %s);" % (self.indent, acc, "-" if neg else "", a, s, acc))
+        self.touched[j] = True
+
+    def finish(self):
+        for j in range(self.n):
+            if not self.touched[j]:
+                self.lines.append("%s%s = 0.0;" % (self.indent, self.name(j)))
+
+
+class _SlotLoader:
+    """Emits broadcast shared-memory loads of aux slots, pairing neighbours into one 16-byte load."""
+
+    def __init__(self, lines, base="ar", needed=(), indent="      ", tag="s"):
+        self.lines, self.base, self.indent, self.tag = lines, base, indent, tag
+        self.needed = set(needed)
+        self.loaded: Dict[int, str] = {}
+
+    def __call__(self, e: int) -> str:
+        nm = self.loaded.get(e)
+        if nm is not None:
+            return nm
+        pair = e ^ 1
+        if pair in self.needed and pair not in self.loaded:
+            lo = min(e, pair)
+            v = "%s%d_%d" % (self.tag, lo, len(self.lines))
+            self.lines.append("%sconst double2 %s = *reinterpret_cast<const double2*>(%s + %d);" % (self.indent, v, self.base, lo))
+            self.loaded[lo] = v + ".x"
+            self.loaded[lo + 1] = v + ".y"
+        else:
+            v = "%s%d_%d" % (self.tag, e, len(self.lines))
+            self.lines.append("%sconst double %s = %s[%d];" % (self.indent, v, self.base, e))
+            self.loaded[e] = v
+        return self.loaded[e]
+
+
+def _odd(n):
+    return n if n % 2 == 1 else n + 1
+
+
+def _even(n):
+    return n if n % 2 == 0 else n + 1
+
+
+# ---------------------------------------------------------------------------------------------
+# OC module
+# ---------------------------------------------------------------------------------------------
+
+class OCModuleSource:
+    """Generates the CUDA source of an ``oc`` module from the symbolic optimal-control system."""
+
+    def __init__(self, state: SX, control: SX, auxvar: SX, dyn: SX, path_cost: SX, final_cost: SX,
+                 chunk: int = 8, warps_per_block: int = 4):
+        self.x, self.u, self.th = state, control, auxvar
+        self.n, self.m, self.r = state.numel(), control.numel(), auxvar.numel()
+        self.ns = self.n + self.m + self.r
+        self.chunk = int(chunk)
+        self.wpb = int(warps_per_block)
+        n, m, r = self.n, self.m, self.r
+        self.dyn = SX(dyn).reshape((n, 1))
+        self.c = SX(path_cost)
+        self.h = SX(final_cost)
+        self.lam = SX.sym("lam", n)
+        # --- diffPMP (reference PDP.py:229-270)
+        Hm = self.c + S.dot(self.dyn, self.lam)
+        self.dfx = S.jacobian(self.dyn, self.x)
+        self.dfu = S.jacobian(self.dyn, self.u)
+        self.dfe = S.jacobian(self.dyn, self.th)
+        self.dHx = S.jacobian(Hm, self.x).T
+        self.dHu = S.jacobian(Hm, self.u).T
+        self.ddHxx = S.jacobian(self.dHx, self.x)
+        self.ddHxu = S.jacobian(self.dHx, self.u)
+        self.ddHxe = S.jacobian(self.dHx, self.th)
+        self.ddHux = S.jacobian(self.dHu, self.x)
+        self.ddHuu = S.jacobian(self.dHu, self.u)
+        self.ddHue = S.jacobian(self.dHu, self.th)
+        self.dhx = S.jacobian(self.h, self.x).T
+        self.ddhxx = S.jacobian(self.dhx, self.x)
+        self.ddhxe = S.jacobian(self.dhx, self.th)
+        self._layout()
+
+    # ---- slot layout ---------------------------------------------------------------------------
+    def _layout(self):
+        n, m, r, ns = self.n, self.m, self.r, self.ns
+        slots = SlotTable()
+        # S = [F | G | E]  (n x ns), row-major walk so slot order follows the use order
+        self.S_ent = [[None] * ns for _ in range(n)]
+        for k in range(n):
+            for j in range(ns):
+                if j < n:
+                    node = self.dfx.at(k, j)
+                elif j < n + m:
+                    node = self.dfu.at(k, j - n)
+                else:
+                    node = self.dfe.at(k, j - n - m)
+                self.S_ent[k][j] = slots.entry(node)
+        self.nvar_s = len(slots)
+        # stacked Hamiltonian Hessian  [[Hxx Hxu],[Hxu^T Huu],[Hxe^T Hue^T]]   (ns x (n+m))
+        # (the reference never uses Hux in arithmetic, only transpose(Hxu): PDP.py:569,572,598)
+        nm = n + m
+        self.H_ent = [[None] * nm for _ in range(ns)]
+        for j in range(ns):
+            for l in range(nm):
+                if j < n and l < n:
+                    node = self.ddHxx.at(j, l)
+                elif j < n:
+                    node = self.ddHxu.at(j, l - n)
+                elif j < nm and l < n:
+                    node = self.ddHxu.at(l, j - n)
+                elif j < nm:
+                    node = self.ddHuu.at(j - n, l - n)
+                elif l < n:
+                    node = self.ddHxe.at(l, j - nm)
+                else:
+                    node = self.ddHue.at(l - n, j - nm)
+                self.H_ent[j][l] = slots.entry(node)
+        self.slots = slots
+        self.nvar = len(slots)
+        self.auxld = _even(max(self.nvar, 2))
+        self.ldh = _odd(nm)
+        self.ldz = _odd(n)
+        self.ldk = _even(n)
+
+    # ---- device functions ----------------------------------------------------------------------
+    def _device_functions(self) -> str:
+        x, u, th, lam = ("x", self.x), ("u", self.u), ("th", self.th), ("lam", self.lam)
+        parts = []
+        parts.append(_emit_function("pdp_f_dyn", [x, u, th], self.dyn.elements(), lambda i: "out[%d]" % i))
+        parts.append(_emit_function("pdp_f_path_cost", [x, u, th], self.c.elements(), lambda i: "out[%d]" % i))
+        parts.append(_emit_function("pdp_f_final_cost", [x, th], self.h.elements(), lambda i: "out[%d]" % i))
+        parts.append(_emit_function("pdp_f_dHx", [x, u, lam, th], self.dHx.elements(), lambda i: "out[%d]" % i))
+        parts.append(_emit_function("pdp_f_dHu", [x, u, lam, th], self.dHu.elements(), lambda i: "out[%d]" % i))
+        parts.append(_emit_function("pdp_f_dhx", [x, th], self.dhx.elements(), lambda i: "out[%d]" % i))
+        # all aux slots / only the dynamics-Jacobian slots
+        parts.append(_emit_function("pdp_f_aux_slots", [x, u, lam, th], self.slots.nodes, lambda i: "out[%d]" % i))
+        parts.append(_emit_function("pdp_f_dyn_slots", [x, u, th], self.slots.nodes[:self.nvar_s] or [S.ZERO],
+                                    lambda i: "out[%d]" % i))
+        # terminal Hessians, dense row-major [hxx (n*n) | hxe (n*r)]
+        term = [self.ddhxx.at(i, j) for i in range(self.n) for j in range(self.n)] + \
+               [self.ddhxe.at(i, j) for i in range(self.n) for j in range(self.r)]
+        parts.append(_emit_function("pdp_f_terminal", [x, th], term, lambda i: "out[%d]" % i))
+        # dense aux matrices for the legacy API: F G E Hxx Hxu Hxe Hux Huu Hue, each row-major
+        dense = []
+        for M in (self.dfx, self.dfu, self.dfe, self.ddHxx, self.ddHxu, self.ddHxe, self.ddHux, self.ddHuu, self.ddHue):
+            dense += [M.at(i, j) for i in range(M.shape[0]) for j in range(M.shape[1])]
+        parts.append(_emit_function("pdp_f_aux_dense", [x, u, lam, th], dense, lambda i: "out[%d]" % i))
+        return "\n\n".join(parts)
+
+    # ---- the Riccati step body ---------------------------------------------------------------------
+    def _backward_step(self) -> str:
+        n, m, r, ns = self.n, self.m, self.r, self.ns
+        nm = n + m
+        L: List[str] = []
+        ind = "      "
+        # phase A: z = y . S   (lanes < n own row i of P in y0..y{n-1})
+        L.append(ind + "// A: Z(i,:) = P(i,:) * [F|G|E]  -- structural non-zeros only, S broadcast from the chunk buffer")
+        L.append(ind + "double " + ", ".join("z%d" % j for j in range(ns)) + ";")
+        needed = {e[1] for row in self.S_ent for e in row if e[0] == "v"}
+        load = _SlotLoader(L, "ar", needed, ind, "sa")
+        acc = _Acc("z", ns, L, ind)
+        for k in range(n):
+            for j in range(ns):
+                acc.add(j, "y%d" % k, self.S_ent[k][j], load)
+        acc.finish()
+        # phase B: transpose through shared memory
+        L.append(ind + "// B: lane j picks up column j of Z; the auxvar lanes add their column of W")
+        L.append(ind + "if (lane < %d) {" % n)
+        for j in range(ns):
+            L.append(ind + "  ZT[%d + lane] = z%d;" % (j * self.ldz, j))
+        L.append(ind + "}")
+        L.append(ind + "__syncwarp();")
+        L.append(ind + "double " + ", ".join("c%d" % k for k in range(n)) + ";")
+        L.append(ind + "{ const double* zr = ZT + lrow * %d;" % self.ldz)
+        for k in range(n):
+            L.append(ind + "  c%d = zr[%d];" % (k, k))
+        L.append(ind + "}")
+        L.append(ind + "if (lane >= %d) {" % nm)
+        for k in range(n):
+            L.append(ind + "  c%d += y%d;" % (k, k))
+        L.append(ind + "}")
+        # phase C: q = Hrow + c . [F|G]
+        L.append(ind + "// C: Q(j,:) = Hstack(j,:) + Z(:,j)^T [F|G]")
+        L.append(ind + "double " + ", ".join("q%d" % l for l in range(nm)) + ";")
+        L.append(ind + "{ const double* hr = Hd + lrow * %d;" % self.ldh)
+        for l in range(nm):
+            L.append(ind + "  q%d = hr[%d];" % (l, l))
+        L.append(ind + "}")
+        needed = {self.S_ent[k][l][1] for k in range(n) for l in range(nm) if self.S_ent[k][l][0] == "v"}
+        load = _SlotLoader(L, "ar", needed, ind, "sc")
+        acc = _Acc("q", nm, L, ind)
+        acc.touched = [True] * nm
+        for k in range(n):
+            for l in range(nm):
+                acc.add(l, "c%d" % k, self.S_ent[k][l], load)
+        # phase D: Quu to smem, LDL^T in every lane, solve for own right-hand side
+        L.append(ind + "// D: Quu = rows n..n+m-1; every lane factors it (LDL^T, uniform) and solves for its own column")
+        L.append(ind + "if (lane >= %d && lane < %d) {" % (n, nm))
+        for a in range(m):
+            L.append(ind + "  QUU[(lane - %d) * %d + %d] = q%d;" % (n, m, a, n + a))
+        L.append(ind + "}")
+        L.append(ind + "__syncwarp();")
+        # LDL^T: A = L D L^T, unit lower L.  d_i, l_ij (i>j)
+        for i in range(m):
+            for j in range(i + 1):
+                L.append(ind + "double a%d%d = QUU[%d];" % (i, j, i * m + j))
+        for j in range(m):
+            # d_j = a_jj - sum_k l_jk^2 d_k
+            expr = "a%d%d" % (j, j)
+            for k in range(j):
+                expr = "fma(-l%d%d * l%d%d, d%d, %s)" % (j, k, j, k, k, expr)
+            L.append(ind + "const double d%d = %s;" % (j, expr))
+            L.append(ind + "bad |= !(d%d > 0.0);" % j)
+            L.append(ind + "const double r%d = 1.0 / d%d;" % (j, j))
+            for i in range(j + 1, m):
+                expr = "a%d%d" % (i, j)
+                for k in range(j):
+                    expr = "fma(-l%d%d * l%d%d, d%d, %s)" % (i, k, j, k, k, expr)
+                L.append(ind + "const double l%d%d = (%s) * r%d;" % (i, j, expr, j))
+        # solve L D L^T v = -rhs ; rhs = q[n..n+m-1]
+        for i in range(m):
+            expr = "-q%d" % (n + i)
+            for k in range(i):
+                expr = "fma(-l%d%d, w%d, %s)" % (i, k, k, expr)
+            L.append(ind + "const double w%d = %s;" % (i, expr))
+        for i in reversed(range(m)):
+            expr = "w%d * r%d" % (i, i)
+            for k in range(i + 1, m):
+                expr = "fma(-l%d%d, v%d, %s)" % (k, i, k, expr)
+            L.append(ind + "const double v%d = %s;" % (i, expr))
+        # phase E: spill gains, share K, update
+        L.append(ind + "// E: spill (K|k) for the forward pass, broadcast K, rank-m update of the stack")
+        L.append(ind + "if (lane < %d) {" % n)
+        for a in range(m):
+            L.append(ind + "  KS[%d + lane] = v%d;" % (a * self.ldk, a))
+        L.append(ind + "}")
+        L.append(ind + "if (gslot >= 0) {")
+        L.append(ind + "  double* gp = gains + ((size_t)b * H + t) * %d + gslot * %d;" % ((n + r) * m, m))
+        L.append(self._vec_store("gp", ["v%d" % a for a in range(m)], ind + "  "))
+        L.append(ind + "}")
+        L.append(ind + "__syncwarp();")
+        for a in range(m):
+            if self.ldk % 2 == 0:
+                for l in range(0, n - 1, 2):
+                    L.append(ind + "{ const double2 kk = *reinterpret_cast<const double2*>(KS + %d); q%d = fma(q%d, kk.x, q%d); q%d = fma(q%d, kk.y, q%d); }"
+                             % (a * self.ldk + l, l, n + a, l, l + 1, n + a, l + 1))
+                if n % 2 == 1:
+                    L.append(ind + "q%d = fma(q%d, KS[%d], q%d);" % (n - 1, n + a, a * self.ldk + n - 1, n - 1))
+            else:
+                for l in range(n):
+                    L.append(ind + "q%d = fma(q%d, KS[%d], q%d);" % (l, n + a, a * self.ldk + l, l))
+        for l in range(n):
+            L.append(ind + "y%d = q%d;" % (l, l))
+        return "\n".join(L)
+
+    def _vec_store(self, ptr, names, ind):
+        m = len(names)
+        out = []
+        if m % 2 == 0:
+            for a in range(0, m, 2):
+                out.append("%s*reinterpret_cast<double2*>(%s + %d) = make_double2(%s, %s);" % (ind, ptr, a, names[a], names[a + 1]))
+        else:
+            for a in range(m):
+                out.append("%s%s[%d] = %s;" % (ind, ptr, a, names[a]))
+        return "\n".join(out)
+
+    def _forward_step(self) -> str:
+        n, m, r, ns = self.n, self.m, self.r, self.ns
+        L: List[str] = []
+        ind = "      "
+        L.append(ind + "// U(:,c) = k(:,c) + K X(:,c)   (lane n+c owns column c)")
+        for a in range(m):
+            L.append(ind + "double u%d = g%d;" % (a, a))
+        for a in range(m):
+            if self.ldk % 2 == 0:
+                for l in range(0, n - 1, 2):
+                    L.append(ind + "{ const double2 kk = *reinterpret_cast<const double2*>(KS + %d); u%d = fma(kk.x, x%d, u%d); u%d = fma(kk.y, x%d, u%d); }"
+                             % (a * self.ldk + l, a, l, a, a, l + 1, a))
+                if n % 2 == 1:
+                    L.append(ind + "u%d = fma(KS[%d], x%d, u%d);" % (a, a * self.ldk + n - 1, n - 1, a))
+            else:
+                for l in range(n):
+                    L.append(ind + "u%d = fma(KS[%d], x%d, u%d);" % (a, a * self.ldk + l, l, a))
+        L.append(ind + "// X+(:,c) = F X(:,c) + G U(:,c) + E(:,c)")
+        L.append(ind + "double " + ", ".join("n%d" % i for i in range(n)) + ";")
+        needed = {e[1] for row in self.S_ent for e in row if e[0] == "v"}
+        load = _SlotLoader(L, "ar", needed, ind, "sf")
+        acc = _Acc("n", n, L, ind)
+        for i in range(n):
+            for l in range(n):
+                acc.add(i, "x%d" % l, self.S_ent[i][l], load)
+            for a in range(m):
+                acc.add(i, "u%d" % a, self.S_ent[i][n + a], load)
+        acc.finish()
+        # E column: predicated adds (E is sparse for mechanical systems)
+        for i in range(n):
+            for c in range(r):
+                ent = self.S_ent[i][n + m + c]
+                if ent[0] == "z":
+                    continue
+                if ent[0] == "c":
+                    val = _lit(ent[1])
+                else:
+                    val = ("-" if ent[2] < 0 else "") + load(ent[1])
+                L.append(ind + "n%d += (col == %d) ? %s : 0.0;" % (i, c, val))
+        return "\n".join(L)
+
+    # ---- whole translation unit ----------------------------------------------------------------
+    def source(self) -> str:
+        n, m, r, ns = self.n, self.m, self.r, self.ns
+        nm = n + m
+        # constant and variable entries of the dense Hamiltonian stack
+        hconst, hvar = [], []
+        for j in range(ns):
+            for l in range(nm):
+                e = self.H_ent[j][l]
+                if e[0] == "c":
+                    hconst.append((j * self.ldh + l, e[1]))
+                elif e[0] == "v":
+                    hvar.append((j * self.ldh + l, e[1], e[2]))
+        nhs = len(hvar)
+        kh = max(1, (nhs + WARP - 1) // WARP)
+        hd_size = _even(ns * self.ldh + 1)  # +1 dummy slot for idle scatter lanes
+        zt_size = _even(max(ns * self.ldz, n * r + m * r))
+        ks_size = _even(m * self.ldk)
+        auxc_size = _even(max(self.chunk * self.auxld, n * n + n * r))
+        off_hd = auxc_size
+        off_zt = off_hd + hd_size
+        off_ks = off_zt + zt_size
+        off_quu = off_ks + ks_size
+        off_th = off_quu + _even(m * m)
+        off_dl = off_th + _even(r)
+        warp_doubles = _even(off_dl + self.chunk * nm)
+        defs = {
+            "N": n, "M": m, "R": r, "NS": ns, "NM": nm, "NVAR": self.nvar, "NVAR_S": self.nvar_s,
+            "AUXLD": self.auxld, "CH": self.chunk, "WPB": self.wpb, "LDH": self.ldh, "LDZ": self.ldz,
+            "LDK": self.ldk, "HD_SIZE": hd_size, "HD_DUMMY": ns * self.ldh,
+            "OFF_HD": off_hd, "OFF_ZT": off_zt, "OFF_KS": off_ks, "OFF_QUU": off_quu, "OFF_TH": off_th, "OFF_DL": off_dl,
+            "WARP_DOUBLES": warp_doubles, "NHS": nhs, "KH": kh, "GREC": (n + r) * m,
+            "NDENSE": n * n + n * m + n * r + n * n + n * m + n * r + m * n + m * m + m * r,
+        }
+        header = ["// GENERATED by pontryagin_differentiable_programming_b200/codegen.py -- do not edit",
+                  "#include <cuda_runtime.h>", "#include <math.h>", "#include <stdint.h>"]
+        header += ["#define PDP_%s %d" % kv for kv in defs.items()]
+        tables = []
+        src_tab = [e for (_, e, _) in hvar] + [0] * (kh * WARP - nhs)
+        dst_tab = [d for (d, _, _) in hvar] + [ns * self.ldh] * (kh * WARP - nhs)
+        sgn_tab = [s for (_, _, s) in hvar] + [0.0] * (kh * WARP - nhs)
+        tables.append("__device__ const short pdp_hs_src[%d] = {%s};" % (len(src_tab), ", ".join(map(str, src_tab))))
+        tables.append("__device__ const short pdp_hs_dst[%d] = {%s};" % (len(dst_tab), ", ".join(map(str, dst_tab))))
+        tables.append("__device__ const double pdp_hs_sgn[%d] = {%s};" % (len(sgn_tab), ", ".join(_lit(s) for s in sgn_tab)))
+        hinit = "\n".join("    if (lane == %d) Hd[%d] = %s;" % (i % WARP, d, _lit(v)) for i, (d, v) in enumerate(hconst))
+        scatter = "\n".join("      Hd[hdst%d] = hsgn%d * ar[hsrc%d];" % (k, k, k) for k in range(kh))
+        tabload = "\n".join("  const int hsrc%d = pdp_hs_src[%d + lane], hdst%d = pdp_hs_dst[%d + lane]; const double hsgn%d = pdp_hs_sgn[%d + lane];"
+                            % (k, k * WARP, k, k * WARP, k, k * WARP) for k in range(kh))
+        ydecl = "double " + ", ".join("y%d = 0.0" % k for k in range(n)) + ";"
+        # terminal init: lane i<n takes row i of hxx, lane n+m+c takes column c of hxe
+        term_init = []
+        for k in range(n):
+            term_init.append("    y%d = (lane < %d) ? TB[lane * %d + %d] : ((lane >= %d && lane < %d) ? TB[%d + %d * %d + (lane - %d)] : 0.0);"
+                             % (k, n, n, k, nm, ns, n * n, k, r, nm))
+        xdecl = "double " + ", ".join("x%d" % k for k in range(n)) + ";"
+        xinit = "\n".join("    x%d = (X0a != nullptr && col >= 0) ? X0a[(size_t)(x0a_stride ? b : 0) * %d + %d * %d + col] : 0.0;"
+                          % (k, n * r, k, r) for k in range(n))
+        gdecl = "double " + ", ".join("g%d = 0.0" % a for a in range(m)) + ";"
+        gload = self._gload()
+        ks_store = "\n".join("        KS[%d + lane] = g%d;" % (a * self.ldk, a) for a in range(m))
+        stage = "\n".join(["        OUT[%d + col] = n%d;" % (i * r, i) for i in range(n)] +
+                          ["        OUT[%d + col] = u%d;" % (n * r + a * r, a) for a in range(m)])
+        xcopy = "\n".join("      x%d = n%d;" % (k, k) for k in range(n))
+        x0stage = "\n".join("      OUT[%d + col] = x%d;" % (i * r, i) for i in range(n))
+
+        kernels = _OC_KERNELS_TEMPLATE
+        rep = {
+            "@@TABLOAD@@": tabload, "@@HINIT@@": hinit, "@@SCATTER@@": scatter, "@@YDECL@@": ydecl,
+            "@@TERM_INIT@@": "\n".join(term_init), "@@BACKWARD_STEP@@": self._backward_step(),
+            "@@XDECL@@": xdecl, "@@XINIT@@": xinit, "@@GDECL@@": gdecl, "@@GLOAD@@": gload,
+            "@@KS_STORE@@": ks_store, "@@FORWARD_STEP@@": self._forward_step(), "@@STAGE@@": stage,
+            "@@XCOPY@@": xcopy, "@@X0STAGE@@": x0stage,
+            "@@DPACC@@": "\n".join(["        dpacc = fma(dl[%d], x%d, dpacc);" % (i, i) for i in range(n)] +
+                                    ["        dpacc = fma(dl[%d], u%d, dpacc);" % (n + a, a) for a in range(m)]),
+            "@@DPTERM@@": "\n".join("      dpacc = fma(dl[%d], x%d, dpacc);" % (i, i) for i in range(n)),
+            "@@XCHK@@": "\n".join("    chk += x%d;" % k for k in range(n)),
+        }
+        for k, v in rep.items():
+            kernels = kernels.replace(k, v)
+        return "\n".join(header) + "\n\n" + "\n".join(tables) + "\n\n" + self._device_functions() + "\n\n" + kernels
+
+    def _gload(self):
+        m = self.m
+        if m % 2 == 0:
+            return "\n".join("        { const double2 gg = *reinterpret_cast<const double2*>(gp + %d); g%d = gg.x; g%d = gg.y; }" % (a, a, a + 1)
+                             for a in range(0, m, 2))
+        return "\n".join("        g%d = gp[%d];" % (a, a) for a in range(m))
+
+    def key(self) -> str:
+        return hashlib.sha256(self.source().encode()).hexdigest()[:20]
+
+
+_OC_KERNELS_TEMPLATE = r'''
+// =====================================================================================================
+// Kernel 1: forward rollout + cost + costate recursion (+ optional dH/du), one thread per trajectory.
+//   restates reference OCSys.ocSolver's rollout semantics at given controls (PDP.py:158-175) and the PMP
+//   costate recursion (PDP.py:203-209): Lam[t] = lambda_{t+1}, lambda_H = dh/dx(x_H).
+// =====================================================================================================
+extern "C" __global__ void __launch_bounds__(128)
+pdp_k_rollout_costate(int B, int H, const double* __restrict__ x0, const double* __restrict__ theta, int theta_stride,
+                      const double* __restrict__ U, double* __restrict__ X, double* __restrict__ Lam,
+                      double* __restrict__ cost, double* __restrict__ dHu, int* __restrict__ status)
+{
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double x[PDP_N], xn[PDP_N], th[PDP_R], u[PDP_M], tmp[1];
+  #pragma unroll
+  for (int i = 0; i < PDP_R; ++i) th[i] = theta[(size_t)b * theta_stride + i];
+  #pragma unroll
+  for (int i = 0; i < PDP_N; ++i) x[i] = x0[(size_t)b * PDP_N + i];
+  double J = 0.0;
+  double* Xb = X + (size_t)b * (H + 1) * PDP_N;
+  const double* Ub = U + (size_t)b * H * PDP_M;
+  #pragma unroll 1
+  for (int t = 0; t < H; ++t) {
+    #pragma unroll
+    for (int i = 0; i < PDP_M; ++i) u[i] = Ub[t * PDP_M + i];
+    #pragma unroll
+    for (int i = 0; i < PDP_N; ++i) Xb[t * PDP_N + i] = x[i];
+    pdp_f_path_cost(x, u, th, tmp);
+    J += tmp[0];
+    pdp_f_dyn(x, u, th, xn);
+    #pragma unroll
+    for (int i = 0; i < PDP_N; ++i) x[i] = xn[i];
+  }
+  #pragma unroll
+  for (int i = 0; i < PDP_N; ++i) Xb[H * PDP_N + i] = x[i];
+  pdp_f_final_cost(x, th, tmp);
+  J += tmp[0];
+  if (cost) cost[b] = J;
+  bool bad = !isfinite(J);
+  if (Lam != nullptr) {
+    double lam[PDP_N], ln[PDP_N], gu[PDP_M];
+    double* Lb = Lam + (size_t)b * H * PDP_N;
+    pdp_f_dhx(x, th, lam);
+    #pragma unroll 1
+    for (int t = H - 1; t >= 0; --t) {
+      #pragma unroll
+      for (int i = 0; i < PDP_N; ++i) Lb[t * PDP_N + i] = lam[i];
+      #pragma unroll
+      for (int i = 0; i < PDP_N; ++i) x[i] = Xb[t * PDP_N + i];
+      #pragma unroll
+      for (int i = 0; i < PDP_M; ++i) u[i] = Ub[t * PDP_M + i];
+      if (dHu != nullptr) {
+        pdp_f_dHu(x, u, lam, th, gu);
+        #pragma unroll
+        for (int i = 0; i < PDP_M; ++i) dHu[((size_t)b * H + t) * PDP_M + i] = gu[i];
+      }
+      if (t > 0) {
+        pdp_f_dHx(x, u, lam, th, ln);
+        #pragma unroll
+        for (int i = 0; i < PDP_N; ++i) lam[i] = ln[i];
+      }
+    }
+  }
+  if (status && bad) atomicOr(&status[b], 1);
+}
+
+// =====================================================================================================
+// Kernel 2: dense auxiliary-system matrices (legacy getAuxSys API, PDP.py:272-314); one thread per (b, t).
+//   out layout per (b,t): [F n*n | G n*m | E n*r | Hxx | Hxu | Hxe | Hux | Huu | Hue], each row-major.
+//   term layout per b   : [hxx n*n | hxe n*r]
+// =====================================================================================================
+extern "C" __global__ void __launch_bounds__(128)
+pdp_k_aux_eval(int B, int H, const double* __restrict__ X, const double* __restrict__ U, const double* __restrict__ Lam,
+               const double* __restrict__ theta, int theta_stride, double* __restrict__ out, double* __restrict__ term)
+{
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * (H + 1)) return;
+  const int b = idx / (H + 1), t = idx - b * (H + 1);
+  const double* th = theta + (size_t)b * theta_stride;
+  if (t == H) {
+    if (term) pdp_f_terminal(X + ((size_t)b * (H + 1) + H) * PDP_N, th, term + (size_t)b * (PDP_N * PDP_N + PDP_N * PDP_R));
+    return;
+  }
+  pdp_f_aux_dense(X + ((size_t)b * (H + 1) + t) * PDP_N, U + ((size_t)b * H + t) * PDP_M, Lam + ((size_t)b * H + t) * PDP_N, th,
+                  out + ((size_t)b * H + t) * PDP_NDENSE);
+}
+
+// =====================================================================================================
+// Kernel 3: fused getAuxSys + LQR.lqrSolver (PDP.py:272-314 + 446-615), ONE WARP PER TRAJECTORY.
+//   Backward Riccati sweep in the stacked form (see DESIGN.md): lane j < NS owns row j of the stack
+//   Y = [P ; . ; W^T]  (rows 0..n-1: P, rows n+m..: columns of W).  Per step
+//       Z      = P [F|G|E] (+ W on the E block)              (structural non-zeros only)
+//       Q      = Hstack + Z^T [F|G]                           (n+m+r) x (n+m)
+//       K|k    = -Quu^{-1} [Qux|Que]   (every lane solves for the column it owns; LDL^T in registers)
+//       Y     <- Q(:,0:n) + Q(:,n:n+m) K
+//   The gains (K_t|k_t) are spilled to HBM and consumed by the forward pass
+//       U_t = K_t X_t + k_t,  X_{t+1} = F_t X_t + G_t U_t + E_t   ->  dX/dtheta, dU/dtheta.
+//   The auxiliary matrices are evaluated in chunks of PDP_CH steps with lanes = time steps.
+// =====================================================================================================
+extern "C" __global__ void __launch_bounds__(PDP_WPB * 32)
+pdp_k_aux_lqr(int B, int H, const double* __restrict__ X, const double* __restrict__ U, const double* __restrict__ Lam,
+              const double* __restrict__ theta, int theta_stride, const double* __restrict__ X0a, int x0a_stride,
+              double* __restrict__ dX, double* __restrict__ dU, double* __restrict__ gains,
+              const double* __restrict__ Xref, const double* __restrict__ Uref, double* __restrict__ loss_dp,
+              int* __restrict__ status)
+{
+  extern __shared__ __align__(16) double pdp_smem[];
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * PDP_WPB + (threadIdx.x >> 5);
+  if (b >= B) return;
+  double* auxc = pdp_smem + (size_t)(threadIdx.x >> 5) * PDP_WARP_DOUBLES;   // [CH][AUXLD]
+  double* Hd = auxc + PDP_OFF_HD;                                            // dense Hamiltonian stack (+1 dummy)
+  double* ZT = auxc + PDP_OFF_ZT;                                            // Z^T staging / output staging
+  double* KS = auxc + PDP_OFF_KS;                                            // K (m x n)
+  double* QUU = auxc + PDP_OFF_QUU;                                          // m x m
+  double* TH = auxc + PDP_OFF_TH;                                            // theta
+  double* DLC = auxc + PDP_OFF_DL;                                           // [CH][n+m] (x - xref | u - uref) per chunk step
+  double* OUT = ZT;
+  double* TB = auxc;                                                         // terminal buffer aliases the chunk buffer
+  const int lrow = lane < PDP_NS ? lane : 0;
+  const int gslot = lane < PDP_N ? lane : ((lane >= PDP_NM && lane < PDP_NS) ? lane - PDP_M : -1);
+  const double* Xb = X + (size_t)b * (H + 1) * PDP_N;
+  const double* Ub = U + (size_t)b * H * PDP_M;
+  const double* Lb = Lam + (size_t)b * H * PDP_N;
+  bool bad = false;
+@@TABLOAD@@
+  for (int i = lane; i < PDP_HD_SIZE; i += 32) Hd[i] = 0.0;
+  if (lane < PDP_R) TH[lane] = theta[(size_t)b * theta_stride + lane];
+  __syncwarp();
+  {
+@@HINIT@@
+  }
+  // ---- terminal condition P = hxx(x_H), W = hxe(x_H)  (PDP.py:561-562)
+  if (lane == 0) pdp_f_terminal(Xb + (size_t)H * PDP_N, TH, TB);
+  __syncwarp();
+  @@YDECL@@
+  {
+@@TERM_INIT@@
+  }
+  __syncwarp();
+  // ---- backward sweep
+  #pragma unroll 1
+  for (int tc = ((H - 1) / PDP_CH) * PDP_CH; tc >= 0; tc -= PDP_CH) {
+    {
+      const int te = tc + lane;
+      if (lane < PDP_CH && te < H)
+        pdp_f_aux_slots(Xb + (size_t)te * PDP_N, Ub + (size_t)te * PDP_M, Lb + (size_t)te * PDP_N, TH, auxc + lane * PDP_AUXLD);
+    }
+    __syncwarp();
+    const int thi = (tc + PDP_CH < H ? tc + PDP_CH : H) - 1;
+    #pragma unroll 1
+    for (int t = thi; t >= tc; --t) {
+      const double* ar = auxc + (t - tc) * PDP_AUXLD;
+@@SCATTER@@
+      __syncwarp();
+@@BACKWARD_STEP@@
+      __syncwarp();
+    }
+  }
+  if (status && bad) { if (lane == 0) atomicOr(&status[b], 2); }
+  // ---- forward pass of the auxiliary system: lane n+c owns column c of X_t (n x r)
+  const int col = (lane >= PDP_N && lane < PDP_N + PDP_R) ? lane - PDP_N : -1;
+  const int fslot = lane < PDP_N + PDP_R ? lane : -1;
+  @@XDECL@@
+  {
+@@XINIT@@
+  }
+  double* dXb = dX ? dX + (size_t)b * (H + 1) * PDP_N * PDP_R : nullptr;
+  double* dUb = dU ? dU + (size_t)b * H * PDP_M * PDP_R : nullptr;
+  __syncwarp();
+  if (dXb) {
+    if (col >= 0) {
+@@X0STAGE@@
+    }
+    __syncwarp();
+    for (int k = lane; k < PDP_N * PDP_R; k += 32) dXb[k] = OUT[k];
+    __syncwarp();
+  }
+  bool badx = false;
+  const bool fused = (loss_dp != nullptr) && (Xref != nullptr);
+  const double* Xr = fused ? Xref + (size_t)b * (H + 1) * PDP_N : nullptr;
+  const double* Ur = (fused && Uref != nullptr) ? Uref + (size_t)b * H * PDP_M : nullptr;
+  double dpacc = 0.0, lossacc = 0.0;
+  #pragma unroll 1
+  for (int tc = 0; tc < H; tc += PDP_CH) {
+    {
+      const int te = tc + lane;
+      if (lane < PDP_CH && te < H) {
+        pdp_f_dyn_slots(Xb + (size_t)te * PDP_N, Ub + (size_t)te * PDP_M, TH, auxc + lane * PDP_AUXLD);
+        if (fused) {
+          // loss / chain rule of the IRL scripts (reference Examples/IRL/quadrotor/uav_PDP.py:67-75)
+          #pragma unroll
+          for (int i = 0; i < PDP_N; ++i) {
+            const double d = Xb[(size_t)te * PDP_N + i] - Xr[(size_t)te * PDP_N + i];
+            DLC[lane * PDP_NM + i] = d; lossacc = fma(d, d, lossacc);
+          }
+          #pragma unroll
+          for (int i = 0; i < PDP_M; ++i) {
+            const double d = Ur ? Ub[(size_t)te * PDP_M + i] - Ur[(size_t)te * PDP_M + i] : 0.0;
+            DLC[lane * PDP_NM + PDP_N + i] = d; lossacc = fma(d, d, lossacc);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    const int tend = tc + PDP_CH < H ? tc + PDP_CH : H;
+    #pragma unroll 1
+    for (int t = tc; t < tend; ++t) {
+      const double* ar = auxc + (t - tc) * PDP_AUXLD;
+      @@GDECL@@
+      if (fslot >= 0) {
+        const double* gp = gains + ((size_t)b * H + t) * PDP_GREC + fslot * PDP_M;
+@@GLOAD@@
+      }
+      if (lane < PDP_N) {
+@@KS_STORE@@
+      }
+      __syncwarp();
+@@FORWARD_STEP@@
+      if (fused) {
+        const double* dl = DLC + (t - tc) * PDP_NM;
+@@DPACC@@
+      }
+      if (col >= 0) {
+@@STAGE@@
+      }
+      __syncwarp();
+      if (dXb) for (int k = lane; k < PDP_N * PDP_R; k += 32) dXb[(size_t)(t + 1) * PDP_N * PDP_R + k] = OUT[k];
+      if (dUb) for (int k = lane; k < PDP_M * PDP_R; k += 32) dUb[(size_t)t * PDP_M * PDP_R + k] = OUT[PDP_N * PDP_R + k];
+      __syncwarp();
+@@XCOPY@@
+    }
+  }
+  {
+    double chk = 0.0;
+@@XCHK@@
+    badx = !isfinite(chk);
+    if (status && col >= 0 && badx) atomicOr(&status[b], 1);
+  }
+  if (fused) {
+    // terminal term of the chain rule and of the loss
+    #pragma unroll
+    for (int i = 0; i < PDP_N; ++i) {
+      const double d = Xb[(size_t)H * PDP_N + i] - Xr[(size_t)H * PDP_N + i];
+      if (lane == 0) lossacc = fma(d, d, lossacc);
+      DLC[i] = d;
+    }
+    __syncwarp();
+    {
+      const double* dl = DLC;
+@@DPTERM@@
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lossacc += __shfl_xor_sync(0xffffffffu, lossacc, o);
+    if (lane == 0) loss_dp[(size_t)b * (PDP_R + 1)] = lossacc;
+    if (col >= 0) loss_dp[(size_t)b * (PDP_R + 1) + 1 + col] = dpacc;
+  }
+}
+
+// =====================================================================================================
+// Host-side launchers (C ABI of the module; bound by csrc/pdp_b200.cpp through dlopen)
+// =====================================================================================================
+extern "C" void pdpmod_info(int* out) {
+  out[0] = 1;            // kind: oc
+  out[1] = PDP_N; out[2] = PDP_M; out[3] = PDP_R; out[4] = PDP_NVAR; out[5] = PDP_NVAR_S;
+  out[6] = PDP_GREC; out[7] = PDP_NDENSE; out[8] = PDP_CH; out[9] = PDP_WPB; out[10] = PDP_WARP_DOUBLES;
+}
+
+extern "C" int pdpmod_rollout_costate(int B, int H, const double* x0, const double* theta, int theta_stride, const double* U,
+                                      double* X, double* Lam, double* cost, double* dHu, int* status, cudaStream_t st) {
+  if (B <= 0) return 0;
+  pdp_k_rollout_costate<<<(B + 127) / 128, 128, 0, st>>>(B, H, x0, theta, theta_stride, U, X, Lam, cost, dHu, status);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int pdpmod_aux_eval(int B, int H, const double* X, const double* U, const double* Lam, const double* theta,
+                               int theta_stride, double* out, double* term, cudaStream_t st) {
+  if (B <= 0) return 0;
+  const int total = B * (H + 1);
+  pdp_k_aux_eval<<<(total + 127) / 128, 128, 0, st>>>(B, H, X, U, Lam, theta, theta_stride, out, term);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int pdpmod_aux_lqr(int B, int H, const double* X, const double* U, const double* Lam, const double* theta,
+                              int theta_stride, const double* X0a, int x0a_stride, double* dX, double* dU, double* gains,
+                              const double* Xref, const double* Uref, double* loss_dp, int* status, cudaStream_t st) {
+  if (B <= 0) return 0;
+  static bool configured = false;
+  const size_t smem = (size_t)PDP_WPB * PDP_WARP_DOUBLES * sizeof(double);
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(pdp_k_aux_lqr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  pdp_k_aux_lqr<<<(B + PDP_WPB - 1) / PDP_WPB, PDP_WPB * 32, smem, st>>>(B, H, X, U, Lam, theta, theta_stride, X0a, x0a_stride,
+                                                                         dX, dU, gains, Xref, Uref, loss_dp, status);
+  return (int)cudaGetLastError();
+}
+'''

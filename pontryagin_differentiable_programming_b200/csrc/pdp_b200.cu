@@ -1,0 +1,224 @@
+// libpdp_b200.so -- C ABI of the B200 PDP engine (see include/pdp_b200.h).
+// Thin, allocation-free dispatch layer: a "system" is a generated CUDA module (one .so per symbolic
+// optimal-control / sysid / planning system, produced by codegen.py + nvcc) opened with dlopen; the
+// kernels themselves live in that module so they are fully specialised on (n, m, r) and on the
+// sparsity pattern of the system's derivatives.
+#include "pdp_b200.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+using fn_info = void (*)(int*);
+using fn_rollout = int (*)(int, int, const double*, const double*, int, const double*, double*, double*, double*, double*, int*,
+                           cudaStream_t);
+using fn_aux_eval = int (*)(int, int, const double*, const double*, const double*, const double*, int, double*, double*,
+                            cudaStream_t);
+using fn_aux_lqr = int (*)(int, int, const double*, const double*, const double*, const double*, int, const double*, int,
+                           double*, double*, double*, const double*, const double*, double*, int*, cudaStream_t);
+using fn_sens = int (*)(int, int, const double*, const double*, int, const double*, const double*, double*, double*, double*,
+                        double*, double*, int*, cudaStream_t);
+
+inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+}  // namespace
+
+struct pdp_system {
+  void* handle = nullptr;
+  int info[16] = {0};
+  fn_rollout rollout = nullptr;
+  fn_aux_eval aux_eval = nullptr;
+  fn_aux_lqr aux_lqr = nullptr;
+  fn_sens sens = nullptr;
+  int kind() const { return info[0]; }
+  int n() const { return info[1]; }
+  int m() const { return info[2]; }
+  int r() const { return info[3]; }
+  int grec() const { return info[6]; }
+};
+
+extern "C" {
+
+const char* pdp_last_error(void) { return g_err; }
+const char* pdp_version(void) { return "pdp_b200 0.1 (sm_100a)"; }
+
+int pdp_load_system(const char* module_path, pdp_system_t** out) {
+  if (!module_path || !out) return fail(PDP_ERR_ARG, "pdp_load_system: null argument");
+  void* h = dlopen(module_path, RTLD_NOW | RTLD_LOCAL);
+  if (!h) return fail(PDP_ERR_LOAD, "pdp_load_system: dlopen(%s) failed: %s", module_path, dlerror());
+  auto info = reinterpret_cast<fn_info>(dlsym(h, "pdpmod_info"));
+  if (!info) {
+    dlclose(h);
+    return fail(PDP_ERR_LOAD, "pdp_load_system: %s is not a PDP system module (no pdpmod_info)", module_path);
+  }
+  pdp_system* s = new (std::nothrow) pdp_system();
+  if (!s) {
+    dlclose(h);
+    return fail(PDP_ERR_LOAD, "pdp_load_system: out of host memory");
+  }
+  s->handle = h;
+  info(s->info);
+  s->rollout = reinterpret_cast<fn_rollout>(dlsym(h, "pdpmod_rollout_costate"));
+  s->aux_eval = reinterpret_cast<fn_aux_eval>(dlsym(h, "pdpmod_aux_eval"));
+  s->aux_lqr = reinterpret_cast<fn_aux_lqr>(dlsym(h, "pdpmod_aux_lqr"));
+  s->sens = reinterpret_cast<fn_sens>(dlsym(h, "pdpmod_sens_fwd"));
+  *out = s;
+  return PDP_OK;
+}
+
+void pdp_free_system(pdp_system_t* sys) {
+  if (!sys) return;
+  if (sys->handle) dlclose(sys->handle);
+  delete sys;
+}
+
+int pdp_system_dims(const pdp_system_t* sys, int* dims) {
+  if (!sys || !dims) return fail(PDP_ERR_ARG, "pdp_system_dims: null argument");
+  dims[0] = sys->kind(); dims[1] = sys->n(); dims[2] = sys->m(); dims[3] = sys->r();
+  return PDP_OK;
+}
+
+size_t pdp_workspace_bytes(const pdp_system_t* sys, int op, int B, int H) {
+  if (!sys || B <= 0 || H <= 0) return 0;
+  const size_t n = sys->n(), m = sys->m(), r = sys->r();
+  const size_t gains = align256(size_t(B) * H * sys->grec() * sizeof(double));
+  switch (op) {
+    case PDP_OP_AUX_LQR:
+    case PDP_OP_SWEEP:
+      return gains;
+    case PDP_OP_SWEEP_HOST: {
+      size_t tot = gains;
+      tot += align256(size_t(B) * n * 8);            // x0
+      tot += align256(size_t(B) * r * 8);            // theta
+      tot += align256(size_t(B) * H * m * 8);        // U
+      tot += 2 * align256(size_t(B) * (H + 1) * n * 8);  // X, Xref
+      tot += align256(size_t(B) * H * n * 8);        // Lam
+      tot += align256(size_t(B) * H * m * 8);        // Uref
+      tot += align256(size_t(B) * 8);                // cost
+      tot += align256(size_t(B) * (r + 1) * 8);      // loss_dp
+      tot += align256(size_t(B) * (H + 1) * n * r * 8);  // dX
+      tot += align256(size_t(B) * H * m * r * 8);    // dU
+      return tot;
+    }
+    default:
+      return 0;
+  }
+}
+
+int pdp_rollout_costate(pdp_system_t* sys, int B, int H, const double* x0, const double* theta, int theta_stride,
+                        const double* U, double* X, double* Lam, double* cost, double* dHu, int* status,
+                        pdp_stream_t stream) {
+  if (!sys || !sys->rollout) return fail(PDP_ERR_UNSUPPORTED, "pdp_rollout_costate: module has no rollout kernel");
+  if (B < 0 || H < 1 || !x0 || !theta || !U || !X) return fail(PDP_ERR_ARG, "pdp_rollout_costate: bad argument");
+  if (dHu && !Lam) return fail(PDP_ERR_ARG, "pdp_rollout_costate: dHu needs Lam");
+  int e = sys->rollout(B, H, x0, theta, theta_stride, U, X, Lam, cost, dHu, status, (cudaStream_t)stream);
+  if (e) return fail(PDP_ERR_CUDA, "pdp_rollout_costate: CUDA error %d (%s)", e, cudaGetErrorString((cudaError_t)e));
+  return PDP_OK;
+}
+
+int pdp_aux_lqr(pdp_system_t* sys, int B, int H, const double* X, const double* U, const double* Lam,
+                const double* theta, int theta_stride, const double* X0aux, int x0aux_stride,
+                double* dXdtheta, double* dUdtheta, const double* Xref, const double* Uref, double* loss_dp,
+                void* workspace, size_t ws_bytes, int* status, pdp_stream_t stream) {
+  if (!sys || !sys->aux_lqr) return fail(PDP_ERR_UNSUPPORTED, "pdp_aux_lqr: module has no aux-LQR kernel");
+  if (B < 0 || H < 1 || !X || !U || !Lam || !theta) return fail(PDP_ERR_ARG, "pdp_aux_lqr: bad argument");
+  if (loss_dp && !Xref) return fail(PDP_ERR_ARG, "pdp_aux_lqr: loss_dp needs Xref");
+  if (ws_bytes < pdp_workspace_bytes(sys, PDP_OP_AUX_LQR, B, H) || (B > 0 && !workspace))
+    return fail(PDP_ERR_WORKSPACE, "pdp_aux_lqr: workspace too small (%zu < %zu)", ws_bytes,
+                pdp_workspace_bytes(sys, PDP_OP_AUX_LQR, B, H));
+  int e = sys->aux_lqr(B, H, X, U, Lam, theta, theta_stride, X0aux, x0aux_stride, dXdtheta, dUdtheta,
+                       reinterpret_cast<double*>(workspace), Xref, Uref, loss_dp, status, (cudaStream_t)stream);
+  if (e) return fail(PDP_ERR_CUDA, "pdp_aux_lqr: CUDA error %d (%s)", e, cudaGetErrorString((cudaError_t)e));
+  return PDP_OK;
+}
+
+int pdp_sweep(pdp_system_t* sys, int B, int H, const double* x0, const double* theta, int theta_stride,
+              const double* U, double* X, double* Lam, double* cost, double* dXdtheta, double* dUdtheta,
+              const double* Xref, const double* Uref, double* loss_dp, void* workspace, size_t ws_bytes,
+              int* status, pdp_stream_t stream) {
+  if (!Lam) return fail(PDP_ERR_ARG, "pdp_sweep: Lam buffer required");
+  int e = pdp_rollout_costate(sys, B, H, x0, theta, theta_stride, U, X, Lam, cost, nullptr, status, stream);
+  if (e) return e;
+  return pdp_aux_lqr(sys, B, H, X, U, Lam, theta, theta_stride, nullptr, 0, dXdtheta, dUdtheta, Xref, Uref, loss_dp,
+                     workspace, ws_bytes, status, stream);
+}
+
+int pdp_aux_eval(pdp_system_t* sys, int B, int H, const double* X, const double* U, const double* Lam,
+                 const double* theta, int theta_stride, double* aux, double* term, pdp_stream_t stream) {
+  if (!sys || !sys->aux_eval) return fail(PDP_ERR_UNSUPPORTED, "pdp_aux_eval: module has no aux-eval kernel");
+  if (B < 0 || H < 1 || !X || !U || !Lam || !theta || !aux) return fail(PDP_ERR_ARG, "pdp_aux_eval: bad argument");
+  int e = sys->aux_eval(B, H, X, U, Lam, theta, theta_stride, aux, term, (cudaStream_t)stream);
+  if (e) return fail(PDP_ERR_CUDA, "pdp_aux_eval: CUDA error %d (%s)", e, cudaGetErrorString((cudaError_t)e));
+  return PDP_OK;
+}
+
+int pdp_sens_fwd(pdp_system_t* sys, int B, int H, const double* x0, const double* theta, int theta_stride,
+                 const double* inputs, const double* Xobs, double* X, double* Uout, double* dX, double* dU,
+                 double* loss_dp, int* status, pdp_stream_t stream) {
+  if (!sys || !sys->sens) return fail(PDP_ERR_UNSUPPORTED, "pdp_sens_fwd: module has no forward-sensitivity kernel");
+  if (B < 0 || H < 1 || !x0 || !theta) return fail(PDP_ERR_ARG, "pdp_sens_fwd: bad argument");
+  int e = sys->sens(B, H, x0, theta, theta_stride, inputs, Xobs, X, Uout, dX, dU, loss_dp, status, (cudaStream_t)stream);
+  if (e) return fail(PDP_ERR_CUDA, "pdp_sens_fwd: CUDA error %d (%s)", e, cudaGetErrorString((cudaError_t)e));
+  return PDP_OK;
+}
+
+int pdp_sweep_host(pdp_system_t* sys, int B, int H, const double* x0_host, const double* theta_host,
+                   int theta_stride, const double* U_host, const double* Xref_host, const double* Uref_host,
+                   double* loss_dp_host, double* cost_host, int keep_dtraj, void* workspace, size_t ws_bytes,
+                   pdp_stream_t stream) {
+  if (!sys || !sys->aux_lqr || !sys->rollout) return fail(PDP_ERR_UNSUPPORTED, "pdp_sweep_host: not an OC module");
+  if (B < 1 || H < 1 || !x0_host || !theta_host || !U_host || !Xref_host || !loss_dp_host)
+    return fail(PDP_ERR_ARG, "pdp_sweep_host: bad argument");
+  if (!workspace || ws_bytes < pdp_workspace_bytes(sys, PDP_OP_SWEEP_HOST, B, H))
+    return fail(PDP_ERR_WORKSPACE, "pdp_sweep_host: workspace too small");
+  const size_t n = sys->n(), m = sys->m(), r = sys->r();
+  cudaStream_t st = (cudaStream_t)stream;
+  char* p = reinterpret_cast<char*>(workspace);
+  auto take = [&](size_t bytes) { char* q = p; p += align256(bytes); return reinterpret_cast<double*>(q); };
+  double* gains = take(size_t(B) * H * sys->grec() * 8);
+  double* d_x0 = take(size_t(B) * n * 8);
+  double* d_th = take(size_t(B) * r * 8);
+  double* d_U = take(size_t(B) * H * m * 8);
+  double* d_X = take(size_t(B) * (H + 1) * n * 8);
+  double* d_Xr = take(size_t(B) * (H + 1) * n * 8);
+  double* d_L = take(size_t(B) * H * n * 8);
+  double* d_Ur = take(size_t(B) * H * m * 8);
+  double* d_cost = take(size_t(B) * 8);
+  double* d_ldp = take(size_t(B) * (r + 1) * 8);
+  double* d_dX = take(size_t(B) * (H + 1) * n * r * 8);
+  double* d_dU = take(size_t(B) * H * m * r * 8);
+  const size_t thn = theta_stride ? size_t(B) * r : r;
+  cudaError_t ce;
+#define PDP_CK(x) if ((ce = (x)) != cudaSuccess) return fail(PDP_ERR_CUDA, "pdp_sweep_host: %s", cudaGetErrorString(ce))
+  PDP_CK(cudaMemcpyAsync(d_x0, x0_host, size_t(B) * n * 8, cudaMemcpyHostToDevice, st));
+  PDP_CK(cudaMemcpyAsync(d_th, theta_host, thn * 8, cudaMemcpyHostToDevice, st));
+  PDP_CK(cudaMemcpyAsync(d_U, U_host, size_t(B) * H * m * 8, cudaMemcpyHostToDevice, st));
+  PDP_CK(cudaMemcpyAsync(d_Xr, Xref_host, size_t(B) * (H + 1) * n * 8, cudaMemcpyHostToDevice, st));
+  if (Uref_host) PDP_CK(cudaMemcpyAsync(d_Ur, Uref_host, size_t(B) * H * m * 8, cudaMemcpyHostToDevice, st));
+  int e = pdp_sweep(sys, B, H, d_x0, d_th, theta_stride, d_U, d_X, d_L, d_cost, keep_dtraj ? d_dX : nullptr,
+                    keep_dtraj ? d_dU : nullptr, d_Xr, Uref_host ? d_Ur : nullptr, d_ldp, gains,
+                    size_t(B) * H * sys->grec() * 8 + 256, nullptr, stream);
+  if (e) return e;
+  PDP_CK(cudaMemcpyAsync(loss_dp_host, d_ldp, size_t(B) * (r + 1) * 8, cudaMemcpyDeviceToHost, st));
+  if (cost_host) PDP_CK(cudaMemcpyAsync(cost_host, d_cost, size_t(B) * 8, cudaMemcpyDeviceToHost, st));
+#undef PDP_CK
+  return PDP_OK;
+}
+
+}  // extern "C"

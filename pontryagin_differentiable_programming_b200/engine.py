@@ -1,0 +1,195 @@
+"""Batched entry points on torch CUDA float64 tensors (the additive API of SURVEY 8(b)).
+
+PyTorch is plumbing only (device memory, streams); all arithmetic runs in the generated
+sm_100a kernels behind the C ABI.  Every method raises ``PDPBackendError`` when no CUDA device
+is available -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import backend, build, codegen
+from .backend import PDPBackendError
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise PDPBackendError(
+            "the PDP B200 engine needs a CUDA device: hot-path methods (rollout / costate / aux-LQR / "
+            "sensitivity sweeps) run only as sm_100a kernels and have no CPU fallback")
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t, shape, name, device):
+    if t.dtype != torch.float64 or not t.is_cuda or not t.is_contiguous():
+        raise ValueError("%s must be a contiguous CUDA float64 tensor" % name)
+    if tuple(t.shape) != tuple(shape):
+        raise ValueError("%s has shape %s, expected %s" % (name, tuple(t.shape), tuple(shape)))
+    if t.device != device:
+        raise ValueError("%s is on %s, expected %s" % (name, t.device, device))
+
+
+class OCSystem:
+    """Compiled optimal-control system: rollout/costate, fused getAuxSys+lqrSolver, dense aux eval."""
+
+    def __init__(self, state, control, auxvar, dyn, path_cost, final_cost, chunk=8, warps_per_block=4, verbose=False):
+        self.src = codegen.OCModuleSource(state, control, auxvar, dyn, path_cost, final_cost, chunk, warps_per_block)
+        self.n, self.m, self.r = self.src.n, self.src.m, self.src.r
+        self.module_path = build.compile_module(self.src.source(), self.src.key(), verbose=verbose)
+        self._handle = None
+        self._ws = {}
+
+    # the handle is created lazily so that systems can be *built* on a CPU-only box
+    @property
+    def handle(self):
+        if self._handle is None:
+            self._handle = backend.SystemHandle(self.module_path)
+        return self._handle
+
+    def _theta(self, theta, B, device):
+        if theta.dim() == 1:
+            theta = theta.unsqueeze(0)
+        if theta.shape[0] == 1:
+            _chk(theta, (1, self.r), "theta", device)
+            return theta, 0
+        _chk(theta, (B, self.r), "theta", device)
+        return theta, self.r
+
+    def _workspace(self, op, B, H, device):
+        need = self.handle.workspace_bytes(op, B, H)
+        key = (op, device)
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(max(need, 256), dtype=torch.uint8, device=device)
+            self._ws[key] = ws
+        return ws, need
+
+    def rollout_costate(self, x0, theta, U, want_costate=True, want_dHu=False, status=None, out=None):
+        """x0[B,n], theta[B|1,r], U[B,H,m] -> X[B,H+1,n], Lam[B,H,n] (Lam[:,t] = lambda_{t+1}), cost[B][, dHu[B,H,m]]."""
+        require_cuda()
+        dev = x0.device
+        B, H = U.shape[0], U.shape[1]
+        _chk(x0, (B, self.n), "x0", dev)
+        _chk(U, (B, H, self.m), "U", dev)
+        theta, ts = self._theta(theta, B, dev)
+        def buf(name, shape):
+            if out is not None and name in out:
+                return out[name]
+            return torch.empty(shape, dtype=torch.float64, device=dev)
+
+        X = buf("X", (B, H + 1, self.n))
+        Lam = buf("Lam", (B, H, self.n)) if (want_costate or want_dHu) else None
+        cost = buf("cost", (B,))
+        dHu = buf("dHu", (B, H, self.m)) if want_dHu else None
+        lib = self.handle.lib
+        st = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            backend.check(lib.pdp_rollout_costate(self.handle.ptr, B, H, _ptr(x0), _ptr(theta), ts, _ptr(U), _ptr(X),
+                                                  _ptr(Lam), _ptr(cost), _ptr(dHu), _ptr(status), st),
+                          "pdp_rollout_costate")
+        out = {"X": X, "Lam": Lam, "cost": cost}
+        if want_dHu:
+            out["dHu"] = dHu
+        return out
+
+    def aux_lqr(self, X, U, Lam, theta, X0aux=None, want_traj=True, Xref=None, Uref=None, status=None, out=None):
+        """Fused getAuxSys + lqrSolver: -> dX[B,H+1,n,r], dU[B,H,m,r] and/or loss_dp[B,r+1]."""
+        require_cuda()
+        dev = X.device
+        B, H = U.shape[0], U.shape[1]
+        _chk(X, (B, H + 1, self.n), "X", dev)
+        _chk(U, (B, H, self.m), "U", dev)
+        _chk(Lam, (B, H, self.n), "Lam", dev)
+        theta, ts = self._theta(theta, B, dev)
+        x0s = 0
+        if X0aux is not None:
+            if X0aux.dim() == 2:
+                X0aux = X0aux.unsqueeze(0)
+            x0s = 0 if X0aux.shape[0] == 1 else 1
+            _chk(X0aux, (B if x0s else 1, self.n, self.r), "X0aux", dev)
+        res = {}
+        dX = dU = None
+        if want_traj:
+            if out is not None:
+                dX, dU = out["dX"], out["dU"]
+            else:
+                dX = torch.empty((B, H + 1, self.n, self.r), dtype=torch.float64, device=dev)
+                dU = torch.empty((B, H, self.m, self.r), dtype=torch.float64, device=dev)
+            res["dX"], res["dU"] = dX, dU
+        ldp = None
+        if Xref is not None:
+            _chk(Xref, (B, H + 1, self.n), "Xref", dev)
+            if Uref is not None:
+                _chk(Uref, (B, H, self.m), "Uref", dev)
+            ldp = out["loss_dp"] if (out is not None and "loss_dp" in out) else \
+                torch.empty((B, self.r + 1), dtype=torch.float64, device=dev)
+            res["loss_dp"] = ldp
+        ws, need = self._workspace(backend.OP_AUX_LQR, B, H, dev)
+        lib = self.handle.lib
+        st = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            backend.check(lib.pdp_aux_lqr(self.handle.ptr, B, H, _ptr(X), _ptr(U), _ptr(Lam), _ptr(theta), ts,
+                                          _ptr(X0aux), x0s, _ptr(dX), _ptr(dU), _ptr(Xref), _ptr(Uref), _ptr(ldp),
+                                          _ptr(ws), ws.numel(), _ptr(status), st), "pdp_aux_lqr")
+        return res
+
+    def sweep(self, x0, theta, U, Xref=None, Uref=None, want_traj=True, status=None, out=None):
+        """One PDP sweep (the BASELINE metric's unit): rollout + costate + fused aux-LQR."""
+        require_cuda()
+        dev = x0.device
+        B, H = U.shape[0], U.shape[1]
+        _chk(x0, (B, self.n), "x0", dev)
+        _chk(U, (B, H, self.m), "U", dev)
+        theta, ts = self._theta(theta, B, dev)
+
+        def buf(name, shape):
+            if out is not None and name in out:
+                return out[name]
+            return torch.empty(shape, dtype=torch.float64, device=dev)
+
+        X = buf("X", (B, H + 1, self.n))
+        Lam = buf("Lam", (B, H, self.n))
+        cost = buf("cost", (B,))
+        dX = buf("dX", (B, H + 1, self.n, self.r)) if want_traj else None
+        dU = buf("dU", (B, H, self.m, self.r)) if want_traj else None
+        ldp = buf("loss_dp", (B, self.r + 1)) if Xref is not None else None
+        ws, need = self._workspace(backend.OP_SWEEP, B, H, dev)
+        lib = self.handle.lib
+        st = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            backend.check(lib.pdp_sweep(self.handle.ptr, B, H, _ptr(x0), _ptr(theta), ts, _ptr(U), _ptr(X), _ptr(Lam),
+                                        _ptr(cost), _ptr(dX), _ptr(dU), _ptr(Xref), _ptr(Uref), _ptr(ldp), _ptr(ws),
+                                        ws.numel(), _ptr(status), st), "pdp_sweep")
+        res = {"X": X, "Lam": Lam, "cost": cost}
+        if want_traj:
+            res["dX"], res["dU"] = dX, dU
+        if ldp is not None:
+            res["loss_dp"] = ldp
+        return res
+
+    def aux_eval(self, X, U, Lam, theta):
+        """Dense auxiliary matrices (legacy getAuxSys return value) as a dict of [B,H,...] tensors."""
+        require_cuda()
+        dev = X.device
+        B, H = U.shape[0], U.shape[1]
+        n, m, r = self.n, self.m, self.r
+        theta, ts = self._theta(theta, B, dev)
+        nd = 2 * (n * n + n * m + n * r) + m * n + m * m + m * r
+        aux = torch.empty((B, H, nd), dtype=torch.float64, device=dev)
+        term = torch.empty((B, n * n + n * r), dtype=torch.float64, device=dev)
+        lib = self.handle.lib
+        st = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            backend.check(lib.pdp_aux_eval(self.handle.ptr, B, H, _ptr(X), _ptr(U), _ptr(Lam), _ptr(theta), ts,
+                                           _ptr(aux), _ptr(term), st), "pdp_aux_eval")
+        out, o = {}, 0
+        for name, (a, b_) in (("dynF", (n, n)), ("dynG", (n, m)), ("dynE", (n, r)), ("Hxx", (n, n)), ("Hxu", (n, m)),
+                              ("Hxe", (n, r)), ("Hux", (m, n)), ("Huu", (m, m)), ("Hue", (m, r))):
+            out[name] = aux[:, :, o:o + a * b_].reshape(B, H, a, b_)
+            o += a * b_
+        out["hxx"] = term[:, :n * n].reshape(B, n, n)
+        out["hxe"] = term[:, n * n:].reshape(B, n, r)
+        return out

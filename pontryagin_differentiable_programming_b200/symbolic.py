@@ -95,6 +95,16 @@ def _isc(n: Node) -> bool:
     return n.op == "const"
 
 
+def _swap(a: Node, b: Node) -> bool:
+    """Canonical operand order of commutative ops: constants first, then creation order.  Constants
+    are shared between systems built in one process, so ordering them by uid would make the
+    generated source (and its cache key) depend on what else was built earlier."""
+    ca, cb = a.op == "const", b.op == "const"
+    if ca != cb:
+        return cb
+    return a.uid > b.uid
+
+
 def add(a: Node, b: Node) -> Node:
     if _isc(a) and _isc(b):
         return const(a.val + b.val)
@@ -106,7 +116,7 @@ def add(a: Node, b: Node) -> Node:
         return sub(a, b.args[0])
     if a.op == "neg":
         return sub(b, a.args[0])
-    if a.uid > b.uid:
+    if _swap(a, b):
         a, b = b, a
     return _mk("add", (a, b))
 
@@ -156,7 +166,7 @@ def mul(a: Node, b: Node) -> Node:
         return neg(mul(a.args[0], b))
     if b.op == "neg":
         return neg(mul(a, b.args[0]))
-    if a.uid > b.uid:
+    if _swap(a, b):
         a, b = b, a
     return _mk("mul", (a, b))
 
