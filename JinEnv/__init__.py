@@ -1,0 +1,1 @@
+"""Drop-in package: ``from JinEnv import JinEnv`` like the reference."""

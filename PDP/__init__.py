@@ -1,1 +1,1 @@
-"""placeholder -- filled in below"""
+"""Drop-in package: ``from PDP import PDP`` like the reference (Examples/IRL/quadrotor/uav_PDP.py:1)."""

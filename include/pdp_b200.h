@@ -29,7 +29,7 @@ typedef struct pdp_system pdp_system_t;
 typedef void* pdp_stream_t; /* cudaStream_t */
 
 enum { PDP_OK = 0, PDP_ERR_ARG = -1, PDP_ERR_LOAD = -2, PDP_ERR_CUDA = -3, PDP_ERR_WORKSPACE = -4, PDP_ERR_UNSUPPORTED = -5 };
-enum { PDP_KIND_OC = 1, PDP_KIND_SYSID = 2, PDP_KIND_CP = 3, PDP_KIND_LQR = 4 };
+enum { PDP_KIND_OC = 1, PDP_KIND_SYSID = 2, PDP_KIND_CP = 3, PDP_KIND_LQR = 4, PDP_KIND_FUNCTION = 5 };
 enum { PDP_OP_AUX_LQR = 1, PDP_OP_SWEEP = 2, PDP_OP_SWEEP_HOST = 3 };
 
 /* Load a generated system module (the product of OCSys.setDyn/setPathCost/setFinalCost + diffPMP,
@@ -63,6 +63,24 @@ int pdp_aux_lqr(pdp_system_t* sys, int B, int H, const double* X, const double* 
                 const double* theta, int theta_stride, const double* X0aux, int x0aux_stride,
                 double* dXdtheta, double* dUdtheta, const double* Xref, const double* Uref, double* loss_dp,
                 void* workspace, size_t ws_bytes, int* status, pdp_stream_t stream);
+
+/* LQR.lqrSolver on caller-supplied matrices (PDP/PDP.py:446-615) for kind PDP_KIND_LQR modules of size
+ * (n, m, r):  aux[B,H,NDENSE] in the per-step layout of pdp_aux_eval, term[B, n*n+n*r] = [hxx|hxe],
+ * X0aux as in pdp_aux_lqr -> Xaux[B,H+1,n,r], Uaux[B,H,m,r].  Hessian blocks must be symmetric
+ * (Hux is ignored and transpose(Hxu) used instead, exactly as the reference does). */
+int pdp_lqr_dense(pdp_system_t* sys, int B, int H, const double* aux, const double* term, const double* X0aux,
+                  int x0aux_stride, double* Xaux, double* Uaux, int forward_only, void* workspace, size_t ws_bytes,
+                  int* status, pdp_stream_t stream);
+/* forward_only != 0: skip the Riccati sweep and run only X+ = F X + G (K X + k) + E with gains the caller has
+ * written into `workspace` as [B,H,(n+r),m] records (rows 0..n-1 = columns of K, rows n.. = columns of k):
+ * ControlPlanning.integrateAuxSys (PDP/PDP.py:813-838, K = dUx, k = dUe, E = 0) and
+ * SysID.integrateAuxSys (PDP/PDP.py:1241-1259, gains = 0). */
+
+/* Evaluate a code-generated symbolic Function (kind 5 module) for B samples: inputs[k] -> [B|1, numel_k]
+ * (input_strides[k] = numel_k or 0 when shared), outputs[k] -> [B, rows_k*cols_k] row-major.  Replaces the
+ * per-step CasADi calls of ControlPlanning.getAuxSys / SysID.getAuxSys (PDP/PDP.py:788-811, 1225-1239). */
+int pdp_eval_function(pdp_system_t* sys, int B, const double* const* inputs, const int* input_strides,
+                      double* const* outputs, pdp_stream_t stream);
 
 /* One full PDP sweep = pdp_rollout_costate + pdp_aux_lqr on device buffers (the BASELINE metric's unit). */
 int pdp_sweep(pdp_system_t* sys, int B, int H, const double* x0, const double* theta, int theta_stride,

@@ -174,6 +174,7 @@ class OCModuleSource:
                  chunk: int = 8, warps_per_block: int = 4):
         self.x, self.u, self.th = state, control, auxvar
         self.n, self.m, self.r = state.numel(), control.numel(), auxvar.numel()
+        self.nth = self.r
         self.ns = self.n + self.m + self.r
         self.chunk = int(chunk)
         self.wpb = int(warps_per_block)
@@ -198,7 +199,12 @@ class OCModuleSource:
         self.dhx = S.jacobian(self.h, self.x).T
         self.ddhxx = S.jacobian(self.dhx, self.x)
         self.ddhxe = S.jacobian(self.dhx, self.th)
+        self._customise()
+        self.ns = self.n + self.m + self.r
         self._layout()
+
+    def _customise(self):
+        """Hook for variants that replace some auxiliary matrices (see NewtonModuleSource)."""
 
     # ---- slot layout ---------------------------------------------------------------------------
     def _layout(self):
@@ -449,14 +455,14 @@ class OCModuleSource:
         off_ks = off_zt + zt_size
         off_quu = off_ks + ks_size
         off_th = off_quu + _even(m * m)
-        off_dl = off_th + _even(r)
+        off_dl = off_th + _even(max(self.nth, 1))
         warp_doubles = _even(off_dl + self.chunk * nm)
         defs = {
             "N": n, "M": m, "R": r, "NS": ns, "NM": nm, "NVAR": self.nvar, "NVAR_S": self.nvar_s,
             "AUXLD": self.auxld, "CH": self.chunk, "WPB": self.wpb, "LDH": self.ldh, "LDZ": self.ldz,
             "LDK": self.ldk, "HD_SIZE": hd_size, "HD_DUMMY": ns * self.ldh,
             "OFF_HD": off_hd, "OFF_ZT": off_zt, "OFF_KS": off_ks, "OFF_QUU": off_quu, "OFF_TH": off_th, "OFF_DL": off_dl,
-            "WARP_DOUBLES": warp_doubles, "NHS": nhs, "KH": kh, "GREC": (n + r) * m,
+            "WARP_DOUBLES": warp_doubles, "NTH": self.nth, "NHS": nhs, "KH": kh, "GREC": (n + r) * m,
             "NDENSE": n * n + n * m + n * r + n * n + n * m + n * r + m * n + m * m + m * r,
         }
         header = ["// GENERATED by pontryagin_differentiable_programming_b200/codegen.py -- do not edit",
@@ -490,7 +496,6 @@ class OCModuleSource:
         xcopy = "\n".join("      x%d = n%d;" % (k, k) for k in range(n))
         x0stage = "\n".join("      OUT[%d + col] = x%d;" % (i * r, i) for i in range(n))
 
-        kernels = _OC_KERNELS_TEMPLATE
         rep = {
             "@@TABLOAD@@": tabload, "@@HINIT@@": hinit, "@@SCATTER@@": scatter, "@@YDECL@@": ydecl,
             "@@TERM_INIT@@": "\n".join(term_init), "@@BACKWARD_STEP@@": self._backward_step(),
@@ -502,9 +507,32 @@ class OCModuleSource:
             "@@DPTERM@@": "\n".join("      dpacc = fma(dl[%d], x%d, dpacc);" % (i, i) for i in range(n)),
             "@@XCHK@@": "\n".join("    chk += x%d;" % k for k in range(n)),
         }
+        rep.update(self._eval_macros())
+        kernels = self._kernel_text()
         for k, v in rep.items():
             kernels = kernels.replace(k, v)
-        return "\n".join(header) + "\n\n" + "\n".join(tables) + "\n\n" + self._device_functions() + "\n\n" + kernels
+        header.append("#define PDP_KIND %d" % self.kind_id)
+        return ("\n".join(header) + "\n\n" + "\n".join(tables + self._extra_tables()) + "\n\n" +
+                self._device_functions() + "\n\n" + kernels)
+
+    kind_id = 1
+
+    def _extra_tables(self):
+        return []
+
+    def _kernel_text(self):
+        return _K_ROLLOUT_AUXEVAL + _K_AUX_LQR + _K_LAUNCH_COMMON + _K_LAUNCH_LQR
+
+    def _eval_macros(self):
+        return {
+            "@@EVAL_TERM@@": "  if (lane == 0) pdp_f_terminal(Xb + (size_t)H * PDP_N, TH, TB);",
+            "@@EVAL_AUX_CHUNK@@": """    {
+      const int te = tc + lane;
+      if (lane < PDP_CH && te < H)
+        pdp_f_aux_slots(Xb + (size_t)te * PDP_N, Ub + (size_t)te * PDP_M, Lb + (size_t)te * PDP_N, TH, auxc + lane * PDP_AUXLD);
+    }""",
+            "@@EVAL_DYN@@": "        pdp_f_dyn_slots(Xb + (size_t)te * PDP_N, Ub + (size_t)te * PDP_M, TH, auxc + lane * PDP_AUXLD);",
+        }
 
     def _gload(self):
         m = self.m
@@ -517,7 +545,178 @@ class OCModuleSource:
         return hashlib.sha256(self.source().encode()).hexdigest()[:20]
 
 
-_OC_KERNELS_TEMPLATE = r'''
+
+class NewtonModuleSource(OCModuleSource):
+    """Newton / iLQR direction for the optimal-control problem itself (the batched ``ocSolver``).
+
+    The exact Newton step of  min_U J(U)  at a dynamically consistent (X, U, lambda) solves an LQ problem
+    with the same structure as the PDP auxiliary system with ONE column: E = 0, Hxe = 0, hxe = 0 and the
+    "Hue" column replaced by the gradient dH/du.  So the fused aux-LQR kernel is reused unchanged; its
+    forward pass returns (dx_t, du_t).  The module's parameter vector is [auxvar, s, mu]:
+    ``s`` scales the costate inside the Hessians (s = 1: exact Newton / DDP Hessians, s = 0: Gauss-Newton =
+    iLQR, always positive definite for convex costs) and ``mu`` is a Levenberg shift added to Huu."""
+
+    def _customise(self):
+        n, m = self.n, self.m
+        s_, mu = SX.sym("newton_s"), SX.sym("newton_mu")
+        lam_scaled = self.lam * s_
+        def scaled(M):
+            return S.substitute(M, self.lam, lam_scaled)
+        self.ddHxx = scaled(self.ddHxx)
+        self.ddHxu = scaled(self.ddHxu)
+        self.ddHux = scaled(self.ddHux)
+        self.ddHuu = scaled(self.ddHuu) + mu * SX.eye(m)
+        self.dfe = SX.zeros(n, 1)
+        self.ddHxe = SX.zeros(n, 1)
+        self.ddHue = self.dHu
+        self.ddhxe = SX.zeros(n, 1)
+        self.th = S.vertcat(self.th, s_, mu)
+        self.nth = self.th.numel()
+        self.r = 1
+
+
+class FunctionModuleSource:
+    """Any symbolic ``Function`` as a batched CUDA kernel (one thread per sample).
+
+    Used for the legacy ``getAuxSys`` return values of ControlPlanning / SysID (reference
+    PDP/PDP.py:788-811, 1225-1239) and for evaluating user-visible ``*_fn`` objects on device.
+    Inputs ``in_k[B or 1, numel_k]`` (stride 0 = shared), outputs ``out_k[B, rows*cols]`` row-major."""
+
+    kind_id = 5
+    MAX_IN, MAX_OUT = 6, 12
+
+    def __init__(self, fn: "S.Function"):
+        self.fn = fn
+        if fn.n_in() > self.MAX_IN or fn.n_out() > self.MAX_OUT:
+            raise ValueError("FunctionModuleSource: too many inputs / outputs")
+
+    def source(self) -> str:
+        fn = self.fn
+        ins, outs = fn.sx_in(), fn.sx_out()
+        leaf, loads = {}, []
+        used = {n.uid for o in outs for n in S.topo_order(o.elements()) if n.op == "sym"}
+        for k, m in enumerate(ins):
+            for q, e in enumerate(m.elements()):  # column-major element order of the input matrix
+                if e.uid in used:
+                    loads.append("  const double i%d_%d = p.in[%d][(size_t)b * p.in_stride[%d] + %d];" % (k, q, k, k, q))
+                    leaf[e.uid] = "i%d_%d" % (k, q)
+        flat, where = [], []
+        for k, o in enumerate(outs):
+            rows, cols = o.shape
+            for i in range(rows):
+                for j in range(cols):
+                    flat.append(o.at(i, j))
+                    where.append((k, i * cols + j, rows * cols))
+        lines, names = S.emit_c(flat, leaf)
+        stores = ["  p.out[%d][(size_t)b * %d + %d] = %s;" % (k, tot, off, nm) for (k, off, tot), nm in zip(where, names)]
+        return "\n".join([
+            "// GENERATED by pontryagin_differentiable_programming_b200/codegen.py (FunctionModuleSource)",
+            "#include <cuda_runtime.h>", "#include <math.h>",
+            "#define PDP_KIND 5", "#define PDP_NIN %d" % len(ins), "#define PDP_NOUT %d" % len(outs),
+            "struct pdp_fn_args { const double* in[%d]; int in_stride[%d]; double* out[%d]; };" % (self.MAX_IN, self.MAX_IN, self.MAX_OUT),
+            'extern "C" __global__ void __launch_bounds__(128) pdp_k_fn(int B, pdp_fn_args p) {',
+            "  const int b = blockIdx.x * blockDim.x + threadIdx.x;", "  if (b >= B) return;"] + loads + lines + stores + [
+            "}",
+            'extern "C" void pdpmod_info(int* out) { out[0] = PDP_KIND; out[1] = PDP_NIN; out[2] = PDP_NOUT; for (int i = 3; i < 11; ++i) out[i] = 0; }',
+            'extern "C" int pdpmod_fn(int B, const double* const* ins, const int* strides, double* const* outs, cudaStream_t st) {',
+            "  if (B <= 0) return 0;", "  pdp_fn_args p;",
+            "  for (int i = 0; i < PDP_NIN; ++i) { p.in[i] = ins[i]; p.in_stride[i] = strides[i]; }",
+            "  for (int i = 0; i < PDP_NOUT; ++i) p.out[i] = outs[i];",
+            "  pdp_k_fn<<<(B + 127) / 128, 128, 0, st>>>(B, p);", "  return (int)cudaGetLastError();", "}", ""])
+
+    def key(self) -> str:
+        return hashlib.sha256(self.source().encode()).hexdigest()[:20]
+
+
+class LQRModuleSource(OCModuleSource):
+    """Generic time-varying matrix LQR of size (n, m, r) whose auxiliary matrices are READ from HBM
+    (the drop-in ``LQR.lqrSolver``, reference PDP/PDP.py:446-615, for user-supplied matrices).
+
+    Same kernel as the fused OC path with every entry treated as a structural non-zero and the
+    per-chunk "evaluation" replaced by a cooperative gather from the dense per-step record
+    ``[F|G|E|Hxx|Hxu|Hxe|Hux|Huu|Hue]`` (the layout ``pdp_aux_eval`` writes).  ``Hux`` is carried but
+    unused, exactly like the reference (PDP.py:569,572,598 use transpose(Hxu))."""
+
+    kind_id = 4
+
+    def __init__(self, n: int, m: int, r: int, chunk: int = 2, warps_per_block: int = 4):
+        self.n, self.m, self.r = int(n), int(m), int(r)
+        self.ns = self.n + self.m + self.r
+        self.nth = 0
+        self.chunk, self.wpb = int(chunk), int(warps_per_block)
+        n, m, r, ns = self.n, self.m, self.r, self.ns
+        nm = n + m
+        oF, oG, oE = 0, n * n, n * n + n * m
+        oHxx = oE + n * r
+        oHxu = oHxx + n * n
+        oHxe = oHxu + n * m
+        oHux = oHxe + n * r
+        oHuu = oHux + m * n
+        oHue = oHuu + m * m
+        self.ndense = oHue + m * r
+        src: List[int] = []
+
+        def slot(off):
+            src.append(off)
+            return ("v", len(src) - 1, 1.0)
+
+        self.S_ent = [[None] * ns for _ in range(n)]
+        for k in range(n):
+            for j in range(ns):
+                if j < n:
+                    self.S_ent[k][j] = slot(oF + k * n + j)
+                elif j < nm:
+                    self.S_ent[k][j] = slot(oG + k * m + (j - n))
+                else:
+                    self.S_ent[k][j] = slot(oE + k * r + (j - nm))
+        self.nvar_s = len(src)
+        self.H_ent = [[None] * nm for _ in range(ns)]
+        for j in range(ns):
+            for l in range(nm):
+                if j < n and l < n:
+                    off = oHxx + j * n + l
+                elif j < n:
+                    off = oHxu + j * m + (l - n)
+                elif j < nm and l < n:
+                    off = oHxu + l * m + (j - n)          # transpose(Hxu)
+                elif j < nm:
+                    off = oHuu + (j - n) * m + (l - n)
+                elif l < n:
+                    off = oHxe + l * r + (j - nm)
+                else:
+                    off = oHue + (l - n) * r + (j - nm)
+                self.H_ent[j][l] = slot(off)
+        self.src_off = src
+        self.nvar = len(src)
+        self.auxld = _even(self.nvar)
+        self.ldh, self.ldz, self.ldk = _odd(nm), _odd(n), _even(n)
+
+    def _device_functions(self) -> str:
+        return ""
+
+    def _extra_tables(self):
+        return ["__device__ const int pdp_slot_src[%d] = {%s};" % (len(self.src_off), ", ".join(map(str, self.src_off)))]
+
+    def _kernel_text(self):
+        info = _K_LAUNCH_COMMON[:_K_LAUNCH_COMMON.index('extern "C" int pdpmod_rollout_costate')]
+        return _K_AUX_LQR + info + _K_LAUNCH_LQR
+
+    def _eval_macros(self):
+        gather = """    {
+      const int nst = (tc + PDP_CH < H ? PDP_CH : H - tc);
+      for (int idx = lane; idx < nst * %(NV)s; idx += 32) {
+        const int l = idx / %(NV)s, e = idx - l * %(NV)s;
+        auxc[l * PDP_AUXLD + e] = auxrec[((size_t)b * H + tc + l) * PDP_NDENSE + pdp_slot_src[e]];
+      }
+    }"""
+        return {
+            "@@EVAL_TERM@@": "  for (int i = lane; i < PDP_N * PDP_N + PDP_N * PDP_R; i += 32) TB[i] = termrec[(size_t)b * (PDP_N * PDP_N + PDP_N * PDP_R) + i];",
+            "@@EVAL_AUX_CHUNK@@": gather % {"NV": "PDP_NVAR"},
+            "@@EVAL_DYN@@": "        for (int e = 0; e < PDP_NVAR_S; ++e) auxc[lane * PDP_AUXLD + e] = auxrec[((size_t)b * H + te) * PDP_NDENSE + pdp_slot_src[e]];",
+        }
+
+
+_K_ROLLOUT_AUXEVAL = r'''
 // =====================================================================================================
 // Kernel 1: forward rollout + cost + costate recursion (+ optional dH/du), one thread per trajectory.
 //   restates reference OCSys.ocSolver's rollout semantics at given controls (PDP.py:158-175) and the PMP
@@ -530,9 +729,9 @@ pdp_k_rollout_costate(int B, int H, const double* __restrict__ x0, const double*
 {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  double x[PDP_N], xn[PDP_N], th[PDP_R], u[PDP_M], tmp[1];
+  double x[PDP_N], xn[PDP_N], th[PDP_NTH], u[PDP_M], tmp[1];
   #pragma unroll
-  for (int i = 0; i < PDP_R; ++i) th[i] = theta[(size_t)b * theta_stride + i];
+  for (int i = 0; i < PDP_NTH; ++i) th[i] = theta[(size_t)b * theta_stride + i];
   #pragma unroll
   for (int i = 0; i < PDP_N; ++i) x[i] = x0[(size_t)b * PDP_N + i];
   double J = 0.0;
@@ -604,6 +803,9 @@ pdp_k_aux_eval(int B, int H, const double* __restrict__ X, const double* __restr
                   out + ((size_t)b * H + t) * PDP_NDENSE);
 }
 
+'''
+
+_K_AUX_LQR = r'''
 // =====================================================================================================
 // Kernel 3: fused getAuxSys + LQR.lqrSolver (PDP.py:272-314 + 446-615), ONE WARP PER TRAJECTORY.
 //   Backward Riccati sweep in the stacked form (see DESIGN.md): lane j < NS owns row j of the stack
@@ -621,6 +823,7 @@ pdp_k_aux_lqr(int B, int H, const double* __restrict__ X, const double* __restri
               const double* __restrict__ theta, int theta_stride, const double* __restrict__ X0a, int x0a_stride,
               double* __restrict__ dX, double* __restrict__ dU, double* __restrict__ gains,
               const double* __restrict__ Xref, const double* __restrict__ Uref, double* __restrict__ loss_dp,
+              const double* __restrict__ auxrec, const double* __restrict__ termrec, int fwd_only,
               int* __restrict__ status)
 {
   extern __shared__ __align__(16) double pdp_smem[];
@@ -644,27 +847,25 @@ pdp_k_aux_lqr(int B, int H, const double* __restrict__ X, const double* __restri
   bool bad = false;
 @@TABLOAD@@
   for (int i = lane; i < PDP_HD_SIZE; i += 32) Hd[i] = 0.0;
-  if (lane < PDP_R) TH[lane] = theta[(size_t)b * theta_stride + lane];
+  if (theta != nullptr) for (int i = lane; i < PDP_NTH; i += 32) TH[i] = theta[(size_t)b * theta_stride + i];
   __syncwarp();
   {
 @@HINIT@@
   }
   // ---- terminal condition P = hxx(x_H), W = hxe(x_H)  (PDP.py:561-562)
-  if (lane == 0) pdp_f_terminal(Xb + (size_t)H * PDP_N, TH, TB);
+  if (!fwd_only) {
+@@EVAL_TERM@@
+  }
   __syncwarp();
   @@YDECL@@
   {
 @@TERM_INIT@@
   }
   __syncwarp();
-  // ---- backward sweep
+  // ---- backward sweep (skipped when the caller supplies the gains: forward-only recursions)
   #pragma unroll 1
-  for (int tc = ((H - 1) / PDP_CH) * PDP_CH; tc >= 0; tc -= PDP_CH) {
-    {
-      const int te = tc + lane;
-      if (lane < PDP_CH && te < H)
-        pdp_f_aux_slots(Xb + (size_t)te * PDP_N, Ub + (size_t)te * PDP_M, Lb + (size_t)te * PDP_N, TH, auxc + lane * PDP_AUXLD);
-    }
+  for (int tc = fwd_only ? -1 : ((H - 1) / PDP_CH) * PDP_CH; tc >= 0; tc -= PDP_CH) {
+@@EVAL_AUX_CHUNK@@
     __syncwarp();
     const int thi = (tc + PDP_CH < H ? tc + PDP_CH : H) - 1;
     #pragma unroll 1
@@ -705,7 +906,7 @@ pdp_k_aux_lqr(int B, int H, const double* __restrict__ X, const double* __restri
     {
       const int te = tc + lane;
       if (lane < PDP_CH && te < H) {
-        pdp_f_dyn_slots(Xb + (size_t)te * PDP_N, Ub + (size_t)te * PDP_M, TH, auxc + lane * PDP_AUXLD);
+@@EVAL_DYN@@
         if (fused) {
           // loss / chain rule of the IRL scripts (reference Examples/IRL/quadrotor/uav_PDP.py:67-75)
           #pragma unroll
@@ -776,12 +977,15 @@ pdp_k_aux_lqr(int B, int H, const double* __restrict__ X, const double* __restri
   }
 }
 
+'''
+
+_K_LAUNCH_COMMON = r'''
 // =====================================================================================================
 // Host-side launchers (C ABI of the module; bound by csrc/pdp_b200.cpp through dlopen)
 // =====================================================================================================
 extern "C" void pdpmod_info(int* out) {
-  out[0] = 1;            // kind: oc
-  out[1] = PDP_N; out[2] = PDP_M; out[3] = PDP_R; out[4] = PDP_NVAR; out[5] = PDP_NVAR_S;
+  out[0] = PDP_KIND;
+  out[1] = PDP_N; out[2] = PDP_M; out[3] = PDP_R; out[4] = PDP_NVAR; out[5] = PDP_NVAR_S; out[11] = PDP_NTH;
   out[6] = PDP_GREC; out[7] = PDP_NDENSE; out[8] = PDP_CH; out[9] = PDP_WPB; out[10] = PDP_WARP_DOUBLES;
 }
 
@@ -800,9 +1004,13 @@ extern "C" int pdpmod_aux_eval(int B, int H, const double* X, const double* U, c
   return (int)cudaGetLastError();
 }
 
+'''
+
+_K_LAUNCH_LQR = r'''
 extern "C" int pdpmod_aux_lqr(int B, int H, const double* X, const double* U, const double* Lam, const double* theta,
                               int theta_stride, const double* X0a, int x0a_stride, double* dX, double* dU, double* gains,
-                              const double* Xref, const double* Uref, double* loss_dp, int* status, cudaStream_t st) {
+                              const double* Xref, const double* Uref, double* loss_dp,
+                              const double* auxrec, const double* termrec, int fwd_only, int* status, cudaStream_t st) {
   if (B <= 0) return 0;
   static bool configured = false;
   const size_t smem = (size_t)PDP_WPB * PDP_WARP_DOUBLES * sizeof(double);
@@ -812,7 +1020,7 @@ extern "C" int pdpmod_aux_lqr(int B, int H, const double* X, const double* U, co
     configured = true;
   }
   pdp_k_aux_lqr<<<(B + PDP_WPB - 1) / PDP_WPB, PDP_WPB * 32, smem, st>>>(B, H, X, U, Lam, theta, theta_stride, X0a, x0a_stride,
-                                                                         dX, dU, gains, Xref, Uref, loss_dp, status);
+                                                                         dX, dU, gains, Xref, Uref, loss_dp, auxrec, termrec, fwd_only, status);
   return (int)cudaGetLastError();
 }
 '''

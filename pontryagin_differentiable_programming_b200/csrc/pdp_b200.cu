@@ -31,7 +31,9 @@ using fn_rollout = int (*)(int, int, const double*, const double*, int, const do
 using fn_aux_eval = int (*)(int, int, const double*, const double*, const double*, const double*, int, double*, double*,
                             cudaStream_t);
 using fn_aux_lqr = int (*)(int, int, const double*, const double*, const double*, const double*, int, const double*, int,
-                           double*, double*, double*, const double*, const double*, double*, int*, cudaStream_t);
+                           double*, double*, double*, const double*, const double*, double*, const double*, const double*,
+                           int, int*, cudaStream_t);
+using fn_eval = int (*)(int, const double* const*, const int*, double* const*, cudaStream_t);
 using fn_sens = int (*)(int, int, const double*, const double*, int, const double*, const double*, double*, double*, double*,
                         double*, double*, int*, cudaStream_t);
 
@@ -46,6 +48,7 @@ struct pdp_system {
   fn_aux_eval aux_eval = nullptr;
   fn_aux_lqr aux_lqr = nullptr;
   fn_sens sens = nullptr;
+  fn_eval fneval = nullptr;
   int kind() const { return info[0]; }
   int n() const { return info[1]; }
   int m() const { return info[2]; }
@@ -78,6 +81,7 @@ int pdp_load_system(const char* module_path, pdp_system_t** out) {
   s->aux_eval = reinterpret_cast<fn_aux_eval>(dlsym(h, "pdpmod_aux_eval"));
   s->aux_lqr = reinterpret_cast<fn_aux_lqr>(dlsym(h, "pdpmod_aux_lqr"));
   s->sens = reinterpret_cast<fn_sens>(dlsym(h, "pdpmod_sens_fwd"));
+  s->fneval = reinterpret_cast<fn_eval>(dlsym(h, "pdpmod_fn"));
   *out = s;
   return PDP_OK;
 }
@@ -136,15 +140,32 @@ int pdp_aux_lqr(pdp_system_t* sys, int B, int H, const double* X, const double* 
                 const double* theta, int theta_stride, const double* X0aux, int x0aux_stride,
                 double* dXdtheta, double* dUdtheta, const double* Xref, const double* Uref, double* loss_dp,
                 void* workspace, size_t ws_bytes, int* status, pdp_stream_t stream) {
-  if (!sys || !sys->aux_lqr) return fail(PDP_ERR_UNSUPPORTED, "pdp_aux_lqr: module has no aux-LQR kernel");
+  if (!sys || !sys->aux_lqr || sys->kind() != PDP_KIND_OC)
+    return fail(PDP_ERR_UNSUPPORTED, "pdp_aux_lqr: module has no fused aux-LQR kernel");
   if (B < 0 || H < 1 || !X || !U || !Lam || !theta) return fail(PDP_ERR_ARG, "pdp_aux_lqr: bad argument");
   if (loss_dp && !Xref) return fail(PDP_ERR_ARG, "pdp_aux_lqr: loss_dp needs Xref");
   if (ws_bytes < pdp_workspace_bytes(sys, PDP_OP_AUX_LQR, B, H) || (B > 0 && !workspace))
     return fail(PDP_ERR_WORKSPACE, "pdp_aux_lqr: workspace too small (%zu < %zu)", ws_bytes,
                 pdp_workspace_bytes(sys, PDP_OP_AUX_LQR, B, H));
   int e = sys->aux_lqr(B, H, X, U, Lam, theta, theta_stride, X0aux, x0aux_stride, dXdtheta, dUdtheta,
-                       reinterpret_cast<double*>(workspace), Xref, Uref, loss_dp, status, (cudaStream_t)stream);
+                       reinterpret_cast<double*>(workspace), Xref, Uref, loss_dp, nullptr, nullptr, 0, status,
+                       (cudaStream_t)stream);
   if (e) return fail(PDP_ERR_CUDA, "pdp_aux_lqr: CUDA error %d (%s)", e, cudaGetErrorString((cudaError_t)e));
+  return PDP_OK;
+}
+
+int pdp_lqr_dense(pdp_system_t* sys, int B, int H, const double* aux, const double* term, const double* X0aux,
+                  int x0aux_stride, double* Xaux, double* Uaux, int forward_only, void* workspace, size_t ws_bytes,
+                  int* status, pdp_stream_t stream) {
+  if (!sys || !sys->aux_lqr || sys->kind() != PDP_KIND_LQR)
+    return fail(PDP_ERR_UNSUPPORTED, "pdp_lqr_dense: not a dense-LQR module");
+  if (B < 0 || H < 1 || !aux || (!term && !forward_only)) return fail(PDP_ERR_ARG, "pdp_lqr_dense: bad argument");
+  if (ws_bytes < pdp_workspace_bytes(sys, PDP_OP_AUX_LQR, B, H) || (B > 0 && !workspace))
+    return fail(PDP_ERR_WORKSPACE, "pdp_lqr_dense: workspace too small");
+  int e = sys->aux_lqr(B, H, nullptr, nullptr, nullptr, nullptr, 0, X0aux, x0aux_stride, Xaux, Uaux,
+                       reinterpret_cast<double*>(workspace), nullptr, nullptr, nullptr, aux, term, forward_only ? 1 : 0,
+                       status, (cudaStream_t)stream);
+  if (e) return fail(PDP_ERR_CUDA, "pdp_lqr_dense: CUDA error %d (%s)", e, cudaGetErrorString((cudaError_t)e));
   return PDP_OK;
 }
 
@@ -175,6 +196,15 @@ int pdp_sens_fwd(pdp_system_t* sys, int B, int H, const double* x0, const double
   if (B < 0 || H < 1 || !x0 || !theta) return fail(PDP_ERR_ARG, "pdp_sens_fwd: bad argument");
   int e = sys->sens(B, H, x0, theta, theta_stride, inputs, Xobs, X, Uout, dX, dU, loss_dp, status, (cudaStream_t)stream);
   if (e) return fail(PDP_ERR_CUDA, "pdp_sens_fwd: CUDA error %d (%s)", e, cudaGetErrorString((cudaError_t)e));
+  return PDP_OK;
+}
+
+int pdp_eval_function(pdp_system_t* sys, int B, const double* const* inputs, const int* input_strides,
+                      double* const* outputs, pdp_stream_t stream) {
+  if (!sys || !sys->fneval) return fail(PDP_ERR_UNSUPPORTED, "pdp_eval_function: not a function module");
+  if (B < 0 || !inputs || !input_strides || !outputs) return fail(PDP_ERR_ARG, "pdp_eval_function: bad argument");
+  int e = sys->fneval(B, inputs, input_strides, outputs, (cudaStream_t)stream);
+  if (e) return fail(PDP_ERR_CUDA, "pdp_eval_function: CUDA error %d (%s)", e, cudaGetErrorString((cudaError_t)e));
   return PDP_OK;
 }
 

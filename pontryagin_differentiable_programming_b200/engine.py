@@ -193,3 +193,191 @@ class OCSystem:
         out["hxx"] = term[:, :n * n].reshape(B, n, n)
         out["hxe"] = term[:, n * n:].reshape(B, n, r)
         return out
+
+
+class _SensSystem:
+    """Common driver of the forward-sensitivity modules (SysID / ControlPlanning)."""
+
+    def __init__(self, src, verbose=False):
+        self.src = src
+        self.n, self.m, self.r = src.n, src.m, src.r
+        self.module_path = build.compile_module(src.source(), src.key(), verbose=verbose)
+        self._handle = None
+
+    @property
+    def handle(self):
+        if self._handle is None:
+            self._handle = backend.SystemHandle(self.module_path)
+        return self._handle
+
+    def _run(self, B, H, x0, theta, inputs, Xobs, want_traj, want_sens, want_loss, status, dev, has_policy):
+        theta2 = theta.unsqueeze(0) if theta.dim() == 1 else theta
+        ts = 0 if theta2.shape[0] == 1 else self.r
+        _chk(theta2, (B if ts else 1, self.r), "theta", dev)
+        _chk(x0, (B, self.n), "x0", dev)
+        mk = lambda *shape: torch.empty(shape, dtype=torch.float64, device=dev)
+        X = mk(B, H + 1, self.n) if want_traj else None
+        Uout = mk(B, H, self.m) if (want_traj and has_policy) else None
+        dX = mk(B, H + 1, self.n, self.r) if want_sens else None
+        dU = mk(B, H, self.m, self.r) if (want_sens and has_policy) else None
+        ldp = mk(B, self.r + 1) if want_loss else None
+        st = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            backend.check(self.handle.lib.pdp_sens_fwd(self.handle.ptr, B, H, _ptr(x0), _ptr(theta2), ts, _ptr(inputs),
+                                                       _ptr(Xobs), _ptr(X), _ptr(Uout), _ptr(dX), _ptr(dU), _ptr(ldp),
+                                                       _ptr(status), st), "pdp_sens_fwd")
+        out = {}
+        for k, v in (("X", X), ("U", Uout), ("dX", dX), ("dU", dU), ("loss_dp", ldp)):
+            if v is not None:
+                out[k] = v
+        return out
+
+
+class SysIDSystem(_SensSystem):
+    """Fused SysID.step (reference PDP/PDP.py:1261-1296): rollout + X+ = F X + E + loss / half-gradient."""
+
+    def __init__(self, state, control, auxvar, dyn, verbose=False, **kw):
+        from . import codegen_sens
+        super().__init__(codegen_sens.SensModuleSource(codegen_sens.KIND_SYSID, state, control, auxvar, dyn, **kw), verbose)
+
+    def step(self, inputs, Xobs, theta, x0=None, want_traj=False, want_sens=False, status=None):
+        """inputs[B,H,m], Xobs[B,H+1,n] (x0 defaults to Xobs[:,0]) -> dict with loss_dp[B,r+1] (+X, dX)."""
+        require_cuda()
+        dev = inputs.device
+        B, H = inputs.shape[0], inputs.shape[1]
+        _chk(inputs, (B, H, self.m), "inputs", dev)
+        if Xobs is not None:
+            _chk(Xobs, (B, H + 1, self.n), "Xobs", dev)
+        if x0 is None:
+            x0 = Xobs[:, 0, :].contiguous()
+        return self._run(B, H, x0, theta, inputs, Xobs, want_traj, want_sens, Xobs is not None, status, dev, False)
+
+
+class CPSystem(_SensSystem):
+    """Fused ControlPlanning.step (reference PDP/PDP.py:850-878) for a parameterised policy."""
+
+    def __init__(self, state, control, auxvar, dyn, policy, tvar, path_cost, final_cost, verbose=False, **kw):
+        from . import codegen_sens
+        super().__init__(codegen_sens.SensModuleSource(codegen_sens.KIND_CP, state, control, auxvar, dyn, policy=policy,
+                                                       tvar=tvar, path_cost=path_cost, final_cost=final_cost, **kw), verbose)
+
+    def step(self, x0, H, theta, want_traj=False, want_sens=False, status=None):
+        """x0[B,n], theta[B|1,r] -> loss_dp[B,r+1] = (cost, dcost/dtheta) (+ X, U, dX, dU)."""
+        require_cuda()
+        dev = x0.device
+        B = x0.shape[0]
+        return self._run(B, int(H), x0, theta, None, None, want_traj, want_sens, True, status, dev, True)
+
+
+class DenseLQR:
+    """Generic (n, m, r) matrix LQR on caller-supplied matrices (the drop-in ``LQR.lqrSolver``)."""
+
+    _cache = {}
+
+    def __init__(self, n, m, r, verbose=False):
+        self.n, self.m, self.r = int(n), int(m), int(r)
+        if self.n + self.m + self.r > 32:
+            raise ValueError("DenseLQR handles n+m+r <= 32 per launch; split the auxvar columns (see LQR.lqrSolver)")
+        self.src = codegen.LQRModuleSource(self.n, self.m, self.r)
+        self.module_path = build.compile_module(self.src.source(), self.src.key(), verbose=verbose)
+        self._handle = None
+        self._ws = None
+
+    @classmethod
+    def get(cls, n, m, r):
+        key = (int(n), int(m), int(r))
+        if key not in cls._cache:
+            cls._cache[key] = cls(*key)
+        return cls._cache[key]
+
+    @property
+    def handle(self):
+        if self._handle is None:
+            self._handle = backend.SystemHandle(self.module_path)
+        return self._handle
+
+    @property
+    def ndense(self):
+        n, m, r = self.n, self.m, self.r
+        return 2 * (n * n + n * m + n * r) + m * n + m * m + m * r
+
+    def solve(self, aux, term, X0aux=None, status=None, gains=None):
+        """aux[B,H,NDENSE], term[B,n*n+n*r] -> Xaux[B,H+1,n,r], Uaux[B,H,m,r].
+        ``gains[B,H,n+r,m]`` given => forward-only recursion with those gains (no Riccati sweep)."""
+        require_cuda()
+        dev = aux.device
+        B, H = aux.shape[0], aux.shape[1]
+        n, m, r = self.n, self.m, self.r
+        _chk(aux, (B, H, self.ndense), "aux", dev)
+        if term is not None:
+            _chk(term, (B, n * n + n * r), "term", dev)
+        x0s = 0
+        if X0aux is not None:
+            if X0aux.dim() == 2:
+                X0aux = X0aux.unsqueeze(0)
+            x0s = 0 if X0aux.shape[0] == 1 else 1
+            _chk(X0aux, (B if x0s else 1, n, r), "X0aux", dev)
+        Xa = torch.empty((B, H + 1, n, r), dtype=torch.float64, device=dev)
+        Ua = torch.empty((B, H, m, r), dtype=torch.float64, device=dev)
+        need = self.handle.workspace_bytes(backend.OP_AUX_LQR, B, H)
+        if gains is not None:
+            _chk(gains, (B, H, n + r, m), "gains", dev)
+            ws = gains.view(torch.uint8).reshape(-1)
+            if ws.numel() < need:
+                ws = torch.cat([ws, torch.zeros(need - ws.numel(), dtype=torch.uint8, device=dev)])
+        else:
+            if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+                self._ws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
+            ws = self._ws
+        st = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            backend.check(self.handle.lib.pdp_lqr_dense(self.handle.ptr, B, H, _ptr(aux), _ptr(term), _ptr(X0aux), x0s,
+                                                        _ptr(Xa), _ptr(Ua), 1 if gains is not None else 0, _ptr(ws),
+                                                        ws.numel(), _ptr(status), st), "pdp_lqr_dense")
+        return Xa, Ua
+
+
+class GpuFunction:
+    """A symbolic ``Function`` compiled to a batched CUDA kernel (one thread per sample)."""
+
+    def __init__(self, fn, verbose=False):
+        self.fn = fn
+        self.src = codegen.FunctionModuleSource(fn)
+        self.module_path = build.compile_module(self.src.source(), self.src.key(), verbose=verbose)
+        self._handle = None
+
+    @property
+    def handle(self):
+        if self._handle is None:
+            self._handle = backend.SystemHandle(self.module_path)
+        return self._handle
+
+    def __call__(self, *args):
+        """args[k]: CUDA float64 tensor [B, numel_k] or [numel_k] (shared).  Returns a list of
+        [B, rows, cols] tensors.  Input elements are in the Function's column-major element order."""
+        import ctypes
+        require_cuda()
+        fn = self.fn
+        if len(args) != fn.n_in():
+            raise TypeError("GpuFunction: expected %d inputs" % fn.n_in())
+        B = max([a.shape[0] for a in args if a.dim() == 2] + [1])
+        dev = args[0].device
+        ins, strides = [], []
+        for k, a in enumerate(args):
+            ne = fn.numel_in(k)
+            a2 = a if a.dim() == 2 else a.unsqueeze(0)
+            _chk(a2, (a2.shape[0], ne), "input %d" % k, dev)
+            if a2.shape[0] not in (1, B):
+                raise ValueError("GpuFunction: inconsistent batch sizes")
+            ins.append(a2)
+            strides.append(ne if a2.shape[0] == B and B > 1 else (ne if B == 1 else 0))
+        outs = [torch.empty((B,) + tuple(fn.size_out(k)), dtype=torch.float64, device=dev) for k in range(fn.n_out())]
+        PtrArr = ctypes.c_void_p * max(len(ins), 1)
+        OutArr = ctypes.c_void_p * max(len(outs), 1)
+        StrArr = ctypes.c_int * max(len(ins), 1)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            backend.check(self.handle.lib.pdp_eval_function(self.handle.ptr, B, PtrArr(*[t.data_ptr() for t in ins]),
+                                                            StrArr(*strides), OutArr(*[t.data_ptr() for t in outs]), st),
+                          "pdp_eval_function")
+        return outs

@@ -74,4 +74,72 @@ def build_all(verbose=False):
         out["oc_" + name] = fn().module_path
         if verbose:
             print("built", name, out["oc_" + name])
+    for name, fn in SENS_BUILDERS.items():
+        out[name] = fn().module_path
+        if verbose:
+            print("built", name, out[name])
     return out
+
+
+# ------------------------------------------------------------------------------ SysID / ControlPlanning
+@functools.lru_cache(maxsize=None)
+def quadrotor_sysid(dt: float = 0.1):
+    """C5: quadrotor SysID, n=13 m=4 r=5 (reference Examples/SysID/quadrotor/uav_PDP.py:9-19)."""
+    env = _jinenv().Quadrotor()
+    env.initDyn(c=0.01)
+    return engine.SysIDSystem(env.X, env.U, env.dyn_auxvar, env.X + dt * env.f)
+
+
+def lagrange_policy(n_control, pivots, tvar):
+    """u(t, theta) = sum_i b_i(t) U_i, Lagrange basis over ``pivots`` (reference PDP/PDP.py:699-725)."""
+    from .symbolic import SX, vcat
+    pol = 0
+    params = []
+    for i in range(len(pivots)):
+        Ui = SX.sym('U_' + str(i), n_control)
+        params.append(Ui)
+        bi = 1
+        for j in range(len(pivots)):
+            if j != i:
+                bi = bi * (tvar - pivots[j]) / (pivots[i] - pivots[j])
+        pol = pol + bi * Ui
+    return pol, vcat(params)
+
+
+def neural_policy(state, n_control, hidden_layers):
+    """tanh MLP with column-major packed weights (reference PDP/PDP.py:727-759)."""
+    from .symbolic import SX, mtimes, tanh, vcat
+    layers = list(hidden_layers) + [n_control]
+    a = state
+    params = []
+    n_in = state.numel()
+    for li, n_out in enumerate(layers):
+        Ak = SX.sym('Ak', n_out, n_in)
+        bk = SX.sym('bk', n_out)
+        params += [Ak.reshape((-1, 1)), bk]
+        if li > 0:
+            a = tanh(a)
+        a = mtimes(Ak, a) + bk
+        n_in = n_out
+    return a, vcat(params)
+
+
+@functools.lru_cache(maxsize=None)
+def cartpole_cp(policy: str = "poly", horizon: int = 50, dt: float = 0.05):
+    """C2: cartpole ControlPlanning n=4 m=1 (reference Examples/OC/cartpole/cartpole_PDP_poly.py:13-30,
+    cartpole_PDP_neural.py:13-30,49): poly r=6 (n_poly=5), neural [4,4] r=45."""
+    import numpy as np
+    from .symbolic import SX
+    env = _jinenv().CartPole()
+    env.initDyn(mc=0.1, mp=0.1, l=1)
+    env.initCost(wx=0.1, wq=0.6, wdx=0.1, wdq=0.1, wu=0.3)
+    t = SX.sym('t')
+    if policy == "poly":
+        pol, th = lagrange_policy(1, np.linspace(0, horizon, 6), t)
+    else:
+        pol, th = neural_policy(env.X, 1, [4, 4])
+    return engine.CPSystem(env.X, env.U, th, env.X + dt * env.f, pol, t, env.path_cost, env.final_cost)
+
+
+SENS_BUILDERS = {"sysid_quadrotor": quadrotor_sysid,
+                 "cp_cartpole_poly": lambda: cartpole_cp("poly"), "cp_cartpole_neural": lambda: cartpole_cp("neural")}

@@ -1,0 +1,217 @@
+"""CPU-only tests: symbolic front-end, code generation, drop-in class surface, C-ABI exports, sharding."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+
+
+# ------------------------------------------------------------------------------------ symbolic front-end
+def test_symbolic_matches_casadi_semantics():
+    from casadi import SX, Function, jacobian, vertcat, horzcat, mtimes, dot, sin, inv, diag, trace, transpose
+    x = SX.sym('x', 3)
+    assert x.shape == (3, 1) and x.numel() == 3
+    A = SX.sym('A', 2, 3)
+    assert A.reshape((-1, 1)).shape == (6, 1)
+    # column-major reshape (reference relies on it: PDP.py:740)
+    f = Function('f', [A], [A.reshape((-1, 1))])
+    v = f(np.array([[1., 2., 3.], [4., 5., 6.]])).full().ravel()
+    assert np.array_equal(v, [1, 4, 2, 5, 3, 6])
+    # ndarray on the left defers to SX
+    e = np.identity(3) - mtimes(transpose(SX.sym('R', 3, 3)), SX.eye(3))
+    assert isinstance(e, SX) and e.shape == (3, 3)
+    # (1,1) ndarray times vector broadcasts (dt loaded from .mat, reference uav_PDP.py:17,24)
+    assert (np.array([[0.1]]) * x).shape == (3, 1)
+    g = vertcat(x[0] * x[1] + sin(x[2]), dot(x, x))
+    J = Function('J', [x], [jacobian(g, x)])
+    got = J([1., 2., 3.]).full()
+    ref = np.array([[2., 1., np.cos(3.)], [2., 4., 6.]])
+    assert np.allclose(got, ref, atol=1e-15)
+    M = vertcat(horzcat(x[0], x[1]), horzcat(x[1], x[2] + 5))
+    Mi = Function('Mi', [x], [inv(M)])([1., 2., 3.]).full()
+    assert np.allclose(Mi, np.linalg.inv(np.array([[1., 2.], [2., 8.]])), atol=1e-15)
+    assert trace(diag(x)).numel() == 1
+    # symbolic call = substitution (used by warped dynamics / NLP transcription in the reference)
+    y = SX.sym('y', 3)
+    assert np.allclose(Function('s', [y], [J(y)])([1., 2., 3.]).full(), ref)
+    # scalar broadcast of a vector argument (auxvar_value=1 default, PDP.py:121)
+    assert np.allclose(J(1.0).full(), J([1., 1., 1.]).full())
+
+
+@pytest.mark.parametrize("env", ["pendulum", "cartpole", "robotarm", "quadrotor", "rocket"])
+def test_product_derivatives_match_oracle(env):
+    """diffPMP of the drop-in OCSys (own symbolic engine) against the sympy oracle at random points."""
+    from PDP import PDP
+    from JinEnv import JinEnv
+    from casadi import vertcat
+    from oracle import envs, pdp_oracle
+    setup = {"pendulum": (JinEnv.SinglePendulum, {}, {}, envs.pendulum, {}),
+             "cartpole": (JinEnv.CartPole, {}, dict(wu=0.1), envs.cartpole, dict(wu=0.1)),
+             "robotarm": (JinEnv.RobotArm, dict(g=0), dict(wu=0.01), envs.robotarm, dict(g=0, wu=0.01)),
+             "quadrotor": (JinEnv.Quadrotor, dict(c=0.01), dict(wthrust=0.1), envs.quadrotor, dict(c=0.01, wthrust=0.1)),
+             "rocket": (JinEnv.Rocket, {}, dict(wthrust=0.1), envs.rocket, dict(wthrust=0.1))}[env]
+    cls, dkw, ckw, obuilder, okw = setup
+    e = cls()
+    e.initDyn(**dkw)
+    e.initCost(**ckw)
+    dt = 0.1
+    oc = PDP.OCSys()
+    oc.setAuxvarVariable(vertcat(e.dyn_auxvar, e.cost_auxvar))
+    oc.setStateVariable(e.X)
+    oc.setControlVariable(e.U)
+    oc.setDyn(e.X + dt * e.f)
+    oc.setPathCost(e.path_cost)
+    oc.setFinalCost(e.final_cost)
+    oc.diffPMP()
+    ref = pdp_oracle.build_oc(obuilder(**okw), dt)
+    ref.diffPMP()
+    assert (oc.n_state, oc.n_control, oc.n_auxvar) == (ref.n, ref.m, ref.r)
+    rng = np.random.default_rng(11)
+    for _ in range(3):
+        x, u, lam = rng.standard_normal(ref.n), rng.standard_normal(ref.m), rng.standard_normal(ref.n)
+        th = rng.uniform(0.5, 1.5, ref.r)
+        pairs = [(oc.dyn_fn(x, u, th), ref.dyn_fn(x, u, th)), (oc.dfx_fn(x, u, th), ref.dfx_fn(x, u, th)),
+                 (oc.dfu_fn(x, u, th), ref.dfu_fn(x, u, th)), (oc.dfe_fn(x, u, th), ref.dfe_fn(x, u, th)),
+                 (oc.dHx_fn(x, u, lam, th), ref.dHx_fn(x, u, lam, th)), (oc.dHu_fn(x, u, lam, th), ref.dHu_fn(x, u, lam, th)),
+                 (oc.ddHxx_fn(x, u, lam, th), ref.ddHxx_fn(x, u, lam, th)), (oc.ddHxu_fn(x, u, lam, th), ref.ddHxu_fn(x, u, lam, th)),
+                 (oc.ddHxe_fn(x, u, lam, th), ref.ddHxe_fn(x, u, lam, th)), (oc.ddHux_fn(x, u, lam, th), ref.ddHux_fn(x, u, lam, th)),
+                 (oc.ddHuu_fn(x, u, lam, th), ref.ddHuu_fn(x, u, lam, th)), (oc.ddHue_fn(x, u, lam, th), ref.ddHue_fn(x, u, lam, th)),
+                 (oc.dhx_fn(x, th), ref.dhx_fn(x, th)), (oc.ddhxx_fn(x, th), ref.ddhxx_fn(x, th)),
+                 (oc.ddhxe_fn(x, th), ref.ddhxe_fn(x, th)), (oc.path_cost_fn(x, u, th), ref.path_cost_fn(x, u, th))]
+        for mine, theirs in pairs:
+            a = mine.full()
+            b = np.asarray(theirs, dtype=np.float64).reshape(a.shape)
+            assert np.max(np.abs(a - b)) <= 1e-11 * max(1.0, np.max(np.abs(b)))
+
+
+def test_k1_rollout_through_function_objects():
+    """Shipped SysID data vs the drop-in dynamics Function (pins JinEnv + Euler step on the product side)."""
+    from PDP import PDP
+    from JinEnv import JinEnv
+    g = np.load(os.path.join(G, "k1_iodata.npz"))
+    rocket = JinEnv.Rocket()
+    rocket.initDyn()
+    sid = PDP.SysID()
+    sid.setAuxvarVariable(rocket.dyn_auxvar)
+    sid.setStateVariable(rocket.X)
+    sid.setControlVariable(rocket.U)
+    sid.setDyn(rocket.X + 0.2 * rocket.f)
+    for inp, st in zip(g["rocket_inputs"], g["rocket_states"]):
+        x = st[0]
+        for t in range(inp.shape[0]):
+            x = sid.dyn_fn(x, inp[t], g["rocket_true_parameter"]).full().ravel()
+            assert np.max(np.abs(x - st[t + 1])) < 1e-12
+
+
+# ------------------------------------------------------------------------------------ code generation
+def test_codegen_structure_and_determinism():
+    from pontryagin_differentiable_programming_b200 import systems
+    q = systems.quadrotor_irl(0.1)
+    s = q.src
+    assert (s.n, s.m, s.r, s.ns) == (13, 4, 9, 26)
+    nnz = sum(1 for row in s.S_ent for e in row if e[0] != "z")
+    assert nnz == 56 + 20 + 14                      # F 56, G 20, E 14 structural non-zeros
+    src = s.source()
+    for sym in ("pdp_k_rollout_costate", "pdp_k_aux_lqr", "pdp_k_aux_eval", "pdpmod_aux_lqr", "pdpmod_info"):
+        assert sym in src
+    assert "fma(" in src and "__syncwarp" in src
+    # a second build in a fresh interpreter generates byte-identical source (cache key stability)
+    code = ("import sys; sys.path.insert(0, %r); from pontryagin_differentiable_programming_b200 import systems;"
+            "systems.pendulum_irl(); print(systems.quadrotor_irl(0.1).src.key())" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True).stdout.strip()
+    assert out == s.key()
+
+
+def test_hot_path_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from PDP import PDP
+    from pontryagin_differentiable_programming_b200.backend import PDPBackendError
+    lqr = PDP.LQR()
+    lqr.setDyn(np.eye(2), np.ones((2, 1)), np.zeros((2, 3)))
+    lqr.setPathCost(np.eye(2), np.eye(1))
+    lqr.setFinalCost(np.eye(2), np.zeros((2, 3)))
+    with pytest.raises(PDPBackendError):
+        lqr.lqrSolver(np.zeros((2, 3)), 5)
+
+
+def test_lqr_argument_validation_like_reference():
+    from PDP import PDP
+    lqr = PDP.LQR()
+    with pytest.raises(AssertionError):
+        lqr.setDyn("bad", np.ones((2, 1)))
+    lqr.setDyn([np.eye(2)] * 3, [np.ones((2, 1))] * 3, [np.zeros((2, 4))] * 3)
+    assert (lqr.n_state, lqr.n_control, lqr.n_batch) == (2, 1, 4)        # n_batch = columns of dynE (trap T3)
+    lqr.setPathCost(np.eye(2), np.eye(1))
+    lqr.setFinalCost(np.eye(2), np.zeros((2, 4)))
+    with pytest.raises(AssertionError):                                  # horizon inconsistent with 3 matrices
+        lqr.lqrSolver(np.zeros((2, 4)), 5)
+    oc = PDP.OCSys()
+    from casadi import SX
+    oc.setStateVariable(SX.sym('x', 2))
+    oc.setControlVariable(SX.sym('u'))
+    with pytest.raises(AssertionError):
+        oc.setPathCost(SX.sym('c', 2))                                   # PDP.py:107
+
+
+# ------------------------------------------------------------------------------------ C ABI
+def test_c_abi_library_exports_every_declared_symbol():
+    from pontryagin_differentiable_programming_b200 import backend, build
+    hdr = open(os.path.join(ROOT, "include", "pdp_b200.h")).read()
+    declared = set(re.findall(r"\b(pdp_[a-z_]+)\s*\(", hdr))
+    lib = ctypes.CDLL(build.build_library())
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(backend.EXPORTS)
+    lib.pdp_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.pdp_version()
+    # loading a non-module fails with an error string, not a crash
+    h = ctypes.c_void_p()
+    lib.pdp_load_system.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]
+    assert lib.pdp_load_system(b"/nonexistent.so", ctypes.byref(h)) == -2
+    lib.pdp_last_error.restype = ctypes.c_char_p
+    assert b"dlopen" in lib.pdp_last_error()
+    # a real module loads and reports its dimensions without touching the GPU
+    from pontryagin_differentiable_programming_b200 import systems
+    handle = backend.SystemHandle(systems.quadrotor_irl(0.1).module_path)
+    assert (handle.kind, handle.n, handle.m, handle.r) == (1, 13, 4, 9)
+    assert handle.workspace_bytes(backend.OP_AUX_LQR, 16, 50) >= 16 * 50 * (13 + 9) * 4 * 8
+
+
+# ------------------------------------------------------------------------------------ multi-process
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from pontryagin_differentiable_programming_b200 import distributed as D
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(0)
+    full = torch.randn((11, 6), dtype=torch.float64, generator=g)        # global per-trajectory (loss, dp)
+    lo, hi = D.shard_bounds(11, rank, world)
+    loss, dp = D.reduce_loss_dp(full[lo:hi])
+    q.put((rank, lo, hi, float(loss), dp.tolist(), float(full[:, 0].mean()), full[:, 1:].mean(0).tolist()))
+    dist.destroy_process_group()
+
+
+def test_sharded_gradient_allreduce_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+    spans = sorted((lo, hi) for _, lo, hi, *_ in res)
+    assert spans == [(0, 6), (6, 11)]
+    for _, _, _, loss, dp, loss_ref, dp_ref in res:
+        assert abs(loss - loss_ref) < 1e-14
+        assert np.allclose(dp, dp_ref, atol=1e-14)
