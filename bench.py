@@ -55,6 +55,20 @@ def alg_bytes_aux_lqr(n, m, r, H):
     return 8 * (((H + 1) * n + H * m + H * n + r) + ((H + 1) * n * r + H * m * r) + 2 * H * m * (n + r))
 
 
+def alg_bytes_bwd(n, m, r, H):
+    """pdp_k_aux_lqr_bwd: read X, U, Lam, theta once; write the gain spill (K_t|k_t) once."""
+    return 8 * (((H + 1) * n + H * m + H * n + r) + H * m * (n + r))
+
+
+def alg_bytes_fwd(n, m, r, H):
+    """pdp_k_aux_lqr_fwd: read X, U, theta, the gain spill, Xref, Uref once; write dX, dU, (loss, dp) once."""
+    return 8 * (((H + 1) * n + H * m + r) + H * m * (n + r) + ((H + 1) * n + H * m) + ((H + 1) * n * r + H * m * r) + r + 1)
+
+
+def alg_flops_bwd(n, m, r, H):
+    return H * (4 * n ** 3 + 6 * n * n * m + 4 * n * m * m + m ** 3 / 3 + 4 * n * n * r + 4 * n * m * r + 2 * m * m * r + 400)
+
+
 def alg_bytes_sweep(n, m, r, H):
     """SURVEY 8(d) figure for the whole sweep (C3: 144 816 B)."""
     return 8 * ((n + r + H * m) + ((H + 1) * n + H * n + (H + 1) * n * r + H * m * r) + 2 * H * m * (n + r))
@@ -78,50 +92,50 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled through NVML by a polling thread DURING the timed region."""
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.samples, self.reasons, self.maxclk = index, [], set(), None
+        self._stop = threading.Event()
+        self.thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.maxclk = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as exc:  # pragma: no cover
+            self.nv, self.err = None, repr(exc)
+
+    def _poll(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
+        if self.nv is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
-        except Exception:
-            self.proc = None
-
-    def _pump(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml unavailable: " + self.err]}
+        self._stop.set()
+        self.thread.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.maxclk,
+                "samples": len(self.samples), "reasons": sorted(self.reasons)}
 
 
 # ------------------------------------------------------------------------------------------- CPU arms
@@ -229,9 +243,12 @@ def run_gpu(args):
         ro = sys_.rollout_costate(d_x0, d_th, d_U, status=status, out=out)
         if ev is not None:
             ev[0].record(stream)
-        sys_.aux_lqr(out["X"], d_U, out["Lam"], d_th, Xref=d_Xr, Uref=d_Ur, status=status, out=out)
+        sys_.aux_lqr(out["X"], d_U, out["Lam"], d_th, status=status, phase="backward")
         if ev is not None:
             ev[1].record(stream)
+        sys_.aux_lqr(out["X"], d_U, out["Lam"], d_th, Xref=d_Xr, Uref=d_Ur, status=status, out=out, phase="forward")
+        if ev is not None:
+            ev[2].record(stream)
         return ro
 
     def barrier():
@@ -245,7 +262,7 @@ def run_gpu(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
@@ -254,7 +271,8 @@ def run_gpu(args):
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
-    k_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    k_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in kev]))      # pdp_k_aux_lqr_bwd (dominant kernel)
+    kf_ms = float(np.mean([b.elapsed_time(c) for _, b, c in kev]))     # pdp_k_aux_lqr_fwd
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- parity subset against the oracle every run (first 4 trajectories of rank 0)
@@ -295,17 +313,18 @@ def run_gpu(args):
     e2e_ok = bool(torch.allclose(ldp_host.to(dev), out["loss_dp"], rtol=1e-12, atol=0))
     del ws
 
-    times = torch.tensor([ms_total, e2e_ms, k_ms], dtype=torch.float64, device=dev)
+    times = torch.tensor([ms_total, e2e_ms, k_ms, kf_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, k_ms = (float(v) for v in times.cpu())
+    ms_total, e2e_ms, k_ms, kf_ms = (float(v) for v in times.cpu())
     nbad = int((status != 0).sum().item())
 
     if rank == 0:
         value = B * world * args.steps / (ms_total * 1e-3)
         e2e_val = B * world * args.steps / (e2e_ms * 1e-3)
         peak, peak_src = measured_peaks()
-        kbytes = alg_bytes_aux_lqr(n, m, r, H) * B
+        kbytes = alg_bytes_bwd(n, m, r, H) * B
+        fbytes = alg_bytes_fwd(n, m, r, H) * B
         achieved = kbytes / (k_ms * 1e-3) / 1e9
         h2d = sum(int(p.numel()) * 8 for p in pinned)
         d2h = int(ldp_host.numel() + cost_host.numel()) * 8
@@ -320,14 +339,20 @@ def run_gpu(args):
                              % ((alg_bytes_sweep(n, m, r, H) * B) / 1e9),
                        "parity_max_rel_err_vs_oracle_first4": parity, "status_flagged_trajectories": nbad,
                        "e2e_matches_device_path": e2e_ok},
-            "roofline": {"kernel": "pdp_k_aux_lqr", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"kernel": "pdp_k_aux_lqr_bwd", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "alg_bytes_per_launch": kbytes, "kernel_ms": k_ms,
                          "kernel_share_of_step": k_ms / (ms_total / args.steps),
-                         "fp64_tflops_alg": alg_flops_sweep(n, m, r, H) * B / (k_ms * 1e-3) / 1e12},
+                         "fp64_tflops_alg_bwd": alg_flops_bwd(n, m, r, H) * B / (k_ms * 1e-3) / 1e12,
+                         "fp64_peak_tflops_nominal": 37.0,
+                         "second_kernel": {"kernel": "pdp_k_aux_lqr_fwd", "kernel_ms": kf_ms, "alg_bytes_per_launch": fbytes,
+                                           "achieved": fbytes / (kf_ms * 1e-3) / 1e9,
+                                           "frac": fbytes / (kf_ms * 1e-3) / 1e9 / peak},
+                         "sweep_alg_bytes": alg_bytes_sweep(n, m, r, H) * B,
+                         "sweep_achieved_GBps": alg_bytes_sweep(n, m, r, H) * B / (ms_total / args.steps * 1e-3) / 1e9},
             "e2e": {"value": e2e_val, "unit": "sweeps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "pdp_sweep_host (C ABI, pinned host buffers)"},
-            "gpu_launches": 2 * args.steps, "clocks": clocks,
+            "gpu_launches": 3 * args.steps, "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1

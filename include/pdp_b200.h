@@ -64,6 +64,17 @@ int pdp_aux_lqr(pdp_system_t* sys, int B, int H, const double* X, const double* 
                 double* dXdtheta, double* dUdtheta, const double* Xref, const double* Uref, double* loss_dp,
                 void* workspace, size_t ws_bytes, int* status, pdp_stream_t stream);
 
+/* The two halves of pdp_aux_lqr as separate calls.  pdp_aux_lqr_backward runs the Riccati sweep only and
+ * leaves the gains (K_t | k_t) in `workspace`; pdp_aux_lqr_forward consumes them (e.g. again with
+ * different Xref/Uref or X0aux, without repeating the sweep). */
+int pdp_aux_lqr_backward(pdp_system_t* sys, int B, int H, const double* X, const double* U, const double* Lam,
+                         const double* theta, int theta_stride, void* workspace, size_t ws_bytes, int* status,
+                         pdp_stream_t stream);
+int pdp_aux_lqr_forward(pdp_system_t* sys, int B, int H, const double* X, const double* U, const double* theta,
+                        int theta_stride, const double* X0aux, int x0aux_stride, double* dXdtheta, double* dUdtheta,
+                        const double* Xref, const double* Uref, double* loss_dp, const void* workspace, size_t ws_bytes,
+                        int* status, pdp_stream_t stream);
+
 /* LQR.lqrSolver on caller-supplied matrices (PDP/PDP.py:446-615) for kind PDP_KIND_LQR modules of size
  * (n, m, r):  aux[B,H,NDENSE] in the per-step layout of pdp_aux_eval, term[B, n*n+n*r] = [hxx|hxe],
  * X0aux as in pdp_aux_lqr -> Xaux[B,H+1,n,r], Uaux[B,H,m,r].  Hessian blocks must be symmetric

@@ -171,7 +171,10 @@ class OCModuleSource:
     """Generates the CUDA source of an ``oc`` module from the symbolic optimal-control system."""
 
     def __init__(self, state: SX, control: SX, auxvar: SX, dyn: SX, path_cost: SX, final_cost: SX,
-                 chunk: int = 8, warps_per_block: int = 4):
+                 chunk: int = 8, warps_per_block: int = 4, min_blocks: int = 1, fwd_warps_per_block: int = 4,
+                 fwd_min_blocks: int = 1):
+        self.min_blocks = int(min_blocks)
+        self.wpbf, self.min_blocks_f = int(fwd_warps_per_block), int(fwd_min_blocks)
         self.x, self.u, self.th = state, control, auxvar
         self.n, self.m, self.r = state.numel(), control.numel(), auxvar.numel()
         self.nth = self.r
@@ -455,14 +458,22 @@ class OCModuleSource:
         off_ks = off_zt + zt_size
         off_quu = off_ks + ks_size
         off_th = off_quu + _even(m * m)
-        off_dl = off_th + _even(max(self.nth, 1))
-        warp_doubles = _even(off_dl + self.chunk * nm)
+        warp_doubles = _even(off_th + max(self.nth, 1))
+        # forward kernel: [CH][FLD] dynamics slots | OUT | KS | TH | DLC
+        fld = _even(max(self.nvar_s, 2))
+        foff_out = _even(self.chunk * fld)
+        foff_ks = foff_out + _even(n * r + m * r)
+        foff_th = foff_ks + ks_size
+        foff_dl = foff_th + _even(max(self.nth, 1))
+        fwarp_doubles = _even(foff_dl + max(self.chunk * nm, n))
         defs = {
             "N": n, "M": m, "R": r, "NS": ns, "NM": nm, "NVAR": self.nvar, "NVAR_S": self.nvar_s,
             "AUXLD": self.auxld, "CH": self.chunk, "WPB": self.wpb, "LDH": self.ldh, "LDZ": self.ldz,
             "LDK": self.ldk, "HD_SIZE": hd_size, "HD_DUMMY": ns * self.ldh,
-            "OFF_HD": off_hd, "OFF_ZT": off_zt, "OFF_KS": off_ks, "OFF_QUU": off_quu, "OFF_TH": off_th, "OFF_DL": off_dl,
-            "WARP_DOUBLES": warp_doubles, "NTH": self.nth, "NHS": nhs, "KH": kh, "GREC": (n + r) * m,
+            "OFF_HD": off_hd, "OFF_ZT": off_zt, "OFF_KS": off_ks, "OFF_QUU": off_quu, "OFF_TH": off_th,
+            "FLD": fld, "FOFF_OUT": foff_out, "FOFF_KS": foff_ks, "FOFF_TH": foff_th, "FOFF_DL": foff_dl,
+            "FWARP_DOUBLES": fwarp_doubles, "WPBF": getattr(self, "wpbf", 4), "MINBF": getattr(self, "min_blocks_f", 1),
+            "WARP_DOUBLES": warp_doubles, "NTH": self.nth, "MINB": getattr(self, "min_blocks", 1), "NHS": nhs, "KH": kh, "GREC": (n + r) * m,
             "NDENSE": n * n + n * m + n * r + n * n + n * m + n * r + m * n + m * m + m * r,
         }
         header = ["// GENERATED by pontryagin_differentiable_programming_b200/codegen.py -- do not edit",
@@ -488,8 +499,9 @@ class OCModuleSource:
         xdecl = "double " + ", ".join("x%d" % k for k in range(n)) + ";"
         xinit = "\n".join("    x%d = (X0a != nullptr && col >= 0) ? X0a[(size_t)(x0a_stride ? b : 0) * %d + %d * %d + col] : 0.0;"
                           % (k, n * r, k, r) for k in range(n))
-        gdecl = "double " + ", ".join("g%d = 0.0" % a for a in range(m)) + ";"
-        gload = self._gload()
+        gndecl = "double " + ", ".join("gn%d = 0.0" % a for a in range(m)) + ";"
+        gcur = "      const double " + ", ".join("g%d = gn%d" % (a, a) for a in range(m)) + ";"
+        gnload = self._gload()
         ks_store = "\n".join("        KS[%d + lane] = g%d;" % (a * self.ldk, a) for a in range(m))
         stage = "\n".join(["        OUT[%d + col] = n%d;" % (i * r, i) for i in range(n)] +
                           ["        OUT[%d + col] = u%d;" % (n * r + a * r, a) for a in range(m)])
@@ -499,7 +511,7 @@ class OCModuleSource:
         rep = {
             "@@TABLOAD@@": tabload, "@@HINIT@@": hinit, "@@SCATTER@@": scatter, "@@YDECL@@": ydecl,
             "@@TERM_INIT@@": "\n".join(term_init), "@@BACKWARD_STEP@@": self._backward_step(),
-            "@@XDECL@@": xdecl, "@@XINIT@@": xinit, "@@GDECL@@": gdecl, "@@GLOAD@@": gload,
+            "@@XDECL@@": xdecl, "@@XINIT@@": xinit, "@@GNDECL@@": gndecl, "@@GNLOAD@@": gnload, "@@GCUR@@": gcur,
             "@@KS_STORE@@": ks_store, "@@FORWARD_STEP@@": self._forward_step(), "@@STAGE@@": stage,
             "@@XCOPY@@": xcopy, "@@X0STAGE@@": x0stage,
             "@@DPACC@@": "\n".join(["        dpacc = fma(dl[%d], x%d, dpacc);" % (i, i) for i in range(n)] +
@@ -531,15 +543,15 @@ class OCModuleSource:
       if (lane < PDP_CH && te < H)
         pdp_f_aux_slots(Xb + (size_t)te * PDP_N, Ub + (size_t)te * PDP_M, Lb + (size_t)te * PDP_N, TH, auxc + lane * PDP_AUXLD);
     }""",
-            "@@EVAL_DYN@@": "        pdp_f_dyn_slots(Xb + (size_t)te * PDP_N, Ub + (size_t)te * PDP_M, TH, auxc + lane * PDP_AUXLD);",
+            "@@EVAL_DYN@@": "        pdp_f_dyn_slots(Xb + (size_t)te * PDP_N, Ub + (size_t)te * PDP_M, TH, auxc + lane * PDP_FLD);",
         }
 
     def _gload(self):
         m = self.m
         if m % 2 == 0:
-            return "\n".join("        { const double2 gg = *reinterpret_cast<const double2*>(gp + %d); g%d = gg.x; g%d = gg.y; }" % (a, a, a + 1)
+            return "\n".join("        { const double2 gg = *reinterpret_cast<const double2*>(gp + %d); gn%d = gg.x; gn%d = gg.y; }" % (a, a, a + 1)
                              for a in range(0, m, 2))
-        return "\n".join("        g%d = gp[%d];" % (a, a) for a in range(m))
+        return "\n".join("        gn%d = gp[%d];" % (a, a) for a in range(m))
 
     def key(self) -> str:
         return hashlib.sha256(self.source().encode()).hexdigest()[:20]
@@ -644,6 +656,7 @@ class LQRModuleSource(OCModuleSource):
         self.ns = self.n + self.m + self.r
         self.nth = 0
         self.chunk, self.wpb = int(chunk), int(warps_per_block)
+        self.min_blocks, self.wpbf, self.min_blocks_f = 1, int(warps_per_block), 1
         n, m, r, ns = self.n, self.m, self.r, self.ns
         nm = n + m
         oF, oG, oE = 0, n * n, n * n + n * m
@@ -712,315 +725,10 @@ class LQRModuleSource(OCModuleSource):
         return {
             "@@EVAL_TERM@@": "  for (int i = lane; i < PDP_N * PDP_N + PDP_N * PDP_R; i += 32) TB[i] = termrec[(size_t)b * (PDP_N * PDP_N + PDP_N * PDP_R) + i];",
             "@@EVAL_AUX_CHUNK@@": gather % {"NV": "PDP_NVAR"},
-            "@@EVAL_DYN@@": "        for (int e = 0; e < PDP_NVAR_S; ++e) auxc[lane * PDP_AUXLD + e] = auxrec[((size_t)b * H + te) * PDP_NDENSE + pdp_slot_src[e]];",
+            "@@EVAL_DYN@@": "        for (int e = 0; e < PDP_NVAR_S; ++e) auxc[lane * PDP_FLD + e] = auxrec[((size_t)b * H + te) * PDP_NDENSE + pdp_slot_src[e]];",
         }
 
 
-_K_ROLLOUT_AUXEVAL = r'''
-// =====================================================================================================
-// Kernel 1: forward rollout + cost + costate recursion (+ optional dH/du), one thread per trajectory.
-//   restates reference OCSys.ocSolver's rollout semantics at given controls (PDP.py:158-175) and the PMP
-//   costate recursion (PDP.py:203-209): Lam[t] = lambda_{t+1}, lambda_H = dh/dx(x_H).
-// =====================================================================================================
-extern "C" __global__ void __launch_bounds__(128)
-pdp_k_rollout_costate(int B, int H, const double* __restrict__ x0, const double* __restrict__ theta, int theta_stride,
-                      const double* __restrict__ U, double* __restrict__ X, double* __restrict__ Lam,
-                      double* __restrict__ cost, double* __restrict__ dHu, int* __restrict__ status)
-{
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  double x[PDP_N], xn[PDP_N], th[PDP_NTH], u[PDP_M], tmp[1];
-  #pragma unroll
-  for (int i = 0; i < PDP_NTH; ++i) th[i] = theta[(size_t)b * theta_stride + i];
-  #pragma unroll
-  for (int i = 0; i < PDP_N; ++i) x[i] = x0[(size_t)b * PDP_N + i];
-  double J = 0.0;
-  double* Xb = X + (size_t)b * (H + 1) * PDP_N;
-  const double* Ub = U + (size_t)b * H * PDP_M;
-  #pragma unroll 1
-  for (int t = 0; t < H; ++t) {
-    #pragma unroll
-    for (int i = 0; i < PDP_M; ++i) u[i] = Ub[t * PDP_M + i];
-    #pragma unroll
-    for (int i = 0; i < PDP_N; ++i) Xb[t * PDP_N + i] = x[i];
-    pdp_f_path_cost(x, u, th, tmp);
-    J += tmp[0];
-    pdp_f_dyn(x, u, th, xn);
-    #pragma unroll
-    for (int i = 0; i < PDP_N; ++i) x[i] = xn[i];
-  }
-  #pragma unroll
-  for (int i = 0; i < PDP_N; ++i) Xb[H * PDP_N + i] = x[i];
-  pdp_f_final_cost(x, th, tmp);
-  J += tmp[0];
-  if (cost) cost[b] = J;
-  bool bad = !isfinite(J);
-  if (Lam != nullptr) {
-    double lam[PDP_N], ln[PDP_N], gu[PDP_M];
-    double* Lb = Lam + (size_t)b * H * PDP_N;
-    pdp_f_dhx(x, th, lam);
-    #pragma unroll 1
-    for (int t = H - 1; t >= 0; --t) {
-      #pragma unroll
-      for (int i = 0; i < PDP_N; ++i) Lb[t * PDP_N + i] = lam[i];
-      #pragma unroll
-      for (int i = 0; i < PDP_N; ++i) x[i] = Xb[t * PDP_N + i];
-      #pragma unroll
-      for (int i = 0; i < PDP_M; ++i) u[i] = Ub[t * PDP_M + i];
-      if (dHu != nullptr) {
-        pdp_f_dHu(x, u, lam, th, gu);
-        #pragma unroll
-        for (int i = 0; i < PDP_M; ++i) dHu[((size_t)b * H + t) * PDP_M + i] = gu[i];
-      }
-      if (t > 0) {
-        pdp_f_dHx(x, u, lam, th, ln);
-        #pragma unroll
-        for (int i = 0; i < PDP_N; ++i) lam[i] = ln[i];
-      }
-    }
-  }
-  if (status && bad) atomicOr(&status[b], 1);
-}
-
-// =====================================================================================================
-// Kernel 2: dense auxiliary-system matrices (legacy getAuxSys API, PDP.py:272-314); one thread per (b, t).
-//   out layout per (b,t): [F n*n | G n*m | E n*r | Hxx | Hxu | Hxe | Hux | Huu | Hue], each row-major.
-//   term layout per b   : [hxx n*n | hxe n*r]
-// =====================================================================================================
-extern "C" __global__ void __launch_bounds__(128)
-pdp_k_aux_eval(int B, int H, const double* __restrict__ X, const double* __restrict__ U, const double* __restrict__ Lam,
-               const double* __restrict__ theta, int theta_stride, double* __restrict__ out, double* __restrict__ term)
-{
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * (H + 1)) return;
-  const int b = idx / (H + 1), t = idx - b * (H + 1);
-  const double* th = theta + (size_t)b * theta_stride;
-  if (t == H) {
-    if (term) pdp_f_terminal(X + ((size_t)b * (H + 1) + H) * PDP_N, th, term + (size_t)b * (PDP_N * PDP_N + PDP_N * PDP_R));
-    return;
-  }
-  pdp_f_aux_dense(X + ((size_t)b * (H + 1) + t) * PDP_N, U + ((size_t)b * H + t) * PDP_M, Lam + ((size_t)b * H + t) * PDP_N, th,
-                  out + ((size_t)b * H + t) * PDP_NDENSE);
-}
-
-'''
-
-_K_AUX_LQR = r'''
-// =====================================================================================================
-// Kernel 3: fused getAuxSys + LQR.lqrSolver (PDP.py:272-314 + 446-615), ONE WARP PER TRAJECTORY.
-//   Backward Riccati sweep in the stacked form (see DESIGN.md): lane j < NS owns row j of the stack
-//   Y = [P ; . ; W^T]  (rows 0..n-1: P, rows n+m..: columns of W).  Per step
-//       Z      = P [F|G|E] (+ W on the E block)              (structural non-zeros only)
-//       Q      = Hstack + Z^T [F|G]                           (n+m+r) x (n+m)
-//       K|k    = -Quu^{-1} [Qux|Que]   (every lane solves for the column it owns; LDL^T in registers)
-//       Y     <- Q(:,0:n) + Q(:,n:n+m) K
-//   The gains (K_t|k_t) are spilled to HBM and consumed by the forward pass
-//       U_t = K_t X_t + k_t,  X_{t+1} = F_t X_t + G_t U_t + E_t   ->  dX/dtheta, dU/dtheta.
-//   The auxiliary matrices are evaluated in chunks of PDP_CH steps with lanes = time steps.
-// =====================================================================================================
-extern "C" __global__ void __launch_bounds__(PDP_WPB * 32)
-pdp_k_aux_lqr(int B, int H, const double* __restrict__ X, const double* __restrict__ U, const double* __restrict__ Lam,
-              const double* __restrict__ theta, int theta_stride, const double* __restrict__ X0a, int x0a_stride,
-              double* __restrict__ dX, double* __restrict__ dU, double* __restrict__ gains,
-              const double* __restrict__ Xref, const double* __restrict__ Uref, double* __restrict__ loss_dp,
-              const double* __restrict__ auxrec, const double* __restrict__ termrec, int fwd_only,
-              int* __restrict__ status)
-{
-  extern __shared__ __align__(16) double pdp_smem[];
-  const int lane = threadIdx.x & 31;
-  const int b = blockIdx.x * PDP_WPB + (threadIdx.x >> 5);
-  if (b >= B) return;
-  double* auxc = pdp_smem + (size_t)(threadIdx.x >> 5) * PDP_WARP_DOUBLES;   // [CH][AUXLD]
-  double* Hd = auxc + PDP_OFF_HD;                                            // dense Hamiltonian stack (+1 dummy)
-  double* ZT = auxc + PDP_OFF_ZT;                                            // Z^T staging / output staging
-  double* KS = auxc + PDP_OFF_KS;                                            // K (m x n)
-  double* QUU = auxc + PDP_OFF_QUU;                                          // m x m
-  double* TH = auxc + PDP_OFF_TH;                                            // theta
-  double* DLC = auxc + PDP_OFF_DL;                                           // [CH][n+m] (x - xref | u - uref) per chunk step
-  double* OUT = ZT;
-  double* TB = auxc;                                                         // terminal buffer aliases the chunk buffer
-  const int lrow = lane < PDP_NS ? lane : 0;
-  const int gslot = lane < PDP_N ? lane : ((lane >= PDP_NM && lane < PDP_NS) ? lane - PDP_M : -1);
-  const double* Xb = X + (size_t)b * (H + 1) * PDP_N;
-  const double* Ub = U + (size_t)b * H * PDP_M;
-  const double* Lb = Lam + (size_t)b * H * PDP_N;
-  bool bad = false;
-@@TABLOAD@@
-  for (int i = lane; i < PDP_HD_SIZE; i += 32) Hd[i] = 0.0;
-  if (theta != nullptr) for (int i = lane; i < PDP_NTH; i += 32) TH[i] = theta[(size_t)b * theta_stride + i];
-  __syncwarp();
-  {
-@@HINIT@@
-  }
-  // ---- terminal condition P = hxx(x_H), W = hxe(x_H)  (PDP.py:561-562)
-  if (!fwd_only) {
-@@EVAL_TERM@@
-  }
-  __syncwarp();
-  @@YDECL@@
-  {
-@@TERM_INIT@@
-  }
-  __syncwarp();
-  // ---- backward sweep (skipped when the caller supplies the gains: forward-only recursions)
-  #pragma unroll 1
-  for (int tc = fwd_only ? -1 : ((H - 1) / PDP_CH) * PDP_CH; tc >= 0; tc -= PDP_CH) {
-@@EVAL_AUX_CHUNK@@
-    __syncwarp();
-    const int thi = (tc + PDP_CH < H ? tc + PDP_CH : H) - 1;
-    #pragma unroll 1
-    for (int t = thi; t >= tc; --t) {
-      const double* ar = auxc + (t - tc) * PDP_AUXLD;
-@@SCATTER@@
-      __syncwarp();
-@@BACKWARD_STEP@@
-      __syncwarp();
-    }
-  }
-  if (status && bad) { if (lane == 0) atomicOr(&status[b], 2); }
-  // ---- forward pass of the auxiliary system: lane n+c owns column c of X_t (n x r)
-  const int col = (lane >= PDP_N && lane < PDP_N + PDP_R) ? lane - PDP_N : -1;
-  const int fslot = lane < PDP_N + PDP_R ? lane : -1;
-  @@XDECL@@
-  {
-@@XINIT@@
-  }
-  double* dXb = dX ? dX + (size_t)b * (H + 1) * PDP_N * PDP_R : nullptr;
-  double* dUb = dU ? dU + (size_t)b * H * PDP_M * PDP_R : nullptr;
-  __syncwarp();
-  if (dXb) {
-    if (col >= 0) {
-@@X0STAGE@@
-    }
-    __syncwarp();
-    for (int k = lane; k < PDP_N * PDP_R; k += 32) dXb[k] = OUT[k];
-    __syncwarp();
-  }
-  bool badx = false;
-  const bool fused = (loss_dp != nullptr) && (Xref != nullptr);
-  const double* Xr = fused ? Xref + (size_t)b * (H + 1) * PDP_N : nullptr;
-  const double* Ur = (fused && Uref != nullptr) ? Uref + (size_t)b * H * PDP_M : nullptr;
-  double dpacc = 0.0, lossacc = 0.0;
-  #pragma unroll 1
-  for (int tc = 0; tc < H; tc += PDP_CH) {
-    {
-      const int te = tc + lane;
-      if (lane < PDP_CH && te < H) {
-@@EVAL_DYN@@
-        if (fused) {
-          // loss / chain rule of the IRL scripts (reference Examples/IRL/quadrotor/uav_PDP.py:67-75)
-          #pragma unroll
-          for (int i = 0; i < PDP_N; ++i) {
-            const double d = Xb[(size_t)te * PDP_N + i] - Xr[(size_t)te * PDP_N + i];
-            DLC[lane * PDP_NM + i] = d; lossacc = fma(d, d, lossacc);
-          }
-          #pragma unroll
-          for (int i = 0; i < PDP_M; ++i) {
-            const double d = Ur ? Ub[(size_t)te * PDP_M + i] - Ur[(size_t)te * PDP_M + i] : 0.0;
-            DLC[lane * PDP_NM + PDP_N + i] = d; lossacc = fma(d, d, lossacc);
-          }
-        }
-      }
-    }
-    __syncwarp();
-    const int tend = tc + PDP_CH < H ? tc + PDP_CH : H;
-    #pragma unroll 1
-    for (int t = tc; t < tend; ++t) {
-      const double* ar = auxc + (t - tc) * PDP_AUXLD;
-      @@GDECL@@
-      if (fslot >= 0) {
-        const double* gp = gains + ((size_t)b * H + t) * PDP_GREC + fslot * PDP_M;
-@@GLOAD@@
-      }
-      if (lane < PDP_N) {
-@@KS_STORE@@
-      }
-      __syncwarp();
-@@FORWARD_STEP@@
-      if (fused) {
-        const double* dl = DLC + (t - tc) * PDP_NM;
-@@DPACC@@
-      }
-      if (col >= 0) {
-@@STAGE@@
-      }
-      __syncwarp();
-      if (dXb) for (int k = lane; k < PDP_N * PDP_R; k += 32) dXb[(size_t)(t + 1) * PDP_N * PDP_R + k] = OUT[k];
-      if (dUb) for (int k = lane; k < PDP_M * PDP_R; k += 32) dUb[(size_t)t * PDP_M * PDP_R + k] = OUT[PDP_N * PDP_R + k];
-      __syncwarp();
-@@XCOPY@@
-    }
-  }
-  {
-    double chk = 0.0;
-@@XCHK@@
-    badx = !isfinite(chk);
-    if (status && col >= 0 && badx) atomicOr(&status[b], 1);
-  }
-  if (fused) {
-    // terminal term of the chain rule and of the loss
-    #pragma unroll
-    for (int i = 0; i < PDP_N; ++i) {
-      const double d = Xb[(size_t)H * PDP_N + i] - Xr[(size_t)H * PDP_N + i];
-      if (lane == 0) lossacc = fma(d, d, lossacc);
-      DLC[i] = d;
-    }
-    __syncwarp();
-    {
-      const double* dl = DLC;
-@@DPTERM@@
-    }
-    #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) lossacc += __shfl_xor_sync(0xffffffffu, lossacc, o);
-    if (lane == 0) loss_dp[(size_t)b * (PDP_R + 1)] = lossacc;
-    if (col >= 0) loss_dp[(size_t)b * (PDP_R + 1) + 1 + col] = dpacc;
-  }
-}
-
-'''
-
-_K_LAUNCH_COMMON = r'''
-// =====================================================================================================
-// Host-side launchers (C ABI of the module; bound by csrc/pdp_b200.cpp through dlopen)
-// =====================================================================================================
-extern "C" void pdpmod_info(int* out) {
-  out[0] = PDP_KIND;
-  out[1] = PDP_N; out[2] = PDP_M; out[3] = PDP_R; out[4] = PDP_NVAR; out[5] = PDP_NVAR_S; out[11] = PDP_NTH;
-  out[6] = PDP_GREC; out[7] = PDP_NDENSE; out[8] = PDP_CH; out[9] = PDP_WPB; out[10] = PDP_WARP_DOUBLES;
-}
-
-extern "C" int pdpmod_rollout_costate(int B, int H, const double* x0, const double* theta, int theta_stride, const double* U,
-                                      double* X, double* Lam, double* cost, double* dHu, int* status, cudaStream_t st) {
-  if (B <= 0) return 0;
-  pdp_k_rollout_costate<<<(B + 127) / 128, 128, 0, st>>>(B, H, x0, theta, theta_stride, U, X, Lam, cost, dHu, status);
-  return (int)cudaGetLastError();
-}
-
-extern "C" int pdpmod_aux_eval(int B, int H, const double* X, const double* U, const double* Lam, const double* theta,
-                               int theta_stride, double* out, double* term, cudaStream_t st) {
-  if (B <= 0) return 0;
-  const int total = B * (H + 1);
-  pdp_k_aux_eval<<<(total + 127) / 128, 128, 0, st>>>(B, H, X, U, Lam, theta, theta_stride, out, term);
-  return (int)cudaGetLastError();
-}
-
-'''
-
-_K_LAUNCH_LQR = r'''
-extern "C" int pdpmod_aux_lqr(int B, int H, const double* X, const double* U, const double* Lam, const double* theta,
-                              int theta_stride, const double* X0a, int x0a_stride, double* dX, double* dU, double* gains,
-                              const double* Xref, const double* Uref, double* loss_dp,
-                              const double* auxrec, const double* termrec, int fwd_only, int* status, cudaStream_t st) {
-  if (B <= 0) return 0;
-  static bool configured = false;
-  const size_t smem = (size_t)PDP_WPB * PDP_WARP_DOUBLES * sizeof(double);
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(pdp_k_aux_lqr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
-  pdp_k_aux_lqr<<<(B + PDP_WPB - 1) / PDP_WPB, PDP_WPB * 32, smem, st>>>(B, H, X, U, Lam, theta, theta_stride, X0a, x0a_stride,
-                                                                         dX, dU, gains, Xref, Uref, loss_dp, auxrec, termrec, fwd_only, status);
-  return (int)cudaGetLastError();
-}
-'''
+from .kernel_templates import (  # noqa: E402
+    K_AUX_LQR as _K_AUX_LQR, K_LAUNCH_COMMON as _K_LAUNCH_COMMON, K_LAUNCH_LQR as _K_LAUNCH_LQR,
+    K_ROLLOUT_AUXEVAL as _K_ROLLOUT_AUXEVAL)

@@ -136,7 +136,7 @@ int pdp_rollout_costate(pdp_system_t* sys, int B, int H, const double* x0, const
   return PDP_OK;
 }
 
-int pdp_aux_lqr(pdp_system_t* sys, int B, int H, const double* X, const double* U, const double* Lam,
+static int aux_lqr_phases(int phases, pdp_system_t* sys, int B, int H, const double* X, const double* U, const double* Lam,
                 const double* theta, int theta_stride, const double* X0aux, int x0aux_stride,
                 double* dXdtheta, double* dUdtheta, const double* Xref, const double* Uref, double* loss_dp,
                 void* workspace, size_t ws_bytes, int* status, pdp_stream_t stream) {
@@ -148,10 +148,33 @@ int pdp_aux_lqr(pdp_system_t* sys, int B, int H, const double* X, const double* 
     return fail(PDP_ERR_WORKSPACE, "pdp_aux_lqr: workspace too small (%zu < %zu)", ws_bytes,
                 pdp_workspace_bytes(sys, PDP_OP_AUX_LQR, B, H));
   int e = sys->aux_lqr(B, H, X, U, Lam, theta, theta_stride, X0aux, x0aux_stride, dXdtheta, dUdtheta,
-                       reinterpret_cast<double*>(workspace), Xref, Uref, loss_dp, nullptr, nullptr, 0, status,
+                       reinterpret_cast<double*>(workspace), Xref, Uref, loss_dp, nullptr, nullptr, phases, status,
                        (cudaStream_t)stream);
   if (e) return fail(PDP_ERR_CUDA, "pdp_aux_lqr: CUDA error %d (%s)", e, cudaGetErrorString((cudaError_t)e));
   return PDP_OK;
+}
+
+int pdp_aux_lqr(pdp_system_t* sys, int B, int H, const double* X, const double* U, const double* Lam,
+                const double* theta, int theta_stride, const double* X0aux, int x0aux_stride,
+                double* dXdtheta, double* dUdtheta, const double* Xref, const double* Uref, double* loss_dp,
+                void* workspace, size_t ws_bytes, int* status, pdp_stream_t stream) {
+  return aux_lqr_phases(3, sys, B, H, X, U, Lam, theta, theta_stride, X0aux, x0aux_stride, dXdtheta, dUdtheta, Xref, Uref,
+                        loss_dp, workspace, ws_bytes, status, stream);
+}
+
+int pdp_aux_lqr_backward(pdp_system_t* sys, int B, int H, const double* X, const double* U, const double* Lam,
+                         const double* theta, int theta_stride, void* workspace, size_t ws_bytes, int* status,
+                         pdp_stream_t stream) {
+  return aux_lqr_phases(1, sys, B, H, X, U, Lam, theta, theta_stride, nullptr, 0, nullptr, nullptr, nullptr, nullptr,
+                        nullptr, workspace, ws_bytes, status, stream);
+}
+
+int pdp_aux_lqr_forward(pdp_system_t* sys, int B, int H, const double* X, const double* U, const double* theta,
+                        int theta_stride, const double* X0aux, int x0aux_stride, double* dXdtheta, double* dUdtheta,
+                        const double* Xref, const double* Uref, double* loss_dp, const void* workspace, size_t ws_bytes,
+                        int* status, pdp_stream_t stream) {
+  return aux_lqr_phases(2, sys, B, H, X, U, X /*unused*/, theta, theta_stride, X0aux, x0aux_stride, dXdtheta, dUdtheta,
+                        Xref, Uref, loss_dp, const_cast<void*>(workspace), ws_bytes, status, stream);
 }
 
 int pdp_lqr_dense(pdp_system_t* sys, int B, int H, const double* aux, const double* term, const double* X0aux,
@@ -163,7 +186,7 @@ int pdp_lqr_dense(pdp_system_t* sys, int B, int H, const double* aux, const doub
   if (ws_bytes < pdp_workspace_bytes(sys, PDP_OP_AUX_LQR, B, H) || (B > 0 && !workspace))
     return fail(PDP_ERR_WORKSPACE, "pdp_lqr_dense: workspace too small");
   int e = sys->aux_lqr(B, H, nullptr, nullptr, nullptr, nullptr, 0, X0aux, x0aux_stride, Xaux, Uaux,
-                       reinterpret_cast<double*>(workspace), nullptr, nullptr, nullptr, aux, term, forward_only ? 1 : 0,
+                       reinterpret_cast<double*>(workspace), nullptr, nullptr, nullptr, aux, term, forward_only ? 2 : 3,
                        status, (cudaStream_t)stream);
   if (e) return fail(PDP_ERR_CUDA, "pdp_lqr_dense: CUDA error %d (%s)", e, cudaGetErrorString((cudaError_t)e));
   return PDP_OK;

@@ -35,8 +35,10 @@ def _chk(t, shape, name, device):
 class OCSystem:
     """Compiled optimal-control system: rollout/costate, fused getAuxSys+lqrSolver, dense aux eval."""
 
-    def __init__(self, state, control, auxvar, dyn, path_cost, final_cost, chunk=8, warps_per_block=4, verbose=False):
-        self.src = codegen.OCModuleSource(state, control, auxvar, dyn, path_cost, final_cost, chunk, warps_per_block)
+    def __init__(self, state, control, auxvar, dyn, path_cost, final_cost, chunk=8, warps_per_block=4, min_blocks=1,
+                 fwd_warps_per_block=4, fwd_min_blocks=1, verbose=False):
+        self.src = codegen.OCModuleSource(state, control, auxvar, dyn, path_cost, final_cost, chunk, warps_per_block,
+                                          min_blocks, fwd_warps_per_block, fwd_min_blocks)
         self.n, self.m, self.r = self.src.n, self.src.m, self.src.r
         self.module_path = build.compile_module(self.src.source(), self.src.key(), verbose=verbose)
         self._handle = None
@@ -95,8 +97,10 @@ class OCSystem:
             out["dHu"] = dHu
         return out
 
-    def aux_lqr(self, X, U, Lam, theta, X0aux=None, want_traj=True, Xref=None, Uref=None, status=None, out=None):
-        """Fused getAuxSys + lqrSolver: -> dX[B,H+1,n,r], dU[B,H,m,r] and/or loss_dp[B,r+1]."""
+    def aux_lqr(self, X, U, Lam, theta, X0aux=None, want_traj=True, Xref=None, Uref=None, status=None, out=None,
+                phase="both"):
+        """Fused getAuxSys + lqrSolver: -> dX[B,H+1,n,r], dU[B,H,m,r] and/or loss_dp[B,r+1].
+        ``phase`` = "both" | "backward" (Riccati sweep only, gains stay in the workspace) | "forward"."""
         require_cuda()
         dev = X.device
         B, H = U.shape[0], U.shape[1]
@@ -131,9 +135,18 @@ class OCSystem:
         lib = self.handle.lib
         st = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
-            backend.check(lib.pdp_aux_lqr(self.handle.ptr, B, H, _ptr(X), _ptr(U), _ptr(Lam), _ptr(theta), ts,
-                                          _ptr(X0aux), x0s, _ptr(dX), _ptr(dU), _ptr(Xref), _ptr(Uref), _ptr(ldp),
-                                          _ptr(ws), ws.numel(), _ptr(status), st), "pdp_aux_lqr")
+            if phase == "backward":
+                backend.check(lib.pdp_aux_lqr_backward(self.handle.ptr, B, H, _ptr(X), _ptr(U), _ptr(Lam), _ptr(theta), ts,
+                                                       _ptr(ws), ws.numel(), _ptr(status), st), "pdp_aux_lqr_backward")
+            elif phase == "forward":
+                backend.check(lib.pdp_aux_lqr_forward(self.handle.ptr, B, H, _ptr(X), _ptr(U), _ptr(theta), ts,
+                                                      _ptr(X0aux), x0s, _ptr(dX), _ptr(dU), _ptr(Xref), _ptr(Uref),
+                                                      _ptr(ldp), _ptr(ws), ws.numel(), _ptr(status), st),
+                              "pdp_aux_lqr_forward")
+            else:
+                backend.check(lib.pdp_aux_lqr(self.handle.ptr, B, H, _ptr(X), _ptr(U), _ptr(Lam), _ptr(theta), ts,
+                                              _ptr(X0aux), x0s, _ptr(dX), _ptr(dU), _ptr(Xref), _ptr(Uref), _ptr(ldp),
+                                              _ptr(ws), ws.numel(), _ptr(status), st), "pdp_aux_lqr")
         return res
 
     def sweep(self, x0, theta, U, Xref=None, Uref=None, want_traj=True, status=None, out=None):

@@ -1,0 +1,343 @@
+"""Hand-written CUDA kernel templates of the OC / LQR modules.
+
+``codegen.py`` fills the ``@@...@@`` holes with generated straight-line code (structural non-zeros of the
+system at hand) and prepends the ``PDP_*`` constants.  See DESIGN.md for the kernel designs."""
+
+K_ROLLOUT_AUXEVAL = r'''
+// =====================================================================================================
+// Kernel 1: forward rollout + cost + costate recursion (+ optional dH/du), one thread per trajectory.
+//   restates reference OCSys.ocSolver's rollout semantics at given controls (PDP.py:158-175) and the PMP
+//   costate recursion (PDP.py:203-209): Lam[t] = lambda_{t+1}, lambda_H = dh/dx(x_H).
+// =====================================================================================================
+extern "C" __global__ void __launch_bounds__(128)
+pdp_k_rollout_costate(int B, int H, const double* __restrict__ x0, const double* __restrict__ theta, int theta_stride,
+                      const double* __restrict__ U, double* __restrict__ X, double* __restrict__ Lam,
+                      double* __restrict__ cost, double* __restrict__ dHu, int* __restrict__ status)
+{
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double x[PDP_N], xn[PDP_N], th[PDP_NTH], u[PDP_M], tmp[1];
+  #pragma unroll
+  for (int i = 0; i < PDP_NTH; ++i) th[i] = theta[(size_t)b * theta_stride + i];
+  #pragma unroll
+  for (int i = 0; i < PDP_N; ++i) x[i] = x0[(size_t)b * PDP_N + i];
+  double J = 0.0;
+  double* Xb = X + (size_t)b * (H + 1) * PDP_N;
+  const double* Ub = U + (size_t)b * H * PDP_M;
+  #pragma unroll 1
+  for (int t = 0; t < H; ++t) {
+    #pragma unroll
+    for (int i = 0; i < PDP_M; ++i) u[i] = Ub[t * PDP_M + i];
+    #pragma unroll
+    for (int i = 0; i < PDP_N; ++i) Xb[t * PDP_N + i] = x[i];
+    pdp_f_path_cost(x, u, th, tmp);
+    J += tmp[0];
+    pdp_f_dyn(x, u, th, xn);
+    #pragma unroll
+    for (int i = 0; i < PDP_N; ++i) x[i] = xn[i];
+  }
+  #pragma unroll
+  for (int i = 0; i < PDP_N; ++i) Xb[H * PDP_N + i] = x[i];
+  pdp_f_final_cost(x, th, tmp);
+  J += tmp[0];
+  if (cost) cost[b] = J;
+  bool bad = !isfinite(J);
+  if (Lam != nullptr) {
+    double lam[PDP_N], ln[PDP_N], gu[PDP_M];
+    double* Lb = Lam + (size_t)b * H * PDP_N;
+    pdp_f_dhx(x, th, lam);
+    #pragma unroll 1
+    for (int t = H - 1; t >= 0; --t) {
+      #pragma unroll
+      for (int i = 0; i < PDP_N; ++i) Lb[t * PDP_N + i] = lam[i];
+      #pragma unroll
+      for (int i = 0; i < PDP_N; ++i) x[i] = Xb[t * PDP_N + i];
+      #pragma unroll
+      for (int i = 0; i < PDP_M; ++i) u[i] = Ub[t * PDP_M + i];
+      if (dHu != nullptr) {
+        pdp_f_dHu(x, u, lam, th, gu);
+        #pragma unroll
+        for (int i = 0; i < PDP_M; ++i) dHu[((size_t)b * H + t) * PDP_M + i] = gu[i];
+      }
+      if (t > 0) {
+        pdp_f_dHx(x, u, lam, th, ln);
+        #pragma unroll
+        for (int i = 0; i < PDP_N; ++i) lam[i] = ln[i];
+      }
+    }
+  }
+  if (status && bad) atomicOr(&status[b], 1);
+}
+
+// =====================================================================================================
+// Kernel 2: dense auxiliary-system matrices (legacy getAuxSys API, PDP.py:272-314); one thread per (b, t).
+//   out layout per (b,t): [F n*n | G n*m | E n*r | Hxx | Hxu | Hxe | Hux | Huu | Hue], each row-major.
+//   term layout per b   : [hxx n*n | hxe n*r]
+// =====================================================================================================
+extern "C" __global__ void __launch_bounds__(128)
+pdp_k_aux_eval(int B, int H, const double* __restrict__ X, const double* __restrict__ U, const double* __restrict__ Lam,
+               const double* __restrict__ theta, int theta_stride, double* __restrict__ out, double* __restrict__ term)
+{
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * (H + 1)) return;
+  const int b = idx / (H + 1), t = idx - b * (H + 1);
+  const double* th = theta + (size_t)b * theta_stride;
+  if (t == H) {
+    if (term) pdp_f_terminal(X + ((size_t)b * (H + 1) + H) * PDP_N, th, term + (size_t)b * (PDP_N * PDP_N + PDP_N * PDP_R));
+    return;
+  }
+  pdp_f_aux_dense(X + ((size_t)b * (H + 1) + t) * PDP_N, U + ((size_t)b * H + t) * PDP_M, Lam + ((size_t)b * H + t) * PDP_N, th,
+                  out + ((size_t)b * H + t) * PDP_NDENSE);
+}
+
+'''
+
+K_AUX_LQR = r'''
+// =====================================================================================================
+// Kernels 3a/3b: fused getAuxSys + LQR.lqrSolver (PDP.py:272-314 + 446-615), ONE WARP PER TRAJECTORY.
+//   3a  pdp_k_aux_lqr_bwd: backward Riccati sweep in the stacked form (see DESIGN.md): lane j < NS owns
+//       row j of the stack  Y = [P ; . ; W^T]  (rows 0..n-1: P, rows n+m..: columns of W).  Per step
+//         Z      = P [F|G|E] (+ W on the E block)              (structural non-zeros only)
+//         Q      = Hstack + Z^T [F|G]                           (n+m+r) x (n+m)
+//         K|k    = -Quu^{-1} [Qux|Que]   (every lane solves for the column it owns; LDL^T in registers)
+//         Y     <- Q(:,0:n) + Q(:,n:n+m) K
+//       and the gains (K_t|k_t) are spilled to HBM.
+//   3b  pdp_k_aux_lqr_fwd: forward pass  U_t = K_t X_t + k_t,  X_{t+1} = F_t X_t + G_t U_t + E_t
+//       -> dX/dtheta, dU/dtheta (and/or the fused IRL loss / chain rule), lane n+c owns column c.
+//   The auxiliary matrices are evaluated in chunks of PDP_CH steps with lanes = time steps; they never
+//   exist in HBM.  Two kernels (not one) so that each gets its own register allocation / occupancy.
+// =====================================================================================================
+extern "C" __global__ void __launch_bounds__(PDP_WPB * 32, PDP_MINB)
+pdp_k_aux_lqr_bwd(int B, int H, const double* __restrict__ X, const double* __restrict__ U, const double* __restrict__ Lam,
+                  const double* __restrict__ theta, int theta_stride, double* __restrict__ gains,
+                  const double* __restrict__ auxrec, const double* __restrict__ termrec, int* __restrict__ status)
+{
+  extern __shared__ __align__(16) double pdp_smem[];
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * PDP_WPB + (threadIdx.x >> 5);
+  if (b >= B) return;
+  double* auxc = pdp_smem + (size_t)(threadIdx.x >> 5) * PDP_WARP_DOUBLES;   // [CH][AUXLD]
+  double* Hd = auxc + PDP_OFF_HD;                                            // dense Hamiltonian stack (+1 dummy)
+  double* ZT = auxc + PDP_OFF_ZT;                                            // Z^T staging
+  double* KS = auxc + PDP_OFF_KS;                                            // K (m x n)
+  double* QUU = auxc + PDP_OFF_QUU;                                          // m x m
+  double* TH = auxc + PDP_OFF_TH;                                            // theta
+  double* TB = auxc;                                                         // terminal buffer aliases the chunk buffer
+  const int lrow = lane < PDP_NS ? lane : 0;
+  const int gslot = lane < PDP_N ? lane : ((lane >= PDP_NM && lane < PDP_NS) ? lane - PDP_M : -1);
+  const double* Xb = X + (size_t)b * (H + 1) * PDP_N;
+  const double* Ub = U + (size_t)b * H * PDP_M;
+  const double* Lb = Lam + (size_t)b * H * PDP_N;
+  (void)Xb; (void)Ub; (void)Lb;
+  bool bad = false;
+@@TABLOAD@@
+  for (int i = lane; i < PDP_HD_SIZE; i += 32) Hd[i] = 0.0;
+  if (theta != nullptr) for (int i = lane; i < PDP_NTH; i += 32) TH[i] = theta[(size_t)b * theta_stride + i];
+  __syncwarp();
+  {
+@@HINIT@@
+  }
+  // ---- terminal condition P = hxx(x_H), W = hxe(x_H)  (PDP.py:561-562)
+@@EVAL_TERM@@
+  __syncwarp();
+  @@YDECL@@
+  {
+@@TERM_INIT@@
+  }
+  __syncwarp();
+  #pragma unroll 1
+  for (int tc = ((H - 1) / PDP_CH) * PDP_CH; tc >= 0; tc -= PDP_CH) {
+@@EVAL_AUX_CHUNK@@
+    __syncwarp();
+    const int thi = (tc + PDP_CH < H ? tc + PDP_CH : H) - 1;
+    #pragma unroll 1
+    for (int t = thi; t >= tc; --t) {
+      const double* ar = auxc + (t - tc) * PDP_AUXLD;
+@@SCATTER@@
+      __syncwarp();
+@@BACKWARD_STEP@@
+      __syncwarp();
+    }
+  }
+  if (status && bad) { if (lane == 0) atomicOr(&status[b], 2); }
+}
+
+extern "C" __global__ void __launch_bounds__(PDP_WPBF * 32, PDP_MINBF)
+pdp_k_aux_lqr_fwd(int B, int H, const double* __restrict__ X, const double* __restrict__ U,
+                  const double* __restrict__ theta, int theta_stride, const double* __restrict__ X0a, int x0a_stride,
+                  double* __restrict__ dX, double* __restrict__ dU, const double* __restrict__ gains,
+                  const double* __restrict__ Xref, const double* __restrict__ Uref, double* __restrict__ loss_dp,
+                  const double* __restrict__ auxrec, int* __restrict__ status)
+{
+  extern __shared__ __align__(16) double pdp_smem[];
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * PDP_WPBF + (threadIdx.x >> 5);
+  if (b >= B) return;
+  double* auxc = pdp_smem + (size_t)(threadIdx.x >> 5) * PDP_FWARP_DOUBLES;  // [CH][FLD] dynamics-Jacobian slots
+  double* OUT = auxc + PDP_FOFF_OUT;                                         // output staging (n*r + m*r)
+  double* KS = auxc + PDP_FOFF_KS;                                           // K (m x n)
+  double* TH = auxc + PDP_FOFF_TH;                                           // theta
+  double* DLC = auxc + PDP_FOFF_DL;                                          // [CH][n+m] (x - xref | u - uref)
+  const double* Xb = X + (size_t)b * (H + 1) * PDP_N;
+  const double* Ub = U + (size_t)b * H * PDP_M;
+  (void)Xb; (void)Ub;
+  if (theta != nullptr) for (int i = lane; i < PDP_NTH; i += 32) TH[i] = theta[(size_t)b * theta_stride + i];
+  const int col = (lane >= PDP_N && lane < PDP_N + PDP_R) ? lane - PDP_N : -1;
+  const int fslot = lane < PDP_N + PDP_R ? lane : -1;
+  @@XDECL@@
+  {
+@@XINIT@@
+  }
+  double* dXb = dX ? dX + (size_t)b * (H + 1) * PDP_N * PDP_R : nullptr;
+  double* dUb = dU ? dU + (size_t)b * H * PDP_M * PDP_R : nullptr;
+  const bool want_out = (dXb != nullptr) || (dUb != nullptr);
+  __syncwarp();
+  if (dXb) {
+    if (col >= 0) {
+@@X0STAGE@@
+    }
+    __syncwarp();
+    for (int k = lane; k < PDP_N * PDP_R; k += 32) dXb[k] = OUT[k];
+    __syncwarp();
+  }
+  const bool fused = (loss_dp != nullptr) && (Xref != nullptr);
+  const double* Xr = fused ? Xref + (size_t)b * (H + 1) * PDP_N : nullptr;
+  const double* Ur = (fused && Uref != nullptr) ? Uref + (size_t)b * H * PDP_M : nullptr;
+  double dpacc = 0.0, lossacc = 0.0;
+  // software prefetch of the gain record of the next step
+  @@GNDECL@@
+  if (fslot >= 0) {
+    const double* gp = gains + ((size_t)b * H) * PDP_GREC + fslot * PDP_M;
+@@GNLOAD@@
+  }
+  #pragma unroll 1
+  for (int tc = 0; tc < H; tc += PDP_CH) {
+    {
+      const int te = tc + lane;
+      if (lane < PDP_CH && te < H) {
+@@EVAL_DYN@@
+        if (fused) {
+          // loss / chain rule of the IRL scripts (reference Examples/IRL/quadrotor/uav_PDP.py:67-75)
+          #pragma unroll
+          for (int i = 0; i < PDP_N; ++i) {
+            const double d = Xb[(size_t)te * PDP_N + i] - Xr[(size_t)te * PDP_N + i];
+            DLC[lane * PDP_NM + i] = d; lossacc = fma(d, d, lossacc);
+          }
+          #pragma unroll
+          for (int i = 0; i < PDP_M; ++i) {
+            const double d = Ur ? Ub[(size_t)te * PDP_M + i] - Ur[(size_t)te * PDP_M + i] : 0.0;
+            DLC[lane * PDP_NM + PDP_N + i] = d; lossacc = fma(d, d, lossacc);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    const int tend = tc + PDP_CH < H ? tc + PDP_CH : H;
+    #pragma unroll 1
+    for (int t = tc; t < tend; ++t) {
+      const double* ar = auxc + (t - tc) * PDP_FLD;
+@@GCUR@@
+      if (fslot >= 0 && t + 1 < H) {
+        const double* gp = gains + ((size_t)b * H + t + 1) * PDP_GREC + fslot * PDP_M;
+@@GNLOAD@@
+      }
+      if (lane < PDP_N) {
+@@KS_STORE@@
+      }
+      __syncwarp();
+@@FORWARD_STEP@@
+      if (fused) {
+        const double* dl = DLC + (t - tc) * PDP_NM;
+@@DPACC@@
+      }
+      if (want_out) {
+        if (col >= 0) {
+@@STAGE@@
+        }
+        __syncwarp();
+        if (dXb) for (int k = lane; k < PDP_N * PDP_R; k += 32) dXb[(size_t)(t + 1) * PDP_N * PDP_R + k] = OUT[k];
+        if (dUb) for (int k = lane; k < PDP_M * PDP_R; k += 32) dUb[(size_t)t * PDP_M * PDP_R + k] = OUT[PDP_N * PDP_R + k];
+      }
+      __syncwarp();
+@@XCOPY@@
+    }
+  }
+  {
+    double chk = 0.0;
+@@XCHK@@
+    if (status && col >= 0 && !isfinite(chk)) atomicOr(&status[b], 1);
+  }
+  if (fused) {
+    // terminal term of the chain rule and of the loss
+    #pragma unroll
+    for (int i = 0; i < PDP_N; ++i) {
+      const double d = Xb[(size_t)H * PDP_N + i] - Xr[(size_t)H * PDP_N + i];
+      if (lane == 0) lossacc = fma(d, d, lossacc);
+      DLC[i] = d;
+    }
+    __syncwarp();
+    {
+      const double* dl = DLC;
+@@DPTERM@@
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lossacc += __shfl_xor_sync(0xffffffffu, lossacc, o);
+    if (lane == 0) loss_dp[(size_t)b * (PDP_R + 1)] = lossacc;
+    if (col >= 0) loss_dp[(size_t)b * (PDP_R + 1) + 1 + col] = dpacc;
+  }
+}
+'''
+
+K_LAUNCH_COMMON = r'''
+// =====================================================================================================
+// Host-side launchers (C ABI of the module; bound by csrc/pdp_b200.cpp through dlopen)
+// =====================================================================================================
+extern "C" void pdpmod_info(int* out) {
+  out[0] = PDP_KIND;
+  out[1] = PDP_N; out[2] = PDP_M; out[3] = PDP_R; out[4] = PDP_NVAR; out[5] = PDP_NVAR_S; out[11] = PDP_NTH;
+  out[6] = PDP_GREC; out[7] = PDP_NDENSE; out[8] = PDP_CH; out[9] = PDP_WPB; out[10] = PDP_WARP_DOUBLES;
+}
+
+extern "C" int pdpmod_rollout_costate(int B, int H, const double* x0, const double* theta, int theta_stride, const double* U,
+                                      double* X, double* Lam, double* cost, double* dHu, int* status, cudaStream_t st) {
+  if (B <= 0) return 0;
+  pdp_k_rollout_costate<<<(B + 127) / 128, 128, 0, st>>>(B, H, x0, theta, theta_stride, U, X, Lam, cost, dHu, status);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int pdpmod_aux_eval(int B, int H, const double* X, const double* U, const double* Lam, const double* theta,
+                               int theta_stride, double* out, double* term, cudaStream_t st) {
+  if (B <= 0) return 0;
+  const int total = B * (H + 1);
+  pdp_k_aux_eval<<<(total + 127) / 128, 128, 0, st>>>(B, H, X, U, Lam, theta, theta_stride, out, term);
+  return (int)cudaGetLastError();
+}
+
+'''
+
+K_LAUNCH_LQR = r'''
+extern "C" int pdpmod_aux_lqr(int B, int H, const double* X, const double* U, const double* Lam, const double* theta,
+                              int theta_stride, const double* X0a, int x0a_stride, double* dX, double* dU, double* gains,
+                              const double* Xref, const double* Uref, double* loss_dp,
+                              const double* auxrec, const double* termrec, int phases, int* status, cudaStream_t st) {
+  if (B <= 0) return 0;
+  static bool configured = false;
+  const size_t smem_b = (size_t)PDP_WPB * PDP_WARP_DOUBLES * sizeof(double);
+  const size_t smem_f = (size_t)PDP_WPBF * PDP_FWARP_DOUBLES * sizeof(double);
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(pdp_k_aux_lqr_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(pdp_k_aux_lqr_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  if (phases & 1)
+    pdp_k_aux_lqr_bwd<<<(B + PDP_WPB - 1) / PDP_WPB, PDP_WPB * 32, smem_b, st>>>(B, H, X, U, Lam, theta, theta_stride, gains,
+                                                                               auxrec, termrec, status);
+  if (phases & 2)
+    pdp_k_aux_lqr_fwd<<<(B + PDP_WPBF - 1) / PDP_WPBF, PDP_WPBF * 32, smem_f, st>>>(B, H, X, U, theta, theta_stride, X0a,
+                                                                                  x0a_stride, dX, dU, gains, Xref, Uref,
+                                                                                  loss_dp, auxrec, status);
+  return (int)cudaGetLastError();
+}
+'''

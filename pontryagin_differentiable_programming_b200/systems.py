@@ -78,6 +78,14 @@ def build_all(verbose=False):
         out[name] = fn().module_path
         if verbose:
             print("built", name, out[name])
+    # Newton (ocSolver) variants, generic dense-LQR sizes used by the drop-in LQR class on the shipped examples
+    from . import ocsolver
+    for name, fn in OC_BUILDERS.items():
+        out["newton_" + name] = ocsolver.newton_system(fn()).module_path
+    for dims in ((13, 4, 9), (2, 1, 5), (4, 1, 7), (4, 2, 8), (13, 3, 10), (5, 2, 4), (5, 1, 4)):
+        out["lqr_%d_%d_%d" % dims] = engine.DenseLQR.get(*dims).module_path
+    if verbose:
+        print("built %d modules in total" % len(out))
     return out
 
 

@@ -183,3 +183,102 @@ def test_dropin_getauxsys_and_legacy_calls():
     lqr.setFinalCost(hxx=aux["hxx"], hxe=aux["hxe"])
     sol = lqr.lqrSolver(np.zeros((13, 9)), 50)
     assert _rel(np.stack(sol["state_traj_opt"]), g6["quadrotor_dX"]) < 1e-9
+
+
+# ------------------------------------------------------------------------------------ ocSolver (K2 / K3)
+def _irl_oc(env):
+    from PDP import PDP
+    from JinEnv import JinEnv
+    from casadi import vertcat
+    g2 = np.load(os.path.join(G, "k2_demos.npz"))
+    if env == "pendulum":
+        e = JinEnv.SinglePendulum(); e.initDyn(); e.initCost()
+    elif env == "quadrotor":
+        e = JinEnv.Quadrotor(); e.initDyn(c=0.01); e.initCost(wthrust=0.1)
+    elif env == "robotarm":
+        e = JinEnv.RobotArm(); e.initDyn(g=0); e.initCost(wu=0.01)
+    else:
+        e = JinEnv.Rocket(); e.initDyn(); e.initCost(wthrust=0.1)
+    oc = PDP.OCSys()
+    oc.setAuxvarVariable(vertcat(e.dyn_auxvar, e.cost_auxvar))
+    oc.setControlVariable(e.U)
+    oc.setStateVariable(e.X)
+    oc.setDyn(e.X + g2[env + "_dt"].reshape(1, 1) * e.f)
+    oc.setPathCost(e.path_cost)
+    oc.setFinalCost(e.final_cost)
+    oc.diffPMP()
+    return oc, g2
+
+
+@pytest.mark.parametrize("env", ["pendulum", "quadrotor", "robotarm", "rocket"])
+def test_k2_ocsolver_reproduces_shipped_ipopt_demos(env):
+    """Drop-in OCSys.ocSolver (CUDA Newton solver, cold start) lands on the demos IPOPT produced."""
+    _dev()
+    oc, g2 = _irl_oc(env)
+    theta = g2[env + "_true_parameter"].reshape(1, -1)       # (1, r) as loaded from the .mat by the scripts
+    for i in range(int(g2[env + "_n"])):
+        Xd, Ud, Ld = (g2["%s_%d_%s" % (env, i, k)] for k in ("X", "U", "L"))
+        sol = oc.ocSolver(Xd[0], Ud.shape[0], theta)
+        assert sol["state_traj_opt"].shape == Xd.shape and sol["costate_traj_opt"].shape == Ld.shape
+        assert abs(sol["cost"].item() - g2["%s_%d_cost" % (env, i)][0]) < 1e-7 * abs(sol["cost"].item())
+        assert np.max(np.abs(sol["state_traj_opt"] - Xd)) < 2e-5 * max(1.0, np.max(np.abs(Xd)))
+        assert np.max(np.abs(sol["control_traj_opt"] - Ud)) < 2e-5 * max(1.0, np.max(np.abs(Ud)))
+        assert np.max(np.abs(sol["costate_traj_opt"] - Ld)) < 5e-5 * max(1.0, np.max(np.abs(Ld)))
+
+
+@pytest.mark.parametrize("env,trial", [("pendulum", 0), ("pendulum", 2), ("quadrotor", 0), ("quadrotor", 3)])
+def test_k3_irl_iteration_matches_shipped_trace(env, trial):
+    """One IRL iteration written exactly like reference Examples/IRL/quadrotor/uav_PDP.py:45-79 (legacy API):
+    loss(theta_k) = loss_trace[k+1] and dp(theta_k) = (theta_k - theta_{k+1}) / lr of the shipped trials."""
+    from PDP import PDP
+    _dev()
+    oc, g2 = _irl_oc(env)
+    g3 = np.load(os.path.join(G, "k3_irl_traces.npz"))
+    lqr_solver = PDP.LQR()
+    lr = float(g3["%s_%d_lr" % (env, trial)][0])
+    n_demo = int(g2[env + "_n"])
+    for k in range(len(g3["%s_%d_iters" % (env, trial)])):
+        current_parameter = g3["%s_%d_theta" % (env, trial)][k].reshape(1, -1)
+        loss, dp = 0, np.zeros(current_parameter.shape)
+        for i in range(n_demo):
+            demo_state_traj, demo_control_traj = g2["%s_%d_X" % (env, i)], g2["%s_%d_U" % (env, i)]
+            demo_horizon = demo_control_traj.shape[0]
+            traj = oc.ocSolver(demo_state_traj[0, :], demo_horizon, current_parameter)
+            aux_sys = oc.getAuxSys(state_traj_opt=traj['state_traj_opt'], control_traj_opt=traj['control_traj_opt'],
+                                   costate_traj_opt=traj['costate_traj_opt'], auxvar_value=current_parameter)
+            lqr_solver.setDyn(dynF=aux_sys['dynF'], dynG=aux_sys['dynG'], dynE=aux_sys['dynE'])
+            lqr_solver.setPathCost(Hxx=aux_sys['Hxx'], Huu=aux_sys['Huu'], Hxu=aux_sys['Hxu'], Hux=aux_sys['Hux'],
+                                   Hxe=aux_sys['Hxe'], Hue=aux_sys['Hue'])
+            lqr_solver.setFinalCost(hxx=aux_sys['hxx'], hxe=aux_sys['hxe'])
+            aux_sol = lqr_solver.lqrSolver(np.zeros((oc.n_state, oc.n_auxvar)), demo_horizon)
+            dxdp_traj, dudp_traj = aux_sol['state_traj_opt'], aux_sol['control_traj_opt']
+            dldx_traj = traj['state_traj_opt'] - demo_state_traj
+            dldu_traj = traj['control_traj_opt'] - demo_control_traj
+            loss = loss + np.linalg.norm(dldx_traj) ** 2 + np.linalg.norm(dldu_traj) ** 2
+            for t in range(demo_horizon):
+                dp = dp + np.matmul(dldx_traj[t, :], dxdp_traj[t]) + np.matmul(dldu_traj[t, :], dudp_traj[t])
+            dp = dp + np.dot(dldx_traj[-1, :], dxdp_traj[-1])
+        dp, loss = dp / n_demo, loss / n_demo
+        dp_ref = (current_parameter - g3["%s_%d_theta_next" % (env, trial)][k]) / lr
+        loss_ref = g3["%s_%d_loss" % (env, trial)][k]
+        # tolerance: the shipped numbers sit on IPOPT's own convergence floor (SURVEY 8(c))
+        assert abs(loss - loss_ref) < 1e-5 * max(abs(loss_ref), 1e-3)
+        assert np.max(np.abs(dp - dp_ref)) < 1e-5 * max(np.max(np.abs(dp_ref)), 1.0)
+
+
+def test_batched_ocsolver_and_fused_irl_gradient_equal_legacy_path():
+    """New batched API: solve + fused sweep in two calls gives the same (loss, dp) as the legacy loop."""
+    dev = _dev()
+    oc, g2 = _irl_oc("quadrotor")
+    g3 = np.load(os.path.join(G, "k3_irl_traces.npz"))
+    theta = _t(g3["quadrotor_0_theta"][0].reshape(1, -1), dev)
+    Xd = _t(np.stack([g2["quadrotor_%d_X" % i] for i in range(2)]), dev)
+    Ud = _t(np.stack([g2["quadrotor_%d_U" % i] for i in range(2)]), dev)
+    sol = oc.ocSolver_batched(Xd[:, 0, :].contiguous(), 50, theta)
+    assert bool(sol["converged"].all())
+    res = oc.pdp_sweep_batched(Xd[:, 0, :].contiguous(), theta, sol["U"], state_ref=Xd, control_ref=Ud, want_traj=False)
+    ldp = res["loss_dp"].mean(dim=0).cpu().numpy()
+    lr = float(g3["quadrotor_0_lr"][0])
+    dp_ref = (g3["quadrotor_0_theta"][0] - g3["quadrotor_0_theta_next"][0]) / lr
+    assert abs(ldp[0] - g3["quadrotor_0_loss"][0]) < 1e-5 * g3["quadrotor_0_loss"][0]
+    assert np.max(np.abs(ldp[1:] - dp_ref)) < 1e-5 * np.max(np.abs(dp_ref))

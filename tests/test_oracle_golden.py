@@ -119,3 +119,46 @@ def test_k6_live_reference_lqr_and_sensitivity_recursions():
     assert np.allclose(np.stack(cp["state_traj"]), g["fs_cp_X"], rtol=0, atol=1e-13)
     sid = ref.SysID().integrateAuxSys(F, E, np.zeros((n, r)))
     assert np.allclose(np.stack(sid["state_traj"]), g["fs_sysid_X"], rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("env,demo", [("pendulum", 0), ("pendulum", 3), ("quadrotor", 0), ("robotarm", 1)])
+def test_k2_oracle_oc_solver_reproduces_shipped_ipopt_demos(env, demo):
+    """The oracle's OC solve from the cold start U = 0 lands on the demo IPOPT found (K2)."""
+    from oracle import oc_solve
+    g = np.load(os.path.join(G, "k2_demos.npz"))
+    builder, kw = IRL_SETUP[env]
+    oc = pdp_oracle.build_oc(builder(**kw), float(g[env + "_dt"][0]))
+    Xd, Ud, Ld = (g["%s_%d_%s" % (env, demo, k)] for k in ("X", "U", "L"))
+    X, U, L, cost, it = oc_solve.solve(oc, Xd[0], Ud.shape[0], g[env + "_true_parameter"])
+    assert abs(cost - g["%s_%d_cost" % (env, demo)][0]) < 1e-7 * abs(cost)
+    assert np.max(np.abs(X - Xd)) < 2e-5 * max(1.0, np.max(np.abs(Xd)))
+    assert np.max(np.abs(U - Ud)) < 2e-5 * max(1.0, np.max(np.abs(Ud)))
+    assert np.max(np.abs(L - Ld)) < 5e-5 * max(1.0, np.max(np.abs(Ld)))
+
+
+@pytest.mark.parametrize("env,trial", [("pendulum", 0), ("pendulum", 1), ("quadrotor", 0)])
+def test_k3_irl_loss_and_gradient_trace(env, trial):
+    """End-to-end hot path: ocSolver -> getAuxSys -> lqrSolver -> chain rule reproduces the shipped traces:
+    loss(theta_k) = loss_trace[k+1], dp(theta_k) = (theta_k - theta_{k+1}) / lr."""
+    from oracle import oc_solve
+    g2 = np.load(os.path.join(G, "k2_demos.npz"))
+    g3 = np.load(os.path.join(G, "k3_irl_traces.npz"))
+    builder, kw = IRL_SETUP[env]
+    oc = pdp_oracle.build_oc(builder(**kw), float(g2[env + "_dt"][0]))
+    lr = float(g3["%s_%d_lr" % (env, trial)][0])
+    nd = int(g2[env + "_n"])
+    for k in range(2 if env == "pendulum" else 1):
+        theta = g3["%s_%d_theta" % (env, trial)][k]
+        loss, dp = 0.0, np.zeros(oc.r)
+        for i in range(nd):
+            Xd, Ud = g2["%s_%d_X" % (env, i)], g2["%s_%d_U" % (env, i)]
+            X, U, L, cost, it = oc_solve.solve(oc, Xd[0], Ud.shape[0], theta)
+            aux = oc.getAuxSys(X, U, L, theta)
+            sol = pdp_oracle.lqr_solve(aux, np.zeros((oc.n, oc.r)), Ud.shape[0])
+            l_i, dp_i = pdp_oracle.irl_loss_grad(X, U, Xd, Ud, sol["state_traj_opt"], sol["control_traj_opt"])
+            loss += l_i
+            dp += dp_i
+        loss, dp = loss / nd, dp / nd
+        dp_ref = (theta - g3["%s_%d_theta_next" % (env, trial)][k]) / lr
+        assert abs(loss - g3["%s_%d_loss" % (env, trial)][k]) < 1e-6 * abs(loss)
+        assert np.max(np.abs(dp - dp_ref)) < 1e-6 * np.max(np.abs(dp_ref))

@@ -1,0 +1,42 @@
+"""Cross-compile (no GPU needed) the modules the GPU tests create through the drop-in classes, so the GPU box
+does not spend its minutes in nvcc.  Run after __graft_entry__.build()."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+
+from PDP import PDP  # noqa: E402
+from JinEnv import JinEnv  # noqa: E402
+from casadi import vertcat  # noqa: E402
+from pontryagin_differentiable_programming_b200 import engine, ocsolver  # noqa: E402
+
+dt11 = np.array([[0.1]])
+for env in ("pendulum", "quadrotor", "robotarm", "rocket"):
+    if env == "pendulum":
+        e = JinEnv.SinglePendulum(); e.initDyn(); e.initCost()
+    elif env == "quadrotor":
+        e = JinEnv.Quadrotor(); e.initDyn(c=0.01); e.initCost(wthrust=0.1)
+    elif env == "robotarm":
+        e = JinEnv.RobotArm(); e.initDyn(g=0); e.initCost(wu=0.01)
+    else:
+        e = JinEnv.Rocket(); e.initDyn(); e.initCost(wthrust=0.1)
+    oc = PDP.OCSys()
+    oc.setAuxvarVariable(vertcat(e.dyn_auxvar, e.cost_auxvar))
+    oc.setControlVariable(e.U)
+    oc.setStateVariable(e.X)
+    oc.setDyn(e.X + dt11 * e.f)
+    oc.setPathCost(e.path_cost)
+    oc.setFinalCost(e.final_cost)
+    print(env, ocsolver.newton_system(oc._system()).module_path)
+
+rocket = JinEnv.Rocket()
+rocket.initDyn(Jx=0.5, Jy=1., Jz=1., mass=1., l=1.)
+rocket.initCost(wr=1, wv=1, wtilt=50, ww=1, wsidethrust=1, wthrust=0.4)
+cp = PDP.ControlPlanning()
+cp.setStateVariable(rocket.X)
+cp.setControlVariable(rocket.U)
+cp.setDyn(rocket.X + 0.1 * rocket.f)
+cp.setPathCost(rocket.path_cost)
+cp.setFinalCost(rocket.final_cost)
+print("rocket recmat", cp._oc_system().module_path)
