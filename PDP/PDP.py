@@ -183,20 +183,29 @@ class OCSys:
     def aux_lqr_batched(self, state_traj, control_traj, costate_traj, auxvar_value, **kw):
         return self._system().aux_lqr(state_traj, control_traj, costate_traj, auxvar_value, **kw)
 
-    def ocSolver_batched(self, ini_state, horizon, auxvar_value, control_init=None, **opts):
-        """Batched optimal-control solve (CUDA Newton / iLQR, see ocsolver.py)."""
+    def ocSolver_batched(self, ini_state, horizon, auxvar_value, control_init=None, n_starts=1, **opts):
+        """Batched optimal-control solve (CUDA Newton / DDP, see ocsolver.py).  ``n_starts`` > 1 tries several
+        seeded initial guesses per problem in the same batch and keeps the best stationary point."""
         from pontryagin_differentiable_programming_b200 import ocsolver
+        if control_init is None and n_starts > 1:
+            return ocsolver.solve_multistart(self._system(), ini_state, int(horizon), auxvar_value, n_starts, **opts)
         return ocsolver.solve(self._system(), ini_state, int(horizon), auxvar_value, control_init, **opts)
 
     # -------------------------------------------------------------------------------- legacy API
-    def ocSolver(self, ini_state, horizon, auxvar_value=1, print_level=0, costate_option=0):
+    def ocSolver(self, ini_state, horizon, auxvar_value=1, print_level=0, costate_option=0, control_init=None,
+                 n_starts=8):
         """Solve the OC problem for one initial state (reference PDP.py:121-220 used IPOPT; here the batched
-        CUDA Newton/iLQR solver with B = 1).  Returns the same dict; ``costate_traj_opt[t] = lambda_{t+1}``."""
+        CUDA Newton/DDP solver).  Returns the same dict; ``costate_traj_opt[t] = lambda_{t+1}`` for either
+        ``costate_option`` (the PMP recursion and the NLP multipliers coincide at a stationary point).
+        Additive keyword arguments: ``control_init`` (H x m warm start) and ``n_starts`` (seeded multi-start)."""
         self._check_defined()
         dev = _device()
         x0 = _dev_tensor(_flat(ini_state, self.n_state, "ini_state")[None, :], dev)
         theta = _dev_tensor(_flat(auxvar_value, self.n_auxvar, "auxvar_value")[None, :], dev)
-        sol = self.ocSolver_batched(x0, horizon, theta, verbose=print_level > 0)
+        if control_init is not None:
+            control_init = _dev_tensor(numpy.asarray(control_init, dtype=numpy.float64).reshape(1, horizon, self.n_control), dev)
+        sol = self.ocSolver_batched(x0, horizon, theta, control_init=control_init, n_starts=n_starts,
+                                    verbose=print_level > 0)
         return {"state_traj_opt": sol["X"][0].cpu().numpy(),
                 "control_traj_opt": sol["U"][0].cpu().numpy(),
                 "costate_traj_opt": sol["Lam"][0].cpu().numpy(),

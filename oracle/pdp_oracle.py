@@ -112,7 +112,7 @@ class OracleOC:
         return out
 
 
-def lqr_solve(aux, ini_state, horizon):
+def lqr_solve(aux, ini_state, horizon, return_gains=False):
     """Matrix-valued LQR, literal reference form (PDP.py:557-608): backward ``PP/WW`` with
     ``inv(Huu)`` and ``inv(I + P R)``, then the forward pass.  Returns lists like the reference."""
     F, G, E = aux["dynF"], aux["dynG"], aux["dynE"]
@@ -138,7 +138,7 @@ def lqr_solve(aux, ini_state, horizon):
         PP[t - 1] = Q + T @ (P @ A)
         WW[t - 1] = N + T @ (W + P @ M)
     Xs = [ini_state]
-    Us, Ls = [], []
+    Us, Ls, Ks, ks = [], [], [], []
     for t in range(horizon):
         P, W = PP[t], WW[t]
         iHuu = np.linalg.inv(Huu[t])
@@ -147,12 +147,19 @@ def lqr_solve(aux, ini_state, horizon):
         M = E[t] - GiH @ Hue[t]
         R = GiH @ G[t].T
         x = Xs[t]
-        u = -iHuu @ (Hxu[t].T @ x + Hue[t]) - iHuu @ G[t].T @ np.linalg.inv(I + P @ R) @ (P @ A @ x + P @ M + W)
+        T2 = np.linalg.inv(I + P @ R)
+        u = -iHuu @ (Hxu[t].T @ x + Hue[t]) - iHuu @ G[t].T @ T2 @ (P @ A @ x + P @ M + W)
+        if return_gains:  # u = K x + k  (same expression, split into its linear and affine parts)
+            Ks.append(-iHuu @ Hxu[t].T - iHuu @ G[t].T @ T2 @ P @ A)
+            ks.append(-iHuu @ Hue[t] - iHuu @ G[t].T @ T2 @ (P @ M + W))
         xn = F[t] @ x + G[t] @ u + E[t]
         Xs.append(xn)
         Us.append(u)
         Ls.append(P @ xn + W)
-    return {"state_traj_opt": Xs, "control_traj_opt": Us, "costate_traj_opt": Ls}
+    out = {"state_traj_opt": Xs, "control_traj_opt": Us, "costate_traj_opt": Ls}
+    if return_gains:
+        out["K"], out["k"] = Ks, ks
+    return out
 
 
 def irl_loss_grad(X, U, Xd, Ud, dX, dU):

@@ -25,7 +25,7 @@ KIND_OC, KIND_SYSID, KIND_CP, KIND_LQR = 1, 2, 3, 4
 EXPORTS = ["pdp_load_system", "pdp_free_system", "pdp_system_dims", "pdp_last_error", "pdp_version",
            "pdp_workspace_bytes", "pdp_rollout_costate", "pdp_aux_lqr", "pdp_sweep", "pdp_aux_eval",
            "pdp_sens_fwd", "pdp_sweep_host", "pdp_lqr_dense", "pdp_eval_function", "pdp_aux_lqr_backward",
-           "pdp_aux_lqr_forward"]
+           "pdp_aux_lqr_forward", "pdp_rollout_feedback"]
 
 
 def library_path():
@@ -63,6 +63,8 @@ def load_library(build_if_missing=True):
         lib.pdp_eval_function.argtypes = [vp, i, ctypes.POINTER(dp), ctypes.POINTER(i), ctypes.POINTER(dp), vp]
         lib.pdp_eval_function.restype = i
         lib.pdp_lqr_dense.restype = i
+        lib.pdp_rollout_feedback.argtypes = [vp, i, i, dp, dp, i, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp, vp]
+        lib.pdp_rollout_feedback.restype = i
         lib.pdp_aux_lqr_backward.argtypes = [vp, i, i, dp, dp, dp, dp, i, dp, sz, dp, vp]
         lib.pdp_aux_lqr_backward.restype = i
         lib.pdp_aux_lqr_forward.argtypes = [vp, i, i, dp, dp, dp, i, dp, i, dp, dp, dp, dp, dp, dp, sz, dp, vp]

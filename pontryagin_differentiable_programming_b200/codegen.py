@@ -61,8 +61,29 @@ class SlotTable:
             self.nodes.append(node)
         return ("v", k, sign)
 
+    def exact(self, node: Node) -> int:
+        """Slot holding exactly ``node`` (sign and constants included) -- used for per-lane indexed loads."""
+        k = self.index.get(("x", node.uid))
+        if k is None:
+            if node.op not in ("neg", "const"):
+                k = self.index.get(node.uid)          # already stored for the S block with sign +1
+            if k is None:
+                k = len(self.nodes)
+                self.nodes.append(node)
+            self.index[("x", node.uid)] = k
+        return k
+
     def __len__(self):
         return len(self.nodes)
+
+
+def _pad_ld(n):
+    """Row stride (doubles) of a per-step slot row: >= n and = 2 (mod 16), so that the 8..16 evaluation
+    lanes (one row each) hit distinct 16-byte bank groups when they store their slots."""
+    v = max(int(n), 2)
+    while v % 16 != 2:
+        v += 1
+    return v
 
 
 def _emit_function(name: str, inputs: Sequence[Tuple[str, SX]], outputs: Sequence[Node], out_expr,
@@ -172,7 +193,8 @@ class OCModuleSource:
 
     def __init__(self, state: SX, control: SX, auxvar: SX, dyn: SX, path_cost: SX, final_cost: SX,
                  chunk: int = 8, warps_per_block: int = 4, min_blocks: int = 1, fwd_warps_per_block: int = 4,
-                 fwd_min_blocks: int = 1):
+                 fwd_min_blocks: int = 1, keep_fg: bool = True):
+        self.keep_fg = bool(keep_fg)
         self.min_blocks = int(min_blocks)
         self.wpbf, self.min_blocks_f = int(fwd_warps_per_block), int(fwd_min_blocks)
         self.x, self.u, self.th = state, control, auxvar
@@ -228,7 +250,7 @@ class OCModuleSource:
         # stacked Hamiltonian Hessian  [[Hxx Hxu],[Hxu^T Huu],[Hxe^T Hue^T]]   (ns x (n+m))
         # (the reference never uses Hux in arithmetic, only transpose(Hxu): PDP.py:569,572,598)
         nm = n + m
-        self.H_ent = [[None] * nm for _ in range(ns)]
+        self.H_idx = [[0] * nm for _ in range(ns)]
         for j in range(ns):
             for l in range(nm):
                 if j < n and l < n:
@@ -243,11 +265,11 @@ class OCModuleSource:
                     node = self.ddHxe.at(l, j - nm)
                 else:
                     node = self.ddHue.at(l - n, j - nm)
-                self.H_ent[j][l] = slots.entry(node)
+                self.H_idx[j][l] = slots.exact(node)
+        self.zero_slot = slots.exact(S.ZERO)
         self.slots = slots
         self.nvar = len(slots)
-        self.auxld = _even(max(self.nvar, 2))
-        self.ldh = _odd(nm)
+        self.auxld = _pad_ld(self.nvar)
         self.ldz = _odd(n)
         self.ldk = _even(n)
 
@@ -262,9 +284,12 @@ class OCModuleSource:
         parts.append(_emit_function("pdp_f_dHu", [x, u, lam, th], self.dHu.elements(), lambda i: "out[%d]" % i))
         parts.append(_emit_function("pdp_f_dhx", [x, th], self.dhx.elements(), lambda i: "out[%d]" % i))
         # all aux slots / only the dynamics-Jacobian slots
-        parts.append(_emit_function("pdp_f_aux_slots", [x, u, lam, th], self.slots.nodes, lambda i: "out[%d]" % i))
+        # the two slot evaluators are deliberately NOT inlined: they run once per chunk on a few lanes and would
+        # otherwise dictate the register allocation (hence the occupancy) of the per-step hot loops
+        parts.append(_emit_function("pdp_f_aux_slots", [x, u, lam, th], self.slots.nodes, lambda i: "out[%d]" % i,
+                                    qualifiers="__device__ __noinline__"))
         parts.append(_emit_function("pdp_f_dyn_slots", [x, u, th], self.slots.nodes[:self.nvar_s] or [S.ZERO],
-                                    lambda i: "out[%d]" % i))
+                                    lambda i: "out[%d]" % i, qualifiers="__device__ __noinline__"))
         # terminal Hessians, dense row-major [hxx (n*n) | hxe (n*r)]
         term = [self.ddhxx.at(i, j) for i in range(self.n) for j in range(self.n)] + \
                [self.ddhxe.at(i, j) for i in range(self.n) for j in range(self.r)]
@@ -309,14 +334,13 @@ class OCModuleSource:
             L.append(ind + "  c%d += y%d;" % (k, k))
         L.append(ind + "}")
         # phase C: q = Hrow + c . [F|G]
-        L.append(ind + "// C: Q(j,:) = Hstack(j,:) + Z(:,j)^T [F|G]")
+        L.append(ind + "// C: Q(j,:) = Hstack(j,:) + Z(:,j)^T [F|G]   (H: per-lane indexed loads; [F|G] still in registers from A)")
         L.append(ind + "double " + ", ".join("q%d" % l for l in range(nm)) + ";")
-        L.append(ind + "{ const double* hr = Hd + lrow * %d;" % self.ldh)
         for l in range(nm):
-            L.append(ind + "  q%d = hr[%d];" % (l, l))
-        L.append(ind + "}")
-        needed = {self.S_ent[k][l][1] for k in range(n) for l in range(nm) if self.S_ent[k][l][0] == "v"}
-        load = _SlotLoader(L, "ar", needed, ind, "sc")
+            L.append(ind + "q%d = ar[ho%d];" % (l, l))
+        if not getattr(self, "keep_fg", True):
+            needed = {self.S_ent[k][l][1] for k in range(n) for l in range(nm) if self.S_ent[k][l][0] == "v"}
+            load = _SlotLoader(L, "ar", needed, ind, "sc")
         acc = _Acc("q", nm, L, ind)
         acc.touched = [True] * nm
         for k in range(n):
@@ -397,19 +421,16 @@ class OCModuleSource:
         n, m, r, ns = self.n, self.m, self.r, self.ns
         L: List[str] = []
         ind = "      "
-        L.append(ind + "// U(:,c) = k(:,c) + K X(:,c)   (lane n+c owns column c)")
+        L.append(ind + "// U(:,c) = k(:,c) + K X(:,c)   (lane n+c owns column c); two partial sums per row shorten the chains")
+        half = (n + 1) // 2
         for a in range(m):
-            L.append(ind + "double u%d = g%d;" % (a, a))
+            L.append(ind + "double u%d = g%d, ub%d = 0.0;" % (a, a, a))
         for a in range(m):
-            if self.ldk % 2 == 0:
-                for l in range(0, n - 1, 2):
-                    L.append(ind + "{ const double2 kk = *reinterpret_cast<const double2*>(KS + %d); u%d = fma(kk.x, x%d, u%d); u%d = fma(kk.y, x%d, u%d); }"
-                             % (a * self.ldk + l, a, l, a, a, l + 1, a))
-                if n % 2 == 1:
-                    L.append(ind + "u%d = fma(KS[%d], x%d, u%d);" % (a, a * self.ldk + n - 1, n - 1, a))
-            else:
-                for l in range(n):
-                    L.append(ind + "u%d = fma(KS[%d], x%d, u%d);" % (a, a * self.ldk + l, l, a))
+            for l in range(n):
+                tgt = "u%d" % a if l < half else "ub%d" % a
+                L.append(ind + "%s = fma(KS[%d], x%d, %s);" % (tgt, a * self.ldk + l, l, tgt))
+        for a in range(m):
+            L.append(ind + "u%d += ub%d;" % (a, a))
         L.append(ind + "// X+(:,c) = F X(:,c) + G U(:,c) + E(:,c)")
         L.append(ind + "double " + ", ".join("n%d" % i for i in range(n)) + ";")
         needed = {e[1] for row in self.S_ent for e in row if e[0] == "v"}
@@ -438,40 +459,27 @@ class OCModuleSource:
     def source(self) -> str:
         n, m, r, ns = self.n, self.m, self.r, self.ns
         nm = n + m
-        # constant and variable entries of the dense Hamiltonian stack
-        hconst, hvar = [], []
-        for j in range(ns):
-            for l in range(nm):
-                e = self.H_ent[j][l]
-                if e[0] == "c":
-                    hconst.append((j * self.ldh + l, e[1]))
-                elif e[0] == "v":
-                    hvar.append((j * self.ldh + l, e[1], e[2]))
-        nhs = len(hvar)
-        kh = max(1, (nhs + WARP - 1) // WARP)
-        hd_size = _even(ns * self.ldh + 1)  # +1 dummy slot for idle scatter lanes
-        zt_size = _even(max(ns * self.ldz, n * r + m * r))
+        kh = 0
+        nhs = 0
+        zt_size = _even(ns * self.ldz)
         ks_size = _even(m * self.ldk)
         auxc_size = _even(max(self.chunk * self.auxld, n * n + n * r))
-        off_hd = auxc_size
-        off_zt = off_hd + hd_size
+        off_zt = auxc_size
         off_ks = off_zt + zt_size
         off_quu = off_ks + ks_size
         off_th = off_quu + _even(m * m)
         warp_doubles = _even(off_th + max(self.nth, 1))
         # forward kernel: [CH][FLD] dynamics slots | OUT | KS | TH | DLC
-        fld = _even(max(self.nvar_s, 2))
-        foff_out = _even(self.chunk * fld)
-        foff_ks = foff_out + _even(n * r + m * r)
+        fld = _pad_ld(self.nvar_s)
+        foff_ks = _even(self.chunk * fld)
         foff_th = foff_ks + ks_size
         foff_dl = foff_th + _even(max(self.nth, 1))
         fwarp_doubles = _even(foff_dl + max(self.chunk * nm, n))
         defs = {
             "N": n, "M": m, "R": r, "NS": ns, "NM": nm, "NVAR": self.nvar, "NVAR_S": self.nvar_s,
-            "AUXLD": self.auxld, "CH": self.chunk, "WPB": self.wpb, "LDH": self.ldh, "LDZ": self.ldz,
-            "LDK": self.ldk, "HD_SIZE": hd_size, "HD_DUMMY": ns * self.ldh,
-            "OFF_HD": off_hd, "OFF_ZT": off_zt, "OFF_KS": off_ks, "OFF_QUU": off_quu, "OFF_TH": off_th,
-            "FLD": fld, "FOFF_OUT": foff_out, "FOFF_KS": foff_ks, "FOFF_TH": foff_th, "FOFF_DL": foff_dl,
+            "AUXLD": self.auxld, "CH": self.chunk, "WPB": self.wpb, "LDZ": self.ldz,
+            "LDK": self.ldk, "OFF_ZT": off_zt, "OFF_KS": off_ks, "OFF_QUU": off_quu, "OFF_TH": off_th,
+            "FLD": fld, "FOFF_KS": foff_ks, "FOFF_TH": foff_th, "FOFF_DL": foff_dl,
             "FWARP_DOUBLES": fwarp_doubles, "WPBF": getattr(self, "wpbf", 4), "MINBF": getattr(self, "min_blocks_f", 1),
             "WARP_DOUBLES": warp_doubles, "NTH": self.nth, "MINB": getattr(self, "min_blocks", 1), "NHS": nhs, "KH": kh, "GREC": (n + r) * m,
             "NDENSE": n * n + n * m + n * r + n * n + n * m + n * r + m * n + m * m + m * r,
@@ -480,16 +488,13 @@ class OCModuleSource:
                   "#include <cuda_runtime.h>", "#include <math.h>", "#include <stdint.h>"]
         header += ["#define PDP_%s %d" % kv for kv in defs.items()]
         tables = []
-        src_tab = [e for (_, e, _) in hvar] + [0] * (kh * WARP - nhs)
-        dst_tab = [d for (d, _, _) in hvar] + [ns * self.ldh] * (kh * WARP - nhs)
-        sgn_tab = [s for (_, _, s) in hvar] + [0.0] * (kh * WARP - nhs)
-        tables.append("__device__ const short pdp_hs_src[%d] = {%s};" % (len(src_tab), ", ".join(map(str, src_tab))))
-        tables.append("__device__ const short pdp_hs_dst[%d] = {%s};" % (len(dst_tab), ", ".join(map(str, dst_tab))))
-        tables.append("__device__ const double pdp_hs_sgn[%d] = {%s};" % (len(sgn_tab), ", ".join(_lit(s) for s in sgn_tab)))
-        hinit = "\n".join("    if (lane == %d) Hd[%d] = %s;" % (i % WARP, d, _lit(v)) for i, (d, v) in enumerate(hconst))
-        scatter = "\n".join("      Hd[hdst%d] = hsgn%d * ar[hsrc%d];" % (k, k, k) for k in range(kh))
-        tabload = "\n".join("  const int hsrc%d = pdp_hs_src[%d + lane], hdst%d = pdp_hs_dst[%d + lane]; const double hsgn%d = pdp_hs_sgn[%d + lane];"
-                            % (k, k * WARP, k, k * WARP, k, k * WARP) for k in range(kh))
+        hid = []
+        for l in range(nm):
+            hid += [self.H_idx[j][l] if j < ns else self.zero_slot for j in range(WARP)]
+        tables.append("__device__ const unsigned short pdp_hidx[%d] = {%s};" % (len(hid), ", ".join(map(str, hid))))
+        tabload = "\n".join("  const int ho%d = pdp_hidx[%d + lane];" % (l, l * WARP) for l in range(nm))
+        hinit = ""
+        scatter = ""
         ydecl = "double " + ", ".join("y%d = 0.0" % k for k in range(n)) + ";"
         # terminal init: lane i<n takes row i of hxx, lane n+m+c takes column c of hxe
         term_init = []
@@ -503,17 +508,17 @@ class OCModuleSource:
         gcur = "      const double " + ", ".join("g%d = gn%d" % (a, a) for a in range(m)) + ";"
         gnload = self._gload()
         ks_store = "\n".join("        KS[%d + lane] = g%d;" % (a * self.ldk, a) for a in range(m))
-        stage = "\n".join(["        OUT[%d + col] = n%d;" % (i * r, i) for i in range(n)] +
-                          ["        OUT[%d + col] = u%d;" % (n * r + a * r, a) for a in range(m)])
+        xstore = "\n".join("          o[%d] = n%d;" % (i * r, i) for i in range(n))
+        ustore = "\n".join("          o[%d] = u%d;" % (a * r, a) for a in range(m))
         xcopy = "\n".join("      x%d = n%d;" % (k, k) for k in range(n))
-        x0stage = "\n".join("      OUT[%d + col] = x%d;" % (i * r, i) for i in range(n))
+        x0store = "\n".join("    o[%d] = x%d;" % (i * r, i) for i in range(n))
 
         rep = {
             "@@TABLOAD@@": tabload, "@@HINIT@@": hinit, "@@SCATTER@@": scatter, "@@YDECL@@": ydecl,
             "@@TERM_INIT@@": "\n".join(term_init), "@@BACKWARD_STEP@@": self._backward_step(),
             "@@XDECL@@": xdecl, "@@XINIT@@": xinit, "@@GNDECL@@": gndecl, "@@GNLOAD@@": gnload, "@@GCUR@@": gcur,
-            "@@KS_STORE@@": ks_store, "@@FORWARD_STEP@@": self._forward_step(), "@@STAGE@@": stage,
-            "@@XCOPY@@": xcopy, "@@X0STAGE@@": x0stage,
+            "@@KS_STORE@@": ks_store, "@@FORWARD_STEP@@": self._forward_step(), "@@XSTORE@@": xstore, "@@USTORE@@": ustore,
+            "@@XCOPY@@": xcopy, "@@X0STORE@@": x0store,
             "@@DPACC@@": "\n".join(["        dpacc = fma(dl[%d], x%d, dpacc);" % (i, i) for i in range(n)] +
                                     ["        dpacc = fma(dl[%d], u%d, dpacc);" % (n + a, a) for a in range(m)]),
             "@@DPTERM@@": "\n".join("      dpacc = fma(dl[%d], x%d, dpacc);" % (i, i) for i in range(n)),
@@ -656,7 +661,7 @@ class LQRModuleSource(OCModuleSource):
         self.ns = self.n + self.m + self.r
         self.nth = 0
         self.chunk, self.wpb = int(chunk), int(warps_per_block)
-        self.min_blocks, self.wpbf, self.min_blocks_f = 1, int(warps_per_block), 1
+        self.min_blocks, self.wpbf, self.min_blocks_f, self.keep_fg = 1, int(warps_per_block), 1, False
         n, m, r, ns = self.n, self.m, self.r, self.ns
         nm = n + m
         oF, oG, oE = 0, n * n, n * n + n * m
@@ -668,10 +673,13 @@ class LQRModuleSource(OCModuleSource):
         oHue = oHuu + m * m
         self.ndense = oHue + m * r
         src: List[int] = []
+        seen: Dict[int, int] = {}
 
         def slot(off):
-            src.append(off)
-            return ("v", len(src) - 1, 1.0)
+            if off not in seen:
+                seen[off] = len(src)
+                src.append(off)
+            return ("v", seen[off], 1.0)
 
         self.S_ent = [[None] * ns for _ in range(n)]
         for k in range(n):
@@ -683,7 +691,7 @@ class LQRModuleSource(OCModuleSource):
                 else:
                     self.S_ent[k][j] = slot(oE + k * r + (j - nm))
         self.nvar_s = len(src)
-        self.H_ent = [[None] * nm for _ in range(ns)]
+        self.H_idx = [[0] * nm for _ in range(ns)]
         for j in range(ns):
             for l in range(nm):
                 if j < n and l < n:
@@ -698,11 +706,12 @@ class LQRModuleSource(OCModuleSource):
                     off = oHxe + l * r + (j - nm)
                 else:
                     off = oHue + (l - n) * r + (j - nm)
-                self.H_ent[j][l] = slot(off)
+                self.H_idx[j][l] = slot(off)[1]
+        self.zero_slot = 0                                 # idle lanes read any valid slot (result unused)
         self.src_off = src
         self.nvar = len(src)
-        self.auxld = _even(self.nvar)
-        self.ldh, self.ldz, self.ldk = _odd(nm), _odd(n), _even(n)
+        self.auxld = _pad_ld(self.nvar)
+        self.ldz, self.ldk = _odd(n), _even(n)
 
     def _device_functions(self) -> str:
         return ""

@@ -36,9 +36,9 @@ class OCSystem:
     """Compiled optimal-control system: rollout/costate, fused getAuxSys+lqrSolver, dense aux eval."""
 
     def __init__(self, state, control, auxvar, dyn, path_cost, final_cost, chunk=8, warps_per_block=4, min_blocks=1,
-                 fwd_warps_per_block=4, fwd_min_blocks=1, verbose=False):
+                 fwd_warps_per_block=4, fwd_min_blocks=4, keep_fg=True, verbose=False):
         self.src = codegen.OCModuleSource(state, control, auxvar, dyn, path_cost, final_cost, chunk, warps_per_block,
-                                          min_blocks, fwd_warps_per_block, fwd_min_blocks)
+                                          min_blocks, fwd_warps_per_block, fwd_min_blocks, keep_fg)
         self.n, self.m, self.r = self.src.n, self.src.m, self.src.r
         self.module_path = build.compile_module(self.src.source(), self.src.key(), verbose=verbose)
         self._handle = None
@@ -93,6 +93,27 @@ class OCSystem:
                                                   _ptr(Lam), _ptr(cost), _ptr(dHu), _ptr(status), st),
                           "pdp_rollout_costate")
         out = {"X": X, "Lam": Lam, "cost": cost}
+        if want_dHu:
+            out["dHu"] = dHu
+        return out
+
+    def rollout_feedback(self, x0, theta, Uref, Xref, gains, alpha, want_dHu=True, status=None):
+        """Closed-loop rollout u_t = Uref[t] + alpha_b k_t + K_t (x_t - Xref[t]); gains[B,H,n+1,m] (or the raw
+        workspace of a one-column Riccati sweep).  -> dict U (applied), X, Lam, cost[, dHu]."""
+        require_cuda()
+        dev = x0.device
+        B, H = Uref.shape[0], Uref.shape[1]
+        theta, ts = self._theta(theta, B, dev)
+        mk = lambda *shape: torch.empty(shape, dtype=torch.float64, device=dev)
+        X, Lam, cost, Uout = mk(B, H + 1, self.n), mk(B, H, self.n), mk(B), mk(B, H, self.m)
+        dHu = mk(B, H, self.m) if want_dHu else None
+        st = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            backend.check(self.handle.lib.pdp_rollout_feedback(self.handle.ptr, B, H, _ptr(x0), _ptr(theta), ts, _ptr(Uref),
+                                                               _ptr(Xref), _ptr(gains), _ptr(alpha), _ptr(Uout), _ptr(X),
+                                                               _ptr(Lam), _ptr(cost), _ptr(dHu), _ptr(status), st),
+                          "pdp_rollout_feedback")
+        out = {"U": Uout, "X": X, "Lam": Lam, "cost": cost}
         if want_dHu:
             out["dHu"] = dHu
         return out

@@ -12,8 +12,13 @@ K_ROLLOUT_AUXEVAL = r'''
 extern "C" __global__ void __launch_bounds__(128)
 pdp_k_rollout_costate(int B, int H, const double* __restrict__ x0, const double* __restrict__ theta, int theta_stride,
                       const double* __restrict__ U, double* __restrict__ X, double* __restrict__ Lam,
-                      double* __restrict__ cost, double* __restrict__ dHu, int* __restrict__ status)
+                      double* __restrict__ cost, double* __restrict__ dHu, int* __restrict__ status,
+                      const double* __restrict__ fb_gains, const double* __restrict__ fb_X,
+                      const double* __restrict__ fb_alpha, double* __restrict__ Uout)
 {
+  // Optional closed-loop mode (batched ocSolver line search): with fb_gains != NULL the applied control is
+  //   u_t = U[t] + alpha_b * k_t + K_t (x_t - fb_X[t])   (gains in the (K|k) record layout of the Riccati
+  // sweep with one column) and is written to Uout.
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   double x[PDP_N], xn[PDP_N], th[PDP_NTH], u[PDP_M], tmp[1];
@@ -24,10 +29,25 @@ pdp_k_rollout_costate(int B, int H, const double* __restrict__ x0, const double*
   double J = 0.0;
   double* Xb = X + (size_t)b * (H + 1) * PDP_N;
   const double* Ub = U + (size_t)b * H * PDP_M;
+  const double fb_a = fb_gains ? fb_alpha[b] : 0.0;
   #pragma unroll 1
   for (int t = 0; t < H; ++t) {
     #pragma unroll
     for (int i = 0; i < PDP_M; ++i) u[i] = Ub[t * PDP_M + i];
+    if (fb_gains != nullptr) {
+      const double* g = fb_gains + ((size_t)b * H + t) * ((PDP_N + 1) * PDP_M);
+      const double* xo = fb_X + ((size_t)b * (H + 1) + t) * PDP_N;
+      #pragma unroll
+      for (int a = 0; a < PDP_M; ++a) u[a] = fma(fb_a, g[PDP_N * PDP_M + a], u[a]);
+      #pragma unroll
+      for (int l = 0; l < PDP_N; ++l) {
+        const double dx = x[l] - xo[l];
+        #pragma unroll
+        for (int a = 0; a < PDP_M; ++a) u[a] = fma(g[l * PDP_M + a], dx, u[a]);
+      }
+      #pragma unroll
+      for (int i = 0; i < PDP_M; ++i) Uout[((size_t)b * H + t) * PDP_M + i] = u[i];
+    }
     #pragma unroll
     for (int i = 0; i < PDP_N; ++i) Xb[t * PDP_N + i] = x[i];
     pdp_f_path_cost(x, u, th, tmp);
@@ -53,7 +73,7 @@ pdp_k_rollout_costate(int B, int H, const double* __restrict__ x0, const double*
       #pragma unroll
       for (int i = 0; i < PDP_N; ++i) x[i] = Xb[t * PDP_N + i];
       #pragma unroll
-      for (int i = 0; i < PDP_M; ++i) u[i] = Ub[t * PDP_M + i];
+      for (int i = 0; i < PDP_M; ++i) u[i] = fb_gains ? Uout[((size_t)b * H + t) * PDP_M + i] : Ub[t * PDP_M + i];
       if (dHu != nullptr) {
         pdp_f_dHu(x, u, lam, th, gu);
         #pragma unroll
@@ -117,7 +137,6 @@ pdp_k_aux_lqr_bwd(int B, int H, const double* __restrict__ X, const double* __re
   const int b = blockIdx.x * PDP_WPB + (threadIdx.x >> 5);
   if (b >= B) return;
   double* auxc = pdp_smem + (size_t)(threadIdx.x >> 5) * PDP_WARP_DOUBLES;   // [CH][AUXLD]
-  double* Hd = auxc + PDP_OFF_HD;                                            // dense Hamiltonian stack (+1 dummy)
   double* ZT = auxc + PDP_OFF_ZT;                                            // Z^T staging
   double* KS = auxc + PDP_OFF_KS;                                            // K (m x n)
   double* QUU = auxc + PDP_OFF_QUU;                                          // m x m
@@ -131,12 +150,8 @@ pdp_k_aux_lqr_bwd(int B, int H, const double* __restrict__ X, const double* __re
   (void)Xb; (void)Ub; (void)Lb;
   bool bad = false;
 @@TABLOAD@@
-  for (int i = lane; i < PDP_HD_SIZE; i += 32) Hd[i] = 0.0;
   if (theta != nullptr) for (int i = lane; i < PDP_NTH; i += 32) TH[i] = theta[(size_t)b * theta_stride + i];
   __syncwarp();
-  {
-@@HINIT@@
-  }
   // ---- terminal condition P = hxx(x_H), W = hxe(x_H)  (PDP.py:561-562)
 @@EVAL_TERM@@
   __syncwarp();
@@ -153,8 +168,6 @@ pdp_k_aux_lqr_bwd(int B, int H, const double* __restrict__ X, const double* __re
     #pragma unroll 1
     for (int t = thi; t >= tc; --t) {
       const double* ar = auxc + (t - tc) * PDP_AUXLD;
-@@SCATTER@@
-      __syncwarp();
 @@BACKWARD_STEP@@
       __syncwarp();
     }
@@ -174,7 +187,6 @@ pdp_k_aux_lqr_fwd(int B, int H, const double* __restrict__ X, const double* __re
   const int b = blockIdx.x * PDP_WPBF + (threadIdx.x >> 5);
   if (b >= B) return;
   double* auxc = pdp_smem + (size_t)(threadIdx.x >> 5) * PDP_FWARP_DOUBLES;  // [CH][FLD] dynamics-Jacobian slots
-  double* OUT = auxc + PDP_FOFF_OUT;                                         // output staging (n*r + m*r)
   double* KS = auxc + PDP_FOFF_KS;                                           // K (m x n)
   double* TH = auxc + PDP_FOFF_TH;                                           // theta
   double* DLC = auxc + PDP_FOFF_DL;                                          // [CH][n+m] (x - xref | u - uref)
@@ -190,15 +202,10 @@ pdp_k_aux_lqr_fwd(int B, int H, const double* __restrict__ X, const double* __re
   }
   double* dXb = dX ? dX + (size_t)b * (H + 1) * PDP_N * PDP_R : nullptr;
   double* dUb = dU ? dU + (size_t)b * H * PDP_M * PDP_R : nullptr;
-  const bool want_out = (dXb != nullptr) || (dUb != nullptr);
   __syncwarp();
-  if (dXb) {
-    if (col >= 0) {
-@@X0STAGE@@
-    }
-    __syncwarp();
-    for (int k = lane; k < PDP_N * PDP_R; k += 32) dXb[k] = OUT[k];
-    __syncwarp();
+  if (dXb != nullptr && col >= 0) {
+    double* o = dXb + col;
+@@X0STORE@@
   }
   const bool fused = (loss_dp != nullptr) && (Xref != nullptr);
   const double* Xr = fused ? Xref + (size_t)b * (H + 1) * PDP_N : nullptr;
@@ -250,13 +257,16 @@ pdp_k_aux_lqr_fwd(int B, int H, const double* __restrict__ X, const double* __re
         const double* dl = DLC + (t - tc) * PDP_NM;
 @@DPACC@@
       }
-      if (want_out) {
-        if (col >= 0) {
-@@STAGE@@
+      if (col >= 0) {
+        // each lane stores its column straight from registers (72-byte runs; L2 merges the partial sectors)
+        if (dXb != nullptr) {
+          double* o = dXb + (size_t)(t + 1) * (PDP_N * PDP_R) + col;
+@@XSTORE@@
         }
-        __syncwarp();
-        if (dXb) for (int k = lane; k < PDP_N * PDP_R; k += 32) dXb[(size_t)(t + 1) * PDP_N * PDP_R + k] = OUT[k];
-        if (dUb) for (int k = lane; k < PDP_M * PDP_R; k += 32) dUb[(size_t)t * PDP_M * PDP_R + k] = OUT[PDP_N * PDP_R + k];
+        if (dUb != nullptr) {
+          double* o = dUb + (size_t)t * (PDP_M * PDP_R) + col;
+@@USTORE@@
+        }
       }
       __syncwarp();
 @@XCOPY@@
@@ -299,9 +309,12 @@ extern "C" void pdpmod_info(int* out) {
 }
 
 extern "C" int pdpmod_rollout_costate(int B, int H, const double* x0, const double* theta, int theta_stride, const double* U,
-                                      double* X, double* Lam, double* cost, double* dHu, int* status, cudaStream_t st) {
+                                      double* X, double* Lam, double* cost, double* dHu, int* status,
+                                      const double* fb_gains, const double* fb_X, const double* fb_alpha, double* Uout,
+                                      cudaStream_t st) {
   if (B <= 0) return 0;
-  pdp_k_rollout_costate<<<(B + 127) / 128, 128, 0, st>>>(B, H, x0, theta, theta_stride, U, X, Lam, cost, dHu, status);
+  pdp_k_rollout_costate<<<(B + 127) / 128, 128, 0, st>>>(B, H, x0, theta, theta_stride, U, X, Lam, cost, dHu, status,
+                                                         fb_gains, fb_X, fb_alpha, Uout);
   return (int)cudaGetLastError();
 }
 

@@ -10,7 +10,9 @@ on the controls (single shooting):
        ``NewtonModuleSource`` variant (one column, "Hue" := g): exact second-order Hessians
        (s = 1) with a per-trajectory fall-back to Gauss-Newton / iLQR Hessians (s = 0) and a
        Levenberg shift mu when Quu is not positive definite or the line search fails;
-    3. batched Armijo back-tracking on the rollout cost (every trial is one rollout launch).
+    3. batched Armijo back-tracking with CLOSED-LOOP trial rollouts (DDP style):
+       u_t = u_t + alpha k_t + K_t (x_t - x_t^old), the gains being the ones the Riccati sweep spilled
+       (every trial is one launch of the rollout kernel in feedback mode).
   until max_t |dH/du_t| <= tol for every trajectory.
 
 Everything stays on the device; the host only reads one convergence scalar per iteration.
@@ -54,7 +56,7 @@ class _NewtonSystem:
             backend.check(self.handle.lib.pdp_aux_lqr(self.handle.ptr, B, H, _ptr(X), _ptr(U), _ptr(Lam), _ptr(theta_ext),
                                                       self.nth, None, 0, _ptr(dX), _ptr(dU), None, None, None,
                                                       _ptr(self._ws), self._ws.numel(), _ptr(status), st), "pdp_aux_lqr(newton)")
-        return dU.squeeze(-1), dX.squeeze(-1)
+        return dU.squeeze(-1), dX.squeeze(-1), self._ws
 
 
 def newton_system(oc: OCSystem) -> _NewtonSystem:
@@ -94,7 +96,7 @@ def solve(oc: OCSystem, x0, horizon, theta, control_init=None, tol=1e-8, max_ite
         ext[:, oc.r] = s_newton
         ext[:, oc.r + 1] = mu
         status.zero_()
-        dU, _ = nt.direction(cur["X"], U, cur["Lam"], ext, status)
+        dU, _, gains = nt.direction(cur["X"], U, cur["Lam"], ext, status)
         slope = (cur["dHu"] * dU).sum(dim=(1, 2))
         bad_dir = (status != 0) | ~torch.isfinite(slope) | (slope >= 0)
         # back-tracking line search on the true cost, per trajectory
@@ -105,9 +107,8 @@ def solve(oc: OCSystem, x0, horizon, theta, control_init=None, tol=1e-8, max_ite
         for _ in range(max_backtrack):
             if bool(accepted.all()):
                 break
-            Utry = U + alpha.view(B, 1, 1) * dU
-            Utry = torch.where(torch.isfinite(Utry), Utry, U)
-            trial = oc.rollout_costate(x0, theta, Utry, want_dHu=True)
+            trial = oc.rollout_feedback(x0, theta, U, cur["X"], gains, alpha, want_dHu=True)
+            Utry = trial["U"]
             ok = (~accepted) & torch.isfinite(trial["cost"]) & (trial["cost"] <= cur["cost"] + 1e-4 * alpha * slope)
             if bool(ok.any()):
                 sel = ok.view(B, 1, 1)
@@ -133,3 +134,37 @@ def solve(oc: OCSystem, x0, horizon, theta, control_init=None, tol=1e-8, max_ite
     scale = 1.0 + cur["Lam"].abs().amax(dim=(1, 2))
     return {"X": cur["X"], "U": U, "Lam": cur["Lam"], "cost": cur["cost"], "iters": it,
             "converged": gnorm <= tol * scale, "grad_norm": gnorm}
+
+
+START_SCALES = (0.0, 0.1, 1.0, 1.0, 3.0, 3.0, 10.0, 10.0)
+
+
+def solve_multistart(oc: OCSystem, x0, horizon, theta, n_starts=8, seed=0, **opts):
+    """Several initial control guesses per problem solved as ONE batch; the best stationary point wins.
+
+    Non-convex problems (rocket landing, swing-ups) have several local minima and no local solver -- IPOPT
+    included -- is guaranteed the best one; the reference always cold-starts IPOPT from zero (PDP.py:146-167).
+    Start 0 is that same all-zero guess; the others are seeded Gaussian controls of growing scale."""
+    dev = x0.device
+    B, H, S_ = x0.shape[0], int(horizon), int(n_starts)
+    if S_ <= 1:
+        return solve(oc, x0, H, theta, **opts)
+    if theta.dim() == 1:
+        theta = theta.unsqueeze(0)
+    if theta.shape[0] == 1:
+        theta = theta.expand(B, -1)
+    gen = torch.Generator(device="cpu").manual_seed(int(seed))
+    noise = torch.randn((S_, B, H, oc.m), dtype=torch.float64, generator=gen).to(dev)
+    scales = torch.tensor([START_SCALES[i % len(START_SCALES)] for i in range(S_)], dtype=torch.float64, device=dev)
+    U0 = (noise * scales.view(S_, 1, 1, 1)).reshape(S_ * B, H, oc.m).contiguous()
+    sol = solve(oc, x0.repeat(S_, 1), H, theta.repeat(S_, 1).contiguous(), control_init=U0, **opts)
+    cost = torch.where(sol["converged"] & torch.isfinite(sol["cost"]), sol["cost"], torch.full_like(sol["cost"], float("inf")))
+    cost = cost.view(S_, B)
+    fallback = torch.where(torch.isfinite(sol["cost"]), sol["cost"], torch.full_like(sol["cost"], float("inf"))).view(S_, B)
+    cost = torch.where(torch.isfinite(cost).any(dim=0, keepdim=True), cost, fallback)
+    best = cost.argmin(dim=0)                                   # [B]
+    idx = best * B + torch.arange(B, device=dev)
+    out = {k: sol[k][idx] for k in ("X", "U", "Lam", "cost", "converged", "grad_norm")}
+    out["iters"] = sol["iters"]
+    out["start"] = best
+    return out

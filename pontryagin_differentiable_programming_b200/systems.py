@@ -151,3 +151,14 @@ def cartpole_cp(policy: str = "poly", horizon: int = 50, dt: float = 0.05):
 
 SENS_BUILDERS = {"sysid_quadrotor": quadrotor_sysid,
                  "cp_cartpole_poly": lambda: cartpole_cp("poly"), "cp_cartpole_neural": lambda: cartpole_cp("neural")}
+
+
+@functools.lru_cache(maxsize=None)
+def rocket_oc_adjoint(dt: float = 0.1):
+    """C4: rocket powered-landing OC, n=13 m=3, gradient dJ/dU by the costate kernel (reference
+    Examples/OC/rocket/rocket_PDP_Recmat.py:10-23 parameters; recmat semantics PDP/PDP.py:1100-1114)."""
+    from .symbolic import SX
+    env = _jinenv().Rocket()
+    env.initDyn(Jx=0.5, Jy=1., Jz=1., mass=1., l=1.)
+    env.initCost(wr=1, wv=1, wtilt=50, ww=1, wsidethrust=1, wthrust=0.4)
+    return engine.OCSystem(env.X, env.U, SX.sym('unused_auxvar'), env.X + dt * env.f, env.path_cost, env.final_cost)

@@ -121,7 +121,7 @@ def test_k6_live_reference_lqr_and_sensitivity_recursions():
     assert np.allclose(np.stack(sid["state_traj"]), g["fs_sysid_X"], rtol=0, atol=1e-13)
 
 
-@pytest.mark.parametrize("env,demo", [("pendulum", 0), ("pendulum", 3), ("quadrotor", 0), ("robotarm", 1)])
+@pytest.mark.parametrize("env,demo", [("pendulum", 0), ("pendulum", 3), ("quadrotor", 0), ("robotarm", 1), ("cartpole", 2)])
 def test_k2_oracle_oc_solver_reproduces_shipped_ipopt_demos(env, demo):
     """The oracle's OC solve from the cold start U = 0 lands on the demo IPOPT found (K2)."""
     from oracle import oc_solve

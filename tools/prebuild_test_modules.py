@@ -12,13 +12,15 @@ from casadi import vertcat  # noqa: E402
 from pontryagin_differentiable_programming_b200 import engine, ocsolver  # noqa: E402
 
 dt11 = np.array([[0.1]])
-for env in ("pendulum", "quadrotor", "robotarm", "rocket"):
+for env in ("pendulum", "quadrotor", "robotarm", "rocket", "cartpole"):
     if env == "pendulum":
         e = JinEnv.SinglePendulum(); e.initDyn(); e.initCost()
     elif env == "quadrotor":
         e = JinEnv.Quadrotor(); e.initDyn(c=0.01); e.initCost(wthrust=0.1)
     elif env == "robotarm":
         e = JinEnv.RobotArm(); e.initDyn(g=0); e.initCost(wu=0.01)
+    elif env == "cartpole":
+        e = JinEnv.CartPole(); e.initDyn(); e.initCost(wu=0.1)
     else:
         e = JinEnv.Rocket(); e.initDyn(); e.initCost(wthrust=0.1)
     oc = PDP.OCSys()
