@@ -287,18 +287,14 @@ def run_gpu(args):
                 worst = max(worst, float(np.max(np.abs(got - ref)) / max(1e-300, np.max(np.abs(ref)))))
         parity = worst
 
-    # ---- e2e: C-ABI host-buffer call, H2D of inputs + D2H of (loss, dp) inside the timed region
-    lib = backend.load_library()
-    ws_bytes = sys_.handle.workspace_bytes(backend.OP_SWEEP_HOST, B, H)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    # ---- e2e: the public host-buffer API (OCSystem.sweep_host -> C-ABI pdp_sweep_host per sub-batch on two
+    #      streams): H2D of every input + all kernels + D2H of (loss, dp, cost) inside the timed region
     ldp_host = torch.empty((B, r + 1), dtype=torch.float64).pin_memory()
     cost_host = torch.empty((B,), dtype=torch.float64).pin_memory()
 
     def e2e_step():
-        backend.check(lib.pdp_sweep_host(sys_.handle.ptr, B, H, pinned[0].data_ptr(), pinned[1].data_ptr(), r,
-                                         pinned[2].data_ptr(), pinned[3].data_ptr(), pinned[4].data_ptr(),
-                                         ldp_host.data_ptr(), cost_host.data_ptr(), 1, ws.data_ptr(), ws_bytes,
-                                         stream.cuda_stream), "pdp_sweep_host")
+        sys_.sweep_host(pinned[0], pinned[1], pinned[2], pinned[3], pinned[4], ldp_host, cost_h=cost_host,
+                        keep_dtraj=True, n_chunks=args.e2e_chunks, device=dev)
 
     for _ in range(3):
         e2e_step()
@@ -311,7 +307,6 @@ def run_gpu(args):
     barrier()
     e2e_ms = f0.elapsed_time(f1)
     e2e_ok = bool(torch.allclose(ldp_host.to(dev), out["loss_dp"], rtol=1e-12, atol=0))
-    del ws
 
     times = torch.tensor([ms_total, e2e_ms, k_ms, kf_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -351,7 +346,7 @@ def run_gpu(args):
                          "sweep_alg_bytes": alg_bytes_sweep(n, m, r, H) * B,
                          "sweep_achieved_GBps": alg_bytes_sweep(n, m, r, H) * B / (ms_total / args.steps * 1e-3) / 1e9},
             "e2e": {"value": e2e_val, "unit": "sweeps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "pdp_sweep_host (C ABI, pinned host buffers)"},
+                    "api": "OCSystem.sweep_host -> pdp_sweep_host (C ABI, pinned host buffers), %d sub-batches on 2 streams" % args.e2e_chunks},
             "gpu_launches": 3 * args.steps, "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -376,6 +371,7 @@ def main():
     ap.add_argument("--horizon", type=int, default=50)
     ap.add_argument("--ref-sample", type=int, default=256, help="trajectories per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=8)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

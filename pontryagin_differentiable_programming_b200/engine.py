@@ -35,7 +35,7 @@ def _chk(t, shape, name, device):
 class OCSystem:
     """Compiled optimal-control system: rollout/costate, fused getAuxSys+lqrSolver, dense aux eval."""
 
-    def __init__(self, state, control, auxvar, dyn, path_cost, final_cost, chunk=8, warps_per_block=4, min_blocks=1,
+    def __init__(self, state, control, auxvar, dyn, path_cost, final_cost, chunk=16, warps_per_block=4, min_blocks=3,
                  fwd_warps_per_block=4, fwd_min_blocks=4, keep_fg=True, verbose=False):
         self.src = codegen.OCModuleSource(state, control, auxvar, dyn, path_cost, final_cost, chunk, warps_per_block,
                                           min_blocks, fwd_warps_per_block, fwd_min_blocks, keep_fg)
@@ -203,6 +203,58 @@ class OCSystem:
         if ldp is not None:
             res["loss_dp"] = ldp
         return res
+
+    def sweep_host(self, x0_h, theta_h, U_h, Xref_h, Uref_h, loss_dp_h, cost_h=None, keep_dtraj=True, n_chunks=4,
+                   device=None):
+        """End-to-end sweep from PINNED HOST tensors: per sub-batch H2D of (x0, theta, U, Xref, Uref) -> rollout /
+        costate / fused aux-LQR kernels -> D2H of (loss, dp) [and cost], through the C-ABI ``pdp_sweep_host``.
+        The batch is cut into ``n_chunks`` sub-batches issued alternately on two side streams so that the copies
+        of one sub-batch overlap the kernels of the other; the call returns with the work ordered into the
+        current stream (synchronise that stream before reading ``loss_dp_h``)."""
+        require_cuda()
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        B, H = U_h.shape[0], U_h.shape[1]
+        for t_, nm_ in ((x0_h, "x0"), (theta_h, "theta"), (U_h, "U"), (Xref_h, "Xref"), (loss_dp_h, "loss_dp")):
+            if not (t_.is_pinned() and t_.is_contiguous() and t_.dtype == torch.float64):
+                raise ValueError("sweep_host: %s must be a pinned contiguous float64 host tensor" % nm_)
+        ts = 0 if theta_h.shape[0] == 1 else self.r
+        n_chunks = max(1, min(int(n_chunks), B))
+        bounds = [(B * c) // n_chunks for c in range(n_chunks + 1)]
+        sizes = [bounds[c + 1] - bounds[c] for c in range(n_chunks)]
+        per = [self.handle.workspace_bytes(backend.OP_SWEEP_HOST, sz, H) for sz in sizes]
+        key = ("host", dev)
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < sum(per):
+            ws = torch.empty(sum(per), dtype=torch.uint8, device=dev)
+            self._ws[key] = ws
+        if getattr(self, "_side", None) is None:
+            self._side = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+        cur = torch.cuda.current_stream(dev)
+        start = torch.cuda.Event()
+        start.record(cur)
+        lib = self.handle.lib
+        off = 0
+        el = 8
+        with torch.cuda.device(dev):
+            for c in range(n_chunks):
+                lo, sz = bounds[c], sizes[c]
+                st = self._side[c % 2] if n_chunks > 1 else cur
+                if n_chunks > 1 and c < 2:
+                    st.wait_event(start)
+                backend.check(lib.pdp_sweep_host(
+                    self.handle.ptr, sz, H, x0_h.data_ptr() + lo * self.n * el,
+                    theta_h.data_ptr() + (lo * self.r * el if ts else 0), ts, U_h.data_ptr() + lo * H * self.m * el,
+                    Xref_h.data_ptr() + lo * (H + 1) * self.n * el,
+                    (Uref_h.data_ptr() + lo * H * self.m * el) if Uref_h is not None else None,
+                    loss_dp_h.data_ptr() + lo * (self.r + 1) * el,
+                    (cost_h.data_ptr() + lo * el) if cost_h is not None else None, 1 if keep_dtraj else 0,
+                    ws.data_ptr() + off, per[c], st.cuda_stream), "pdp_sweep_host")
+                off += per[c]
+            if n_chunks > 1:
+                for st in self._side:
+                    done = torch.cuda.Event()
+                    done.record(st)
+                    cur.wait_event(done)
 
     def aux_eval(self, X, U, Lam, theta):
         """Dense auxiliary matrices (legacy getAuxSys return value) as a dict of [B,H,...] tensors."""

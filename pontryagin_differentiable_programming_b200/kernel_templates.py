@@ -138,8 +138,7 @@ pdp_k_aux_lqr_bwd(int B, int H, const double* __restrict__ X, const double* __re
   if (b >= B) return;
   double* auxc = pdp_smem + (size_t)(threadIdx.x >> 5) * PDP_WARP_DOUBLES;   // [CH][AUXLD]
   double* ZT = auxc + PDP_OFF_ZT;                                            // Z^T staging
-  double* KS = auxc + PDP_OFF_KS;                                            // K (m x n)
-  double* QUU = auxc + PDP_OFF_QUU;                                          // m x m
+  double* QU = auxc + PDP_OFF_QU;                                            // [Qux | Quu] rows of the m control lanes
   double* TH = auxc + PDP_OFF_TH;                                            // theta
   double* TB = auxc;                                                         // terminal buffer aliases the chunk buffer
   const int lrow = lane < PDP_NS ? lane : 0;
@@ -162,6 +161,7 @@ pdp_k_aux_lqr_bwd(int B, int H, const double* __restrict__ X, const double* __re
   __syncwarp();
   #pragma unroll 1
   for (int tc = ((H - 1) / PDP_CH) * PDP_CH; tc >= 0; tc -= PDP_CH) {
+    __syncwarp();            // every lane is done reading the previous chunk's slots
 @@EVAL_AUX_CHUNK@@
     __syncwarp();
     const int thi = (tc + PDP_CH < H ? tc + PDP_CH : H) - 1;
@@ -169,7 +169,7 @@ pdp_k_aux_lqr_bwd(int B, int H, const double* __restrict__ X, const double* __re
     for (int t = thi; t >= tc; --t) {
       const double* ar = auxc + (t - tc) * PDP_AUXLD;
 @@BACKWARD_STEP@@
-      __syncwarp();
+      // no barrier needed here: the two barriers inside the step already order ZT / QU reuse (see DESIGN.md)
     }
   }
   if (status && bad) { if (lane == 0) atomicOr(&status[b], 2); }

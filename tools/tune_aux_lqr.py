@@ -14,7 +14,8 @@ sys.path.insert(0, ROOT)
 
 # (chunk, bwd warps/block, bwd min blocks, fwd warps/block, fwd min blocks)
 # (chunk, bwd warps/block, bwd min blocks, fwd warps/block, fwd min blocks, keep [F|G] slots in registers A->C)
-VARIANTS = ([(8, 4, mb, 4, 4, kf) for mb in (1, 3, 4) for kf in (True, False)] +
+VARIANTS = [(16, 4, 3, 4, 4, True), (16, 4, 1, 4, 4, True), (16, 4, 3, 4, 3, True), (32, 4, 3, 4, 4, True), (16, 2, 6, 2, 8, True), (16, 4, 3, 4, 4, False), (8, 4, 3, 4, 4, True)]
+_OLD = ([(8, 4, mb, 4, 4, kf) for mb in (1, 3, 4) for kf in (True, False)] +
             [(8, 4, 3, 4, mf, True) for mf in (2, 3)] + [(16, 4, 3, 4, 4, True), (4, 4, 3, 4, 4, True), (8, 2, 6, 2, 8, True)])
 
 
