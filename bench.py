@@ -182,7 +182,7 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     H = args.horizon
-    per_core = max(2, args.ref_sample // cores)
+    per_core = args.ref_per_core
     for _ in range(min(args.warmup, 1)):
         cpu_sweeps_per_s(H, 1, cores)
     vals = []
@@ -333,6 +333,8 @@ def run_gpu(args):
                        "l2": "per-step working set %.2f GB per GPU >> 126 MB L2 (no flush needed)"
                              % ((alg_bytes_sweep(n, m, r, H) * B) / 1e9),
                        "parity_max_rel_err_vs_oracle_first4": parity, "status_flagged_trajectories": nbad,
+                       "status_note": "flag bit 1 = Quu not positive definite: expected for random (non-optimal) controls, "
+                                      "the sweep is still the reference's algebra (parity above); 0 at OC optima (tests)",
                        "e2e_matches_device_path": e2e_ok},
             "roofline": {"kernel": "pdp_k_aux_lqr_bwd", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
@@ -351,7 +353,7 @@ def run_gpu(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            per_core = max(2, args.ref_sample // cores)
+            per_core = args.ref_per_core
             v, wall = cpu_sweeps_per_s(H, per_core, cores)
             line["cpu_baseline"] = {"value": v, "unit": "sweeps/s", "cores": cores, "kind": "port",
                                     "sample": "%d trajectories of the same workload (%d per core), %.1f s wall"
@@ -369,7 +371,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=16384, help="trajectories per GPU")
     ap.add_argument("--horizon", type=int, default=50)
-    ap.add_argument("--ref-sample", type=int, default=256, help="trajectories per CPU-baseline step")
+    ap.add_argument("--ref-per-core", type=int, default=48,
+                    help="trajectories per host core in one CPU-baseline step (about 2 s of work per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=8)
     args = ap.parse_args()

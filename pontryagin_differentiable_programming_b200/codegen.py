@@ -338,9 +338,9 @@ class OCModuleSource:
         needed = {e[1] for row in self.S_ent for e in row if e[0] == "v"}
         load = _SlotLoader(L, "ar", needed, ind, "sa")
         acc = _Acc("z", ns, L, ind)
-        ents = [(j, k) for k in range(n) for j in range(ns) if self.S_ent[k][j][0] != "z"]
-        for j, k in _interleave(ents, lambda e: e[0]):
-            acc.add(j, "y%d" % k, self.S_ent[k][j], load)
+        for k in range(n):
+            for j in range(ns):
+                acc.add(j, "y%d" % k, self.S_ent[k][j], load)
         acc.finish()
         # phase B: transpose through shared memory
         L.append(ind + "// B: lane j picks up column j of Z; the auxvar lanes add their column of W")
@@ -368,26 +368,22 @@ class OCModuleSource:
             load = _SlotLoader(L, "ar", needed, ind, "sc")
         acc = _Acc("q", nm, L, ind)
         acc.touched = [True] * nm
-        ents = [(l, k) for k in range(n) for l in range(nm) if self.S_ent[k][l][0] != "z"]
-        for l, k in _interleave(ents, lambda e: e[0]):
-            acc.add(l, "c%d" % k, self.S_ent[k][l], load)
-        # phase D/E: the m control rows publish their whole Q row (Qux | Quu); every lane factors Quu (LDL^T,
-        # uniform code), solves for the column it owns and applies the rank-m update with ITS OWN solution:
-        #   Y(j,:) <- Q(j,0:n) + v_j^T Qux,   v_j = -Quu^{-1} Q(j,n:n+m)^T   (= K(:,j) for j < n, k(:,c) for the aux lanes)
-        ldq = self.ldq
-        L.append(ind + "// D: rows n..n+m-1 publish [Qux | Quu]; LDL^T of Quu in every lane, own right-hand side")
+        for k in range(n):
+            for l in range(nm):
+                acc.add(l, "c%d" % k, self.S_ent[k][l], load)
+        # phase D: Quu to smem, LDL^T in every lane, solve for own right-hand side
+        L.append(ind + "// D: Quu = rows n..n+m-1; every lane factors it (LDL^T, uniform) and solves for its own column")
         L.append(ind + "if (lane >= %d && lane < %d) {" % (n, nm))
-        L.append(ind + "  double* qr = QU + (lane - %d) * %d;" % (n, ldq))
-        for l in range(0, nm - 1, 2):
-            L.append(ind + "  *reinterpret_cast<double2*>(qr + %d) = make_double2(q%d, q%d);" % (l, l, l + 1))
-        if nm % 2 == 1:
-            L.append(ind + "  qr[%d] = q%d;" % (nm - 1, nm - 1))
+        for a in range(m):
+            L.append(ind + "  QUU[(lane - %d) * %d + %d] = q%d;" % (n, m, a, n + a))
         L.append(ind + "}")
         L.append(ind + "__syncwarp();")
+        # LDL^T: A = L D L^T, unit lower L.  d_i, l_ij (i>j)
         for i in range(m):
             for j in range(i + 1):
-                L.append(ind + "double a%d%d = QU[%d];" % (i, j, i * ldq + n + j))
+                L.append(ind + "double a%d%d = QUU[%d];" % (i, j, i * m + j))
         for j in range(m):
+            # d_j = a_jj - sum_k l_jk^2 d_k
             expr = "a%d%d" % (j, j)
             for k in range(j):
                 expr = "fma(-l%d%d * l%d%d, d%d, %s)" % (j, k, j, k, k, expr)
@@ -399,6 +395,7 @@ class OCModuleSource:
                 for k in range(j):
                     expr = "fma(-l%d%d * l%d%d, d%d, %s)" % (i, k, j, k, k, expr)
                 L.append(ind + "const double l%d%d = (%s) * r%d;" % (i, j, expr, j))
+        # solve L D L^T v = -rhs ; rhs = q[n..n+m-1]
         for i in range(m):
             expr = "-q%d" % (n + i)
             for k in range(i):
@@ -409,17 +406,27 @@ class OCModuleSource:
             for k in range(i + 1, m):
                 expr = "fma(-l%d%d, v%d, %s)" % (k, i, k, expr)
             L.append(ind + "const double v%d = %s;" % (i, expr))
-        L.append(ind + "// E: spill (K|k) for the forward pass; rank-m update with the broadcast Qux rows")
+        # phase E: spill gains, share K, update
+        L.append(ind + "// E: spill (K|k) for the forward pass, broadcast K, rank-m update of the stack")
+        L.append(ind + "if (lane < %d) {" % n)
+        for a in range(m):
+            L.append(ind + "  KS[%d + lane] = v%d;" % (a * self.ldk, a))
+        L.append(ind + "}")
         L.append(ind + "if (gslot >= 0) {")
         L.append(ind + "  double* gp = gains + ((size_t)b * H + t) * %d + gslot * %d;" % ((n + r) * m, m))
         L.append(self._vec_store("gp", ["v%d" % a for a in range(m)], ind + "  "))
         L.append(ind + "}")
-        for bb in range(m):
-            for l in range(0, n - 1, 2):
-                L.append(ind + "{ const double2 kk = *reinterpret_cast<const double2*>(QU + %d); q%d = fma(v%d, kk.x, q%d); q%d = fma(v%d, kk.y, q%d); }"
-                         % (bb * ldq + l, l, bb, l, l + 1, bb, l + 1))
-            if n % 2 == 1:
-                L.append(ind + "q%d = fma(v%d, QU[%d], q%d);" % (n - 1, bb, bb * ldq + n - 1, n - 1))
+        L.append(ind + "__syncwarp();")
+        for a in range(m):
+            if self.ldk % 2 == 0:
+                for l in range(0, n - 1, 2):
+                    L.append(ind + "{ const double2 kk = *reinterpret_cast<const double2*>(KS + %d); q%d = fma(q%d, kk.x, q%d); q%d = fma(q%d, kk.y, q%d); }"
+                             % (a * self.ldk + l, l, n + a, l, l + 1, n + a, l + 1))
+                if n % 2 == 1:
+                    L.append(ind + "q%d = fma(q%d, KS[%d], q%d);" % (n - 1, n + a, a * self.ldk + n - 1, n - 1))
+            else:
+                for l in range(n):
+                    L.append(ind + "q%d = fma(q%d, KS[%d], q%d);" % (l, n + a, a * self.ldk + l, l))
         for l in range(n):
             L.append(ind + "y%d = q%d;" % (l, l))
         return "\n".join(L)
@@ -483,8 +490,9 @@ class OCModuleSource:
         ks_size = _even(m * self.ldk)
         auxc_size = _even(max(self.chunk * self.auxld, n * n + n * r))
         off_zt = auxc_size
-        off_qu = off_zt + zt_size
-        off_th = off_qu + _even(m * self.ldq)
+        off_ks = off_zt + zt_size
+        off_quu = off_ks + ks_size
+        off_th = off_quu + _even(m * m)
         warp_doubles = _even(off_th + max(self.nth, 1))
         # forward kernel: [CH][FLD] dynamics slots | OUT | KS | TH | DLC
         fld = _pad_ld(self.nvar_s)
@@ -495,7 +503,7 @@ class OCModuleSource:
         defs = {
             "N": n, "M": m, "R": r, "NS": ns, "NM": nm, "NVAR": self.nvar, "NVAR_S": self.nvar_s,
             "AUXLD": self.auxld, "CH": self.chunk, "WPB": self.wpb, "LDZ": self.ldz,
-            "LDK": self.ldk, "LDQ": self.ldq, "OFF_ZT": off_zt, "OFF_QU": off_qu, "OFF_TH": off_th,
+            "LDK": self.ldk, "OFF_ZT": off_zt, "OFF_KS": off_ks, "OFF_QUU": off_quu, "OFF_TH": off_th,
             "FLD": fld, "FOFF_KS": foff_ks, "FOFF_TH": foff_th, "FOFF_DL": foff_dl,
             "FWARP_DOUBLES": fwarp_doubles, "WPBF": getattr(self, "wpbf", 4), "MINBF": getattr(self, "min_blocks_f", 1),
             "WARP_DOUBLES": warp_doubles, "NTH": self.nth, "MINB": getattr(self, "min_blocks", 1), "NHS": nhs, "KH": kh, "GREC": (n + r) * m,

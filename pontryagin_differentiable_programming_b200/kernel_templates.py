@@ -138,7 +138,8 @@ pdp_k_aux_lqr_bwd(int B, int H, const double* __restrict__ X, const double* __re
   if (b >= B) return;
   double* auxc = pdp_smem + (size_t)(threadIdx.x >> 5) * PDP_WARP_DOUBLES;   // [CH][AUXLD]
   double* ZT = auxc + PDP_OFF_ZT;                                            // Z^T staging
-  double* QU = auxc + PDP_OFF_QU;                                            // [Qux | Quu] rows of the m control lanes
+  double* KS = auxc + PDP_OFF_KS;                                            // K (m x n)
+  double* QUU = auxc + PDP_OFF_QUU;                                          // m x m
   double* TH = auxc + PDP_OFF_TH;                                            // theta
   double* TB = auxc;                                                         // terminal buffer aliases the chunk buffer
   const int lrow = lane < PDP_NS ? lane : 0;
@@ -169,7 +170,7 @@ pdp_k_aux_lqr_bwd(int B, int H, const double* __restrict__ X, const double* __re
     for (int t = thi; t >= tc; --t) {
       const double* ar = auxc + (t - tc) * PDP_AUXLD;
 @@BACKWARD_STEP@@
-      // no barrier needed here: the two barriers inside the step already order ZT / QU reuse (see DESIGN.md)
+      __syncwarp();
     }
   }
   if (status && bad) { if (lane == 0) atomicOr(&status[b], 2); }

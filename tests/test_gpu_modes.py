@@ -300,3 +300,40 @@ def test_batched_ocsolver_and_fused_irl_gradient_equal_legacy_path():
     dp_ref = (g3["quadrotor_0_theta"][0] - g3["quadrotor_0_theta_next"][0]) / lr
     assert abs(ldp[0] - g3["quadrotor_0_loss"][0]) < 1e-5 * g3["quadrotor_0_loss"][0]
     assert np.max(np.abs(ldp[1:] - dp_ref)) < 1e-5 * np.max(np.abs(dp_ref))
+
+
+def test_device_resident_irl_loop_follows_the_shipped_parameter_trace():
+    """IRLTrainer (batched ocSolver + fused sweep + update) reproduces consecutive rows of the shipped
+    quadrotor trial-0 parameter trace: theta_{k+1} = theta_k - lr * dp(theta_k)."""
+    from pontryagin_differentiable_programming_b200 import irl, systems
+    dev = _dev()
+    g2 = np.load(os.path.join(G, "k2_demos.npz"))
+    g3 = np.load(os.path.join(G, "k3_irl_traces.npz"))
+    sys_ = systems.quadrotor_irl(float(g2["quadrotor_dt"][0]))
+    Xd = _t(np.stack([g2["quadrotor_%d_X" % i] for i in range(2)]), dev)
+    Ud = _t(np.stack([g2["quadrotor_%d_U" % i] for i in range(2)]), dev)
+    lr = float(g3["quadrotor_0_lr"][0])
+    trainer = irl.IRLTrainer(sys_, Xd, Ud, lr)
+    for k in range(2):                                        # iters 0 and 1 are consecutive rows of the trace
+        theta = _t(g3["quadrotor_0_theta"][k], dev)
+        loss, theta_next = trainer.step(theta)
+        ref = g3["quadrotor_0_theta_next"][k]
+        assert abs(loss.item() - g3["quadrotor_0_loss"][k]) < 1e-5 * g3["quadrotor_0_loss"][k]
+        assert np.max(np.abs(theta_next.cpu().numpy() - ref)) < 1e-5 * lr * 600 + 1e-9
+
+
+def test_host_buffer_sweep_matches_device_path():
+    from pontryagin_differentiable_programming_b200 import systems
+    import bench
+    dev = _dev()
+    sys_ = systems.quadrotor_irl(0.1)
+    B, H = 37, 21
+    host = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in bench.synth_quadrotor(B, H, seed=3)]
+    ldp = torch.empty((B, 10), dtype=torch.float64).pin_memory()
+    cost = torch.empty((B,), dtype=torch.float64).pin_memory()
+    sys_.sweep_host(host[0], host[1], host[2], host[3], host[4], ldp, cost_h=cost, n_chunks=3, device=dev)
+    torch.cuda.synchronize()
+    d = [h.to(dev) for h in host]
+    ref = sys_.sweep(d[0], d[1], d[2], Xref=d[3], Uref=d[4])
+    assert torch.allclose(ldp.to(dev), ref["loss_dp"], rtol=1e-13, atol=0)
+    assert torch.allclose(cost.to(dev), ref["cost"], rtol=1e-13, atol=0)
