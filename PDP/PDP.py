@@ -530,12 +530,65 @@ class ControlPlanning:
         cost, _, X = self.recmat_step_batched(x0, _dev_tensor(U[None], dev))
         return {'state_traj': X[0].cpu().numpy(), 'control_traj': U, 'cost': cost.cpu().numpy().reshape(1)}
 
-    def _warp_unsupported(self, *a, **k):
-        raise NotImplementedError("time-warped policies (warp_*) are not part of the accelerated hot path yet; "
-                                  "use init_step/step or recmat_* (see DESIGN.md, out of scope)")
+    # -------------------------------------------------------------------------------- time-warped policies
+    # Reference PDP.py:882-1035 composes the dynamics / cost over every interval of a time grid symbolically and
+    # parameterises the control by a Lagrange polynomial whose pivots are the integer warped steps 0..whorizon.
+    # At an integer warped step wt the basis is the identity, so the applied control on interval wt is simply the
+    # wt-th parameter block (the last block never acts).  The warped problem is therefore the original rollout
+    # with piecewise-constant controls, and d(cost)/d(block wt) = sum of dH/du over the interval -- the same
+    # adjoint kernel as recmat_*; no symbolic composition is needed.
+    def warp_init_step(self, horizon, time_grid=None):
+        assert hasattr(self, 'dyn_fn'), 'Please set the dynamics first!'
+        assert hasattr(self, 'path_cost_fn'), 'Please set the path cost first!'
+        assert hasattr(self, 'final_cost_fn'), 'Please set the final cost first!'
+        if time_grid is None:
+            time_grid = numpy.linspace(0, 1, numpy.amin([horizon + 1, 11]))
+        if type(time_grid) == list:
+            time_grid = numpy.array(time_grid)
+        if numpy.isscalar(time_grid) and time_grid == -1:
+            time_grid = numpy.linspace(0, horizon - 1, horizon)      # (sic) the reference's grid for -1, PDP.py:967-968
+        time_grid = numpy.asarray(time_grid, dtype=numpy.float64)
+        self.time_grid = numpy.rint(horizon * time_grid / time_grid[-1]).astype(int)
+        self.whorizon = len(self.time_grid) - 1
+        self.setPolyControl(numpy.linspace(0, self.whorizon, self.whorizon + 1))   # n_auxvar = (whorizon + 1) * m
+        self._interval = numpy.repeat(numpy.arange(self.whorizon), numpy.diff(self.time_grid))
 
-    warp_dynCost = warp_integrateSys = warp_getAuxSys = warp_init_step = warp_step = warp_unwarp = _warp_unsupported
-    recmat_recoveryMatrix = _warp_unsupported
+    def _warp_controls(self, auxvar_value):
+        blocks = _flat(auxvar_value, self.n_auxvar, "auxvar_value").reshape(self.whorizon + 1, self.n_control)
+        return blocks[:self.whorizon]
+
+    def warp_integrateSys(self, ini_state, whorizon, auxvar_value):
+        assert hasattr(self, 'time_grid'), "Warp the dynamics first by runing the method of warp_init_step! "
+        dev = _device()
+        Uw = self._warp_controls(auxvar_value)
+        x0 = _dev_tensor(_flat(ini_state, self.n_state, "ini_state")[None], dev)
+        cost, _, X = self.recmat_step_batched(x0, _dev_tensor(Uw[self._interval][None], dev))
+        return {'wstate_traj': X[0].cpu().numpy()[self.time_grid], 'wcontrol_traj': Uw,
+                'wcost': cost.cpu().numpy().reshape(1, 1)}
+
+    def warp_step(self, ini_state, horizon, auxvar_value):
+        assert hasattr(self, 'time_grid'), "Run warp_init_step first!"
+        dev = _device()
+        Uw = self._warp_controls(auxvar_value)
+        x0 = _dev_tensor(_flat(ini_state, self.n_state, "ini_state")[None], dev)
+        cost, dHu, _ = self.recmat_step_batched(x0, _dev_tensor(Uw[self._interval][None], dev))
+        dw = numpy.zeros((self.whorizon + 1, self.n_control))
+        numpy.add.at(dw, self._interval, dHu[0].cpu().numpy())
+        return cost.cpu().numpy().reshape(1, 1), dw.reshape(-1)
+
+    def warp_unwarp(self, ini_state, horizon, auxvar_value):
+        dev = _device()
+        U = self._warp_controls(auxvar_value)[self._interval]
+        x0 = _dev_tensor(_flat(ini_state, self.n_state, "ini_state")[None], dev)
+        cost, _, X = self.recmat_step_batched(x0, _dev_tensor(U[None], dev))
+        return {'state_traj': X[0].cpu().numpy(), 'control_traj': U, 'cost': cost.cpu().numpy().reshape(1)}
+
+    def _symbolic_composition_unsupported(self, *a, **k):
+        raise NotImplementedError("the symbolic H-fold compositions (warp_dynCost / warp_getAuxSys / "
+                                  "recmat_recoveryMatrix) are not built; warp_step / recmat_step compute the same "
+                                  "losses and gradients with the adjoint kernel (see DESIGN.md)")
+
+    warp_dynCost = warp_getAuxSys = recmat_recoveryMatrix = _symbolic_composition_unsupported
 
 
 def _forward_recursion(dynF, dynG, dUx, dUe, dynE, ini_condition):

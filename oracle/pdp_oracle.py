@@ -333,6 +333,54 @@ class OracleCP:
         return cost, g, X
 
 
+def warp_step(cp: "OracleCP", x0, horizon, time_grid, theta):
+    """Restates ControlPlanning.warp_init_step/warp_step (PDP.py:882-1008) numerically: warped dynamics/cost =
+    composition over each grid interval, Lagrange policy over the integer warped steps, forward sensitivity
+    X_{w+1} = wF X_w + wG U_w with U_w = dUe (dUx = 0), chain rule with the warped cost gradients."""
+    n, m = cp.n, cp.m
+    time_grid = np.asarray(time_grid, dtype=np.float64)
+    grid = np.rint(horizon * time_grid / time_grid[-1]).astype(int)
+    wh = len(grid) - 1
+    pivots = np.linspace(0, wh, wh + 1)
+    r = (wh + 1) * m
+    theta = np.asarray(theta, dtype=np.float64).reshape(wh + 1, m)
+
+    def basis(wt):
+        b = np.ones(wh + 1)
+        for i in range(wh + 1):
+            for j in range(wh + 1):
+                if j != i:
+                    b[i] *= (wt - pivots[j]) / (pivots[i] - pivots[j])
+        return b
+
+    X = np.asarray(x0, dtype=np.float64)
+    dXdth = np.zeros((n, r))
+    cost, grad = 0.0, np.zeros(r)
+    for wt in range(wh):
+        b = basis(wt)
+        u = b @ theta                                               # policy_fn(wt, x, theta)
+        dUe = np.kron(b[None, :], np.eye(m))                        # d u / d theta  (m x r)
+        Sx, Su = np.eye(n), np.zeros((n, m))                        # d x_t / d X_wt, d x_t / d u inside the interval
+        cx_w, cu_w = np.zeros(n), np.zeros(m)
+        x = X.copy()
+        for t in range(grid[wt], grid[wt + 1]):
+            cost += float(np.asarray(cp.path_cost_fn(x, u)))
+            cx = np.asarray(cp.dcx_fn(x, u), dtype=np.float64).reshape(n)
+            cu = np.asarray(cp.dcu_fn(x, u), dtype=np.float64).reshape(m)
+            cx_w += cx @ Sx
+            cu_w += cx @ Su + cu
+            F = np.asarray(cp.dfx_fn(x, u), dtype=np.float64).reshape(n, n)
+            G = np.asarray(cp.dfu_fn(x, u), dtype=np.float64).reshape(n, m)
+            Sx, Su = F @ Sx, F @ Su + G
+            x = np.asarray(cp.dyn_fn(x, u), dtype=np.float64).reshape(n)
+        grad += cx_w @ dXdth + cu_w @ dUe                           # PDP.py:1002-1005
+        dXdth = Sx @ dXdth + Su @ dUe                               # integrateAuxSys with wdynF, wdynG
+        X = x
+    cost += float(np.asarray(cp.final_cost_fn(X)))
+    grad += np.asarray(cp.dhx_fn(X), dtype=np.float64).reshape(n) @ dXdth
+    return cost, grad
+
+
 def build_oc(env: dict, dt, theta_syms=None):
     """OCSys on ``dyn = X + dt*f`` with auxvar = [dyn_params, cost_params] (reference
     ``Examples/IRL/quadrotor/uav_PDP.py:20-27``)."""

@@ -30,10 +30,17 @@ pdp_k_rollout_costate(int B, int H, const double* __restrict__ x0, const double*
   double* Xb = X + (size_t)b * (H + 1) * PDP_N;
   const double* Ub = U + (size_t)b * H * PDP_M;
   const double fb_a = fb_gains ? fb_alpha[b] : 0.0;
+  double un[PDP_M];                       // software prefetch: the next step's control is in flight during this step
+  #pragma unroll
+  for (int i = 0; i < PDP_M; ++i) un[i] = Ub[i];
   #pragma unroll 1
   for (int t = 0; t < H; ++t) {
     #pragma unroll
-    for (int i = 0; i < PDP_M; ++i) u[i] = Ub[t * PDP_M + i];
+    for (int i = 0; i < PDP_M; ++i) u[i] = un[i];
+    if (t + 1 < H) {
+      #pragma unroll
+      for (int i = 0; i < PDP_M; ++i) un[i] = Ub[(t + 1) * PDP_M + i];
+    }
     if (fb_gains != nullptr) {
       const double* g = fb_gains + ((size_t)b * H + t) * ((PDP_N + 1) * PDP_M);
       const double* xo = fb_X + ((size_t)b * (H + 1) + t) * PDP_N;
@@ -66,14 +73,26 @@ pdp_k_rollout_costate(int B, int H, const double* __restrict__ x0, const double*
     double lam[PDP_N], ln[PDP_N], gu[PDP_M];
     double* Lb = Lam + (size_t)b * H * PDP_N;
     pdp_f_dhx(x, th, lam);
+    const double* Ua = fb_gains ? Uout + (size_t)b * H * PDP_M : Ub;      // the controls actually applied
+    double xp[PDP_N], up[PDP_M];          // prefetch of (x_{t-1}, u_{t-1}) while step t is being processed
+    #pragma unroll
+    for (int i = 0; i < PDP_N; ++i) xp[i] = Xb[(H - 1) * PDP_N + i];
+    #pragma unroll
+    for (int i = 0; i < PDP_M; ++i) up[i] = Ua[(H - 1) * PDP_M + i];
     #pragma unroll 1
     for (int t = H - 1; t >= 0; --t) {
       #pragma unroll
       for (int i = 0; i < PDP_N; ++i) Lb[t * PDP_N + i] = lam[i];
       #pragma unroll
-      for (int i = 0; i < PDP_N; ++i) x[i] = Xb[t * PDP_N + i];
+      for (int i = 0; i < PDP_N; ++i) x[i] = xp[i];
       #pragma unroll
-      for (int i = 0; i < PDP_M; ++i) u[i] = fb_gains ? Uout[((size_t)b * H + t) * PDP_M + i] : Ub[t * PDP_M + i];
+      for (int i = 0; i < PDP_M; ++i) u[i] = up[i];
+      if (t > 0) {
+        #pragma unroll
+        for (int i = 0; i < PDP_N; ++i) xp[i] = Xb[(t - 1) * PDP_N + i];
+        #pragma unroll
+        for (int i = 0; i < PDP_M; ++i) up[i] = Ua[(t - 1) * PDP_M + i];
+      }
       if (dHu != nullptr) {
         pdp_f_dHu(x, u, lam, th, gu);
         #pragma unroll

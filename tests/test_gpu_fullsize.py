@@ -1,0 +1,106 @@
+"""BASELINE-size checks through size-independent properties (the oracle only finishes small cases in seconds):
+batch independence, fused-vs-materialised chain rule, linearity of the auxiliary system in its initial condition,
+determinism, ragged horizons / batch sizes, and sharded == unsharded."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _inputs(B, H, dev, seed=0):
+    import bench
+    return [torch.as_tensor(np.ascontiguousarray(a), device=dev) for a in bench.synth_quadrotor(B, H, seed=seed)]
+
+
+def test_c3_full_size_batch_independence_and_chain_rule():
+    """B = 16384, H = 50 (config C3): (a) trajectory b's result does not depend on the rest of the batch (bitwise),
+    (b) the fused (loss, dp) equals the contraction of the materialised dX, dU with the residuals, (c) two
+    launches are bitwise identical."""
+    from pontryagin_differentiable_programming_b200 import systems
+    dev = _dev()
+    sys_ = systems.quadrotor_irl(0.1)
+    B, H = 16384, 50
+    x0, th, U, Xr, Ur = _inputs(B, H, dev)
+    full = sys_.sweep(x0, th, U, Xref=Xr, Uref=Ur)
+    again = sys_.sweep(x0, th, U, Xref=Xr, Uref=Ur)
+    for k in ("X", "Lam", "dX", "dU", "loss_dp"):
+        assert torch.equal(full[k], again[k]), k
+    idx = torch.tensor([0, 1, 31, 32, 33, 4095, 8191, 16383], device=dev)
+    sub = sys_.sweep(x0[idx].contiguous(), th[idx].contiguous(), U[idx].contiguous(), Xref=Xr[idx].contiguous(), Uref=Ur[idx].contiguous())
+    for k in ("X", "Lam", "dX", "dU", "loss_dp"):
+        assert torch.equal(full[k][idx], sub[k]), k
+    # chain rule (reference uav_PDP.py:67-75) from the materialised sensitivities, in torch float64
+    dlx, dlu = full["X"] - Xr, U - Ur
+    loss = (dlx ** 2).sum(dim=(1, 2)) + (dlu ** 2).sum(dim=(1, 2))
+    dp = torch.einsum("bti,btir->br", dlx, full["dX"]) + torch.einsum("bta,btar->br", dlu, full["dU"])
+    ok = torch.isfinite(full["loss_dp"]).all(dim=1) & torch.isfinite(dp).all(dim=1)
+    assert ok.float().mean() > 0.9
+    scale = dp[ok].abs().amax(dim=1, keepdim=True).clamp_min(1e-300)
+    assert ((full["loss_dp"][ok, 1:] - dp[ok]).abs() / scale).max() < 1e-9
+    assert ((full["loss_dp"][ok, 0] - loss[ok]).abs() / loss[ok]).max() < 1e-12
+
+
+def test_aux_system_is_linear_in_its_initial_condition():
+    """X_aux(X0 = a A + b B) - X_aux(0) = a (X_aux(A) - X_aux(0)) + b (X_aux(B) - X_aux(0)) for the fused LQR."""
+    from pontryagin_differentiable_programming_b200 import systems
+    dev = _dev()
+    sys_ = systems.quadrotor_irl(0.1)
+    B, H = 64, 50
+    g = torch.Generator().manual_seed(1)
+    import os
+    g2 = np.load(os.path.join(os.path.dirname(__file__), "golden", "k2_demos.npz"))
+    X = torch.as_tensor(np.repeat(g2["quadrotor_0_X"][None], B, 0), device=dev)
+    U = torch.as_tensor(np.repeat(g2["quadrotor_0_U"][None], B, 0), device=dev)
+    L = torch.as_tensor(np.repeat(g2["quadrotor_0_L"][None], B, 0), device=dev)
+    th = torch.as_tensor(g2["quadrotor_true_parameter"] * 1.05, device=dev)
+    A = torch.randn((B, 13, 9), dtype=torch.float64, generator=g).to(dev)
+    Bm = torch.randn((B, 13, 9), dtype=torch.float64, generator=g).to(dev)
+    run = lambda X0: sys_.aux_lqr(X, U, L, th, X0aux=X0)
+    z, a_, b_, c_ = run(None), run(A), run(Bm), run((0.7 * A - 1.9 * Bm).contiguous())
+    for k in ("dX", "dU"):
+        lhs = c_[k] - z[k]
+        rhs = 0.7 * (a_[k] - z[k]) - 1.9 * (b_[k] - z[k])
+        assert (lhs - rhs).abs().max() < 1e-9 * max(1.0, rhs.abs().max().item())
+
+
+@pytest.mark.parametrize("B,H", [(1, 1), (3, 2), (5, 17), (130, 33)])
+def test_ragged_sizes_match_oracle(B, H):
+    """Edge sizes: single step, single trajectory, batch not a multiple of the block, horizon not a multiple of the chunk."""
+    from oracle import envs, pdp_oracle
+    from pontryagin_differentiable_programming_b200 import systems
+    dev = _dev()
+    sys_ = systems.quadrotor_irl(0.1)
+    oc = pdp_oracle.build_oc(envs.quadrotor(c=0.01, wthrust=0.1), 0.1)
+    x0, th, U, Xr, Ur = _inputs(B, H, dev, seed=5)
+    res = sys_.sweep(x0, th, U, Xref=Xr, Uref=Ur)
+    for b in sorted({0, B - 1}):
+        X, L, cost, dX, dU = pdp_oracle.pdp_sweep(oc, x0[b].cpu().numpy(), U[b].cpu().numpy(), th[b].cpu().numpy())
+        rel = lambda a, r: np.max(np.abs(a - r)) / max(1e-300, np.max(np.abs(r)))
+        assert rel(res["X"][b].cpu().numpy(), X) < 1e-12
+        assert rel(res["Lam"][b].cpu().numpy(), L) < 1e-10
+        assert rel(res["dX"][b].cpu().numpy(), dX) < 1e-7
+        assert rel(res["dU"][b].cpu().numpy(), dU) < 1e-7
+
+
+def test_sharded_equals_unsharded():
+    """Weak-scaling layout: running two contiguous shards separately gives exactly the unsharded per-trajectory results,
+    and the reduction of (loss, dp) over shards equals the global mean (what the one all-reduce computes)."""
+    from pontryagin_differentiable_programming_b200 import distributed, systems
+    dev = _dev()
+    sys_ = systems.quadrotor_irl(0.1)
+    B, H = 1000, 50
+    x0, th, U, Xr, Ur = _inputs(B, H, dev, seed=2)
+    full = sys_.sweep(x0, th, U, Xref=Xr, Uref=Ur, want_traj=False)["loss_dp"]
+    parts = []
+    for rank in range(2):
+        lo, hi = distributed.shard_bounds(B, rank, 2)
+        sl = lambda t: t[lo:hi].contiguous()
+        parts.append(sys_.sweep(sl(x0), sl(th), sl(U), Xref=sl(Xr), Uref=sl(Ur), want_traj=False)["loss_dp"])
+    assert torch.equal(torch.cat(parts), full)

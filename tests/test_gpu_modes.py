@@ -337,3 +337,34 @@ def test_host_buffer_sweep_matches_device_path():
     ref = sys_.sweep(d[0], d[1], d[2], Xref=d[3], Uref=d[4])
     assert torch.allclose(ldp.to(dev), ref["loss_dp"], rtol=1e-13, atol=0)
     assert torch.allclose(cost.to(dev), ref["cost"], rtol=1e-13, atol=0)
+
+
+def test_warp_step_matches_oracle_restatement_of_symbolic_warping():
+    """ControlPlanning.warp_* (adjoint kernel) vs the oracle's numeric restatement of the reference's symbolic
+    time-warping (PDP.py:882-1008) on the cart-pole."""
+    from PDP import PDP
+    from JinEnv import JinEnv
+    _dev()
+    cartpole = JinEnv.CartPole()
+    cartpole.initDyn(mc=0.1, mp=0.1, l=1)
+    cartpole.initCost(wx=0.1, wq=0.6, wdx=0.1, wdq=0.1, wu=0.3)
+    dt, H = 0.05, 23
+    oc = PDP.ControlPlanning()
+    oc.setStateVariable(cartpole.X)
+    oc.setControlVariable(cartpole.U)
+    oc.setDyn(cartpole.X + dt * cartpole.f)
+    oc.setPathCost(cartpole.path_cost)
+    oc.setFinalCost(cartpole.final_cost)
+    oc.warp_init_step(H)                                   # default grid: linspace(0, 1, 11)
+    e = envs.cartpole(mc=0.1, mp=0.1, l=1, wx=0.1, wq=0.6, wdx=0.1, wdq=0.1, wu=0.3)
+    ref = pdp_oracle.OracleCP(e["X"], e["U"], e["X"] + dt * e["f"], e["path_cost"], e["final_cost"])
+    rng = np.random.default_rng(9)
+    theta = rng.standard_normal(oc.n_auxvar)
+    x0 = [0.1, 0.2, -0.1, 0.05]
+    loss, g = oc.warp_step(x0, H, theta)
+    loss_ref, g_ref = pdp_oracle.warp_step(ref, x0, H, np.linspace(0, 1, 11), theta)
+    assert oc.n_auxvar == g_ref.size
+    assert abs(float(loss) - loss_ref) < 1e-11 * abs(loss_ref)
+    assert _rel(g, g_ref) < 1e-10
+    sol = oc.warp_unwarp(x0, H, theta)
+    assert abs(float(sol["cost"]) - loss_ref) < 1e-11 * abs(loss_ref)

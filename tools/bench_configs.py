@@ -69,6 +69,16 @@ def main():
     alg = 8 * (H * 4 + (H + 1) * 13 + 5 + 1)
     rows.append({"config": "C5 quadrotor SysID n=13 r=5 H=100 B=32768/GPU (fused loss)", "ms": ms,
                  "sweeps_per_s": B / ms * 1e3, "alg_bytes": alg, "alg_GBps": alg * B / ms / 1e6})
+    # ---- C5 variants: column-group size x block size of pdp_k_sens_fwd
+    from JinEnv import JinEnv
+    from pontryagin_differentiable_programming_b200 import engine
+    env = JinEnv.Quadrotor()
+    env.initDyn(c=0.01)
+    for gc, blk in ((12, 64), (12, 128), (3, 64), (2, 64), (1, 64), (1, 128), (2, 128)):
+        sv = engine.SysIDSystem(env.X, env.U, env.dyn_auxvar, env.X + 0.1 * env.f, max_group_cols=gc, block=blk)
+        ms = timeit(lambda: sv.step(inputs, Xobs, th))
+        rows.append({"config": "C5 variant group_cols=%d block=%d" % (gc, blk), "ms": ms, "sweeps_per_s": B / ms * 1e3,
+                     "alg_GBps": alg * B / ms / 1e6})
     for r_ in rows:
         print(json.dumps(r_))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
