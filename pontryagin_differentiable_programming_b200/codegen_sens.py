@@ -289,7 +289,10 @@ extern "C" int pdpmod_sens_fwd(int B, int H, const double* x0, const double* the
                                const double* Xobs, double* X, double* Uout, double* dX, double* dU, double* loss_dp,
                                int* status, cudaStream_t st) {
   if (B <= 0) return 0;
-  static bool configured = false;
+  static bool configured_dev[64] = {false};      // the opt-in shared-memory attribute is per device
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  bool& configured = configured_dev[dev_ & 63];
   const size_t smem = (size_t)PDP_GMAX * PDP_N * PDP_BLOCK * sizeof(double);
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(pdp_k_sens_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -354,7 +354,10 @@ extern "C" int pdpmod_aux_lqr(int B, int H, const double* X, const double* U, co
                               const double* Xref, const double* Uref, double* loss_dp,
                               const double* auxrec, const double* termrec, int phases, int* status, cudaStream_t st) {
   if (B <= 0) return 0;
-  static bool configured = false;
+  static bool configured_dev[64] = {false};      // the opt-in shared-memory attribute is per device
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  bool& configured = configured_dev[dev_ & 63];
   const size_t smem_b = (size_t)PDP_WPB * PDP_WARP_DOUBLES * sizeof(double);
   const size_t smem_f = (size_t)PDP_WPBF * PDP_FWARP_DOUBLES * sizeof(double);
   if (!configured) {
