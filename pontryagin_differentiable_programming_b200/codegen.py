@@ -217,8 +217,9 @@ class OCModuleSource:
 
     def __init__(self, state: SX, control: SX, auxvar: SX, dyn: SX, path_cost: SX, final_cost: SX,
                  chunk: int = 8, warps_per_block: int = 4, min_blocks: int = 1, fwd_warps_per_block: int = 4,
-                 fwd_min_blocks: int = 1, keep_fg: bool = True):
+                 fwd_min_blocks: int = 1, keep_fg: bool = True, fast_rcp: bool = False, early_solve: bool = False):
         self.keep_fg = bool(keep_fg)
+        self.fast_rcp, self.early_solve = bool(fast_rcp), bool(early_solve)
         self.min_blocks = int(min_blocks)
         self.wpbf, self.min_blocks_f = int(fwd_warps_per_block), int(fwd_min_blocks)
         self.x, self.u, self.th = state, control, auxvar
@@ -368,9 +369,20 @@ class OCModuleSource:
             load = _SlotLoader(L, "ar", needed, ind, "sc")
         acc = _Acc("q", nm, L, ind)
         acc.touched = [True] * nm
+        early = getattr(self, "early_solve", False)
+        # with early_solve the control columns (Quu / Qxu / Qeu, needed by the factorisation) are accumulated first and
+        # the state columns afterwards, in the same basic block as the serial LDL^T chain so the scheduler can overlap them
+        first_cols = range(n, nm) if early else range(nm)
         for k in range(n):
-            for l in range(nm):
+            for l in first_cols:
                 acc.add(l, "c%d" % k, self.S_ent[k][l], load)
+        late_lines: List[str] = []
+        if early:
+            acc_late = _Acc("q", nm, late_lines, ind)
+            acc_late.touched = [True] * nm
+            for k in range(n):
+                for l in range(n):
+                    acc_late.add(l, "c%d" % k, self.S_ent[k][l], load if getattr(self, "keep_fg", True) else load)
         # phase D: Quu to smem, LDL^T in every lane, solve for own right-hand side
         L.append(ind + "// D: Quu = rows n..n+m-1; every lane factors it (LDL^T, uniform) and solves for its own column")
         L.append(ind + "if (lane >= %d && lane < %d) {" % (n, nm))
@@ -389,12 +401,22 @@ class OCModuleSource:
                 expr = "fma(-l%d%d * l%d%d, d%d, %s)" % (j, k, j, k, k, expr)
             L.append(ind + "const double d%d = %s;" % (j, expr))
             L.append(ind + "bad |= !(d%d > 0.0);" % j)
-            L.append(ind + "const double r%d = 1.0 / d%d;" % (j, j))
+            if getattr(self, "fast_rcp", False):
+                # reciprocal = hardware seed + two Newton steps (<= 1 ulp; no special-case slow path in the chain)
+                L.append(ind + "double r%d; asm(\"rcp.approx.ftz.f64 %%0, %%1;\" : \"=d\"(r%d) : \"d\"(d%d));" % (j, j, j))
+                L.append(ind + "r%d = fma(r%d, fma(-d%d, r%d, 1.0), r%d);" % (j, j, j, j, j))
+                L.append(ind + "r%d = fma(r%d, fma(-d%d, r%d, 1.0), r%d);" % (j, j, j, j, j))
+            else:
+                L.append(ind + "const double r%d = 1.0 / d%d;" % (j, j))
             for i in range(j + 1, m):
                 expr = "a%d%d" % (i, j)
                 for k in range(j):
                     expr = "fma(-l%d%d * l%d%d, d%d, %s)" % (i, k, j, k, k, expr)
                 L.append(ind + "const double l%d%d = (%s) * r%d;" % (i, j, expr, j))
+            if late_lines:   # a slice of the independent state-column FMAs after every pivot
+                take = (len(late_lines) + (m - j) - 1) // (m - j)
+                L.extend(late_lines[:take])
+                del late_lines[:take]
         # solve L D L^T v = -rhs ; rhs = q[n..n+m-1]
         for i in range(m):
             expr = "-q%d" % (n + i)

@@ -30,7 +30,10 @@ from .engine import OCSystem, _ptr, require_cuda
 class _NewtonSystem:
     def __init__(self, oc: OCSystem):
         s = oc.src
-        self.src = codegen.NewtonModuleSource(s.x, s.u, s.th, s.dyn, s.c, s.h, chunk=s.chunk, warps_per_block=s.wpb)
+        self.src = codegen.NewtonModuleSource(s.x, s.u, s.th, s.dyn, s.c, s.h, chunk=s.chunk, warps_per_block=s.wpb,
+                                              min_blocks=s.min_blocks, fwd_warps_per_block=s.wpbf,
+                                              fwd_min_blocks=s.min_blocks_f, keep_fg=s.keep_fg, fast_rcp=s.fast_rcp,
+                                              early_solve=s.early_solve)
         self.module_path = build.compile_module(self.src.source(), self.src.key())
         self._handle = None
         self.n, self.m, self.nth = self.src.n, self.src.m, self.src.nth

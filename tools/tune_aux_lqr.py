@@ -14,12 +14,15 @@ sys.path.insert(0, ROOT)
 
 # (chunk, bwd warps/block, bwd min blocks, fwd warps/block, fwd min blocks)
 # (chunk, bwd warps/block, bwd min blocks, fwd warps/block, fwd min blocks, keep [F|G] slots in registers A->C)
-VARIANTS = [(16, 4, 3, 4, 4, True), (16, 4, 1, 4, 4, True), (16, 4, 3, 4, 3, True), (32, 4, 3, 4, 4, True), (16, 2, 6, 2, 8, True), (16, 4, 3, 4, 4, False), (8, 4, 3, 4, 4, True)]
+# (chunk, bwd warps/block, bwd min blocks, fwd warps/block, fwd min blocks, keep_fg, fast_rcp, early_solve)
+VARIANTS = [(16, 4, 3, 4, 4, True, False, False), (16, 4, 3, 4, 4, True, True, False), (16, 4, 3, 4, 4, True, False, True),
+            (16, 4, 3, 4, 4, True, True, True), (16, 4, 1, 4, 4, True, True, True), (16, 4, 4, 4, 4, True, True, True),
+            (16, 4, 4, 4, 4, False, True, True)]
 _OLD = ([(8, 4, mb, 4, 4, kf) for mb in (1, 3, 4) for kf in (True, False)] +
             [(8, 4, 3, 4, mf, True) for mf in (2, 3)] + [(16, 4, 3, 4, 4, True), (4, 4, 3, 4, 4, True), (8, 2, 6, 2, 8, True)])
 
 
-def make(ch, wpb, mb, wpbf=4, mbf=1, kf=True, verbose=False):
+def make(ch, wpb, mb, wpbf=4, mbf=1, kf=True, frcp=False, early=False, verbose=False):
     from JinEnv import JinEnv
     from pontryagin_differentiable_programming_b200 import engine
     from pontryagin_differentiable_programming_b200.symbolic import vertcat
@@ -28,7 +31,7 @@ def make(ch, wpb, mb, wpbf=4, mbf=1, kf=True, verbose=False):
     env.initCost(wthrust=0.1)
     return engine.OCSystem(env.X, env.U, vertcat(env.dyn_auxvar, env.cost_auxvar), env.X + 0.1 * env.f, env.path_cost,
                            env.final_cost, chunk=ch, warps_per_block=wpb, min_blocks=mb, fwd_warps_per_block=wpbf,
-                           fwd_min_blocks=mbf, keep_fg=kf, verbose=verbose)
+                           fwd_min_blocks=mbf, keep_fg=kf, fast_rcp=frcp, early_solve=early, verbose=verbose)
 
 
 def main():
@@ -39,7 +42,7 @@ def main():
     args = ap.parse_args()
     if args.build:
         for v in VARIANTS:
-            print("== variant chunk=%d wpb=%d minb=%d wpbf=%d minbf=%d keep_fg=%s" % v)
+            print("== variant", v)
             make(*v, verbose=True)
     if args.run:
         import numpy as np
@@ -67,7 +70,7 @@ def main():
                 e1.record()
                 torch.cuda.synchronize()
                 ms[phase] = e0.elapsed_time(e1) / 10
-            rows.append({"chunk": v[0], "wpb": v[1], "minb": v[2], "wpbf": v[3], "minbf": v[4], "keep_fg": v[5], "bwd_ms": ms["backward"],
+            rows.append({"chunk": v[0], "wpb": v[1], "minb": v[2], "wpbf": v[3], "minbf": v[4], "keep_fg": v[5], "fast_rcp": v[6], "early_solve": v[7], "bwd_ms": ms["backward"],
                          "fwd_ms": ms["forward"], "sweeps_per_s": B / (ms["backward"] + ms["forward"]) * 1e3})
             print(json.dumps(rows[-1]), flush=True)
             del out
