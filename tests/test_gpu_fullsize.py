@@ -104,3 +104,23 @@ def test_sharded_equals_unsharded():
         sl = lambda t: t[lo:hi].contiguous()
         parts.append(sys_.sweep(sl(x0), sl(th), sl(U), Xref=sl(Xr), Uref=sl(Ur), want_traj=False)["loss_dp"])
     assert torch.equal(torch.cat(parts), full)
+
+
+def test_empty_batch_and_status_flags():
+    """B = 0 is a no-op that returns correctly shaped empty tensors; a non-finite input raises status bit 0 for that
+    trajectory only; an indefinite Quu raises bit 1 (the C ABI never throws for data-dependent conditions)."""
+    from pontryagin_differentiable_programming_b200 import systems
+    dev = _dev()
+    sys_ = systems.quadrotor_irl(0.1)
+    H = 7
+    e = lambda *s: torch.empty(s, dtype=torch.float64, device=dev)
+    res = sys_.sweep(e(0, 13), e(0, 9), e(0, H, 4))
+    assert res["dX"].shape == (0, H + 1, 13, 9) and res["X"].shape == (0, H + 1, 13)
+    x0, th, U, _, _ = _inputs(6, H, dev, seed=8)
+    U[2, 3, 1] = float("nan")
+    status = torch.zeros(6, dtype=torch.int32, device=dev)
+    res = sys_.sweep(x0, th, U, status=status)
+    torch.cuda.synchronize()
+    st = status.cpu().numpy()
+    assert st[2] & 1 and not (st[[0, 1, 3, 4, 5]] & 1).any()
+    assert torch.isfinite(res["dX"][[0, 1, 3, 4, 5]]).all() or (st[[0, 1, 3, 4, 5]] & 2).any()
