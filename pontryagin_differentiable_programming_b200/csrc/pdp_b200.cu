@@ -129,6 +129,7 @@ int pdp_rollout_costate(pdp_system_t* sys, int B, int H, const double* x0, const
                         const double* U, double* X, double* Lam, double* cost, double* dHu, int* status,
                         pdp_stream_t stream) {
   if (!sys || !sys->rollout) return fail(PDP_ERR_UNSUPPORTED, "pdp_rollout_costate: module has no rollout kernel");
+  if (B == 0) return PDP_OK;  /* empty batch: nothing to do, pointers may be NULL */
   if (B < 0 || H < 1 || !x0 || !theta || !U || !X) return fail(PDP_ERR_ARG, "pdp_rollout_costate: bad argument");
   if (dHu && !Lam) return fail(PDP_ERR_ARG, "pdp_rollout_costate: dHu needs Lam");
   int e = sys->rollout(B, H, x0, theta, theta_stride, U, X, Lam, cost, dHu, status, nullptr, nullptr, nullptr, nullptr,
@@ -141,6 +142,7 @@ int pdp_rollout_feedback(pdp_system_t* sys, int B, int H, const double* x0, cons
                          const double* Uref, const double* Xref, const double* gains, const double* alpha, double* Uout,
                          double* X, double* Lam, double* cost, double* dHu, int* status, pdp_stream_t stream) {
   if (!sys || !sys->rollout) return fail(PDP_ERR_UNSUPPORTED, "pdp_rollout_feedback: module has no rollout kernel");
+  if (B == 0) return PDP_OK;  /* empty batch: nothing to do, pointers may be NULL */
   if (B < 0 || H < 1 || !x0 || !theta || !Uref || !Xref || !gains || !alpha || !Uout || !X)
     return fail(PDP_ERR_ARG, "pdp_rollout_feedback: bad argument");
   if (dHu && !Lam) return fail(PDP_ERR_ARG, "pdp_rollout_feedback: dHu needs Lam");
@@ -156,6 +158,7 @@ static int aux_lqr_phases(int phases, pdp_system_t* sys, int B, int H, const dou
                 void* workspace, size_t ws_bytes, int* status, pdp_stream_t stream) {
   if (!sys || !sys->aux_lqr || sys->kind() != PDP_KIND_OC)
     return fail(PDP_ERR_UNSUPPORTED, "pdp_aux_lqr: module has no fused aux-LQR kernel");
+  if (B == 0) return PDP_OK;  /* empty batch: nothing to do, pointers may be NULL */
   if (B < 0 || H < 1 || !X || !U || !Lam || !theta) return fail(PDP_ERR_ARG, "pdp_aux_lqr: bad argument");
   if (loss_dp && !Xref) return fail(PDP_ERR_ARG, "pdp_aux_lqr: loss_dp needs Xref");
   if (ws_bytes < pdp_workspace_bytes(sys, PDP_OP_AUX_LQR, B, H) || (B > 0 && !workspace))
@@ -196,6 +199,7 @@ int pdp_lqr_dense(pdp_system_t* sys, int B, int H, const double* aux, const doub
                   int* status, pdp_stream_t stream) {
   if (!sys || !sys->aux_lqr || sys->kind() != PDP_KIND_LQR)
     return fail(PDP_ERR_UNSUPPORTED, "pdp_lqr_dense: not a dense-LQR module");
+  if (B == 0) return PDP_OK;  /* empty batch: nothing to do, pointers may be NULL */
   if (B < 0 || H < 1 || !aux || (!term && !forward_only)) return fail(PDP_ERR_ARG, "pdp_lqr_dense: bad argument");
   if (ws_bytes < pdp_workspace_bytes(sys, PDP_OP_AUX_LQR, B, H) || (B > 0 && !workspace))
     return fail(PDP_ERR_WORKSPACE, "pdp_lqr_dense: workspace too small");
@@ -210,6 +214,7 @@ int pdp_sweep(pdp_system_t* sys, int B, int H, const double* x0, const double* t
               const double* U, double* X, double* Lam, double* cost, double* dXdtheta, double* dUdtheta,
               const double* Xref, const double* Uref, double* loss_dp, void* workspace, size_t ws_bytes,
               int* status, pdp_stream_t stream) {
+  if (B == 0) return PDP_OK;
   if (!Lam) return fail(PDP_ERR_ARG, "pdp_sweep: Lam buffer required");
   int e = pdp_rollout_costate(sys, B, H, x0, theta, theta_stride, U, X, Lam, cost, nullptr, status, stream);
   if (e) return e;
@@ -220,6 +225,7 @@ int pdp_sweep(pdp_system_t* sys, int B, int H, const double* x0, const double* t
 int pdp_aux_eval(pdp_system_t* sys, int B, int H, const double* X, const double* U, const double* Lam,
                  const double* theta, int theta_stride, double* aux, double* term, pdp_stream_t stream) {
   if (!sys || !sys->aux_eval) return fail(PDP_ERR_UNSUPPORTED, "pdp_aux_eval: module has no aux-eval kernel");
+  if (B == 0) return PDP_OK;  /* empty batch: nothing to do, pointers may be NULL */
   if (B < 0 || H < 1 || !X || !U || !Lam || !theta || !aux) return fail(PDP_ERR_ARG, "pdp_aux_eval: bad argument");
   int e = sys->aux_eval(B, H, X, U, Lam, theta, theta_stride, aux, term, (cudaStream_t)stream);
   if (e) return fail(PDP_ERR_CUDA, "pdp_aux_eval: CUDA error %d (%s)", e, cudaGetErrorString((cudaError_t)e));
@@ -230,6 +236,7 @@ int pdp_sens_fwd(pdp_system_t* sys, int B, int H, const double* x0, const double
                  const double* inputs, const double* Xobs, double* X, double* Uout, double* dX, double* dU,
                  double* loss_dp, int* status, pdp_stream_t stream) {
   if (!sys || !sys->sens) return fail(PDP_ERR_UNSUPPORTED, "pdp_sens_fwd: module has no forward-sensitivity kernel");
+  if (B == 0) return PDP_OK;  /* empty batch: nothing to do, pointers may be NULL */
   if (B < 0 || H < 1 || !x0 || !theta) return fail(PDP_ERR_ARG, "pdp_sens_fwd: bad argument");
   int e = sys->sens(B, H, x0, theta, theta_stride, inputs, Xobs, X, Uout, dX, dU, loss_dp, status, (cudaStream_t)stream);
   if (e) return fail(PDP_ERR_CUDA, "pdp_sens_fwd: CUDA error %d (%s)", e, cudaGetErrorString((cudaError_t)e));
@@ -239,6 +246,7 @@ int pdp_sens_fwd(pdp_system_t* sys, int B, int H, const double* x0, const double
 int pdp_eval_function(pdp_system_t* sys, int B, const double* const* inputs, const int* input_strides,
                       double* const* outputs, pdp_stream_t stream) {
   if (!sys || !sys->fneval) return fail(PDP_ERR_UNSUPPORTED, "pdp_eval_function: not a function module");
+  if (B == 0) return PDP_OK;  /* empty batch: nothing to do, pointers may be NULL */
   if (B < 0 || !inputs || !input_strides || !outputs) return fail(PDP_ERR_ARG, "pdp_eval_function: bad argument");
   int e = sys->fneval(B, inputs, input_strides, outputs, (cudaStream_t)stream);
   if (e) return fail(PDP_ERR_CUDA, "pdp_eval_function: CUDA error %d (%s)", e, cudaGetErrorString((cudaError_t)e));

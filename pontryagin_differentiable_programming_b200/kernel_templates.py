@@ -8,60 +8,28 @@ K_ROLLOUT_AUXEVAL = r'''
 // Kernel 1: forward rollout + cost + costate recursion (+ optional dH/du), one thread per trajectory.
 //   restates reference OCSys.ocSolver's rollout semantics at given controls (PDP.py:158-175) and the PMP
 //   costate recursion (PDP.py:203-209): Lam[t] = lambda_{t+1}, lambda_H = dh/dx(x_H).
-//   I/O of X and Lam is staged through a per-warp shared-memory tile (PDP_KT steps x n x 32 trajectories,
-//   padded to 33) and moved to / from HBM by the whole warp as contiguous runs: thread-per-trajectory
-//   8-byte accesses touch one 32-byte sector each, which made this kernel sector-throughput bound
-//   (profiles/README.md); the tile copies touch four doubles per sector.
 // =====================================================================================================
-#define PDP_KT (PDP_N <= 16 ? 4 : (PDP_N <= 32 ? 2 : 1))
-#define PDP_TILE (PDP_KT * PDP_N * 33)
-
-__device__ __forceinline__ void pdp_tile_store(const double* T, double* G, size_t traj_stride, int b0,
-                                               int nvalid, int t0, int nt, int lane) {
-  const int cnt = nt * PDP_N;                       // T[(tt * n + i) * 33 + trajectory]
-  for (int bb = 0; bb < nvalid; ++bb) {
-    double* g = G + (size_t)(b0 + bb) * traj_stride + (size_t)t0 * PDP_N;
-    for (int e = lane; e < cnt; e += 32) g[e] = T[e * 33 + bb];
-  }
-}
-
-__device__ __forceinline__ void pdp_tile_load(double* T, const double* G, size_t traj_stride, int b0,
-                                              int nvalid, int t0, int nt, int lane) {
-  const int cnt = nt * PDP_N;
-  for (int bb = 0; bb < nvalid; ++bb) {
-    const double* g = G + (size_t)(b0 + bb) * traj_stride + (size_t)t0 * PDP_N;
-    for (int e = lane; e < cnt; e += 32) T[e * 33 + bb] = g[e];
-  }
-}
-
 extern "C" __global__ void __launch_bounds__(128)
 pdp_k_rollout_costate(int B, int H, const double* __restrict__ x0, const double* __restrict__ theta, int theta_stride,
-                      const double* __restrict__ U, double* X, double* __restrict__ Lam,
+                      const double* __restrict__ U, double* __restrict__ X, double* __restrict__ Lam,
                       double* __restrict__ cost, double* __restrict__ dHu, int* __restrict__ status,
                       const double* __restrict__ fb_gains, const double* __restrict__ fb_X,
-                      const double* __restrict__ fb_alpha, double* Uout)
+                      const double* __restrict__ fb_alpha, double* __restrict__ Uout)
 {
   // Optional closed-loop mode (batched ocSolver line search): with fb_gains != NULL the applied control is
   //   u_t = U[t] + alpha_b * k_t + K_t (x_t - fb_X[t])   (gains in the (K|k) record layout of the Riccati
   // sweep with one column) and is written to Uout.
-  extern __shared__ __align__(16) double pdp_smem[];
-  const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b0 = b - lane;                                        // first trajectory of this warp
-  if (b0 >= B) return;                                            // whole warp out of range
-  const bool live = b < B;
-  const int nvalid = (B - b0) < 32 ? (B - b0) : 32;
-  const int bc = live ? b : B - 1;                                // idle lanes shadow the last trajectory (no stores)
-  double* TA = pdp_smem + (size_t)(threadIdx.x >> 5) * (2 * PDP_TILE);   // out tile (X, then Lam)
-  double* TB = TA + PDP_TILE;                                            // in tile (X in the backward loop)
+  if (b >= B) return;
   double x[PDP_N], xn[PDP_N], th[PDP_NTH], u[PDP_M], tmp[1];
   #pragma unroll
-  for (int i = 0; i < PDP_NTH; ++i) th[i] = theta[(size_t)bc * theta_stride + i];
+  for (int i = 0; i < PDP_NTH; ++i) th[i] = theta[(size_t)b * theta_stride + i];
   #pragma unroll
-  for (int i = 0; i < PDP_N; ++i) x[i] = x0[(size_t)bc * PDP_N + i];
+  for (int i = 0; i < PDP_N; ++i) x[i] = x0[(size_t)b * PDP_N + i];
   double J = 0.0;
-  const double* Ub = U + (size_t)bc * H * PDP_M;
-  const double fb_a = fb_gains ? fb_alpha[bc] : 0.0;
+  double* Xb = X + (size_t)b * (H + 1) * PDP_N;
+  const double* Ub = U + (size_t)b * H * PDP_M;
+  const double fb_a = fb_gains ? fb_alpha[b] : 0.0;
   double un[PDP_M];                       // software prefetch: the next step's control is in flight during this step
   #pragma unroll
   for (int i = 0; i < PDP_M; ++i) un[i] = Ub[i];
@@ -74,8 +42,8 @@ pdp_k_rollout_costate(int B, int H, const double* __restrict__ x0, const double*
       for (int i = 0; i < PDP_M; ++i) un[i] = Ub[(t + 1) * PDP_M + i];
     }
     if (fb_gains != nullptr) {
-      const double* g = fb_gains + ((size_t)bc * H + t) * ((PDP_N + 1) * PDP_M);
-      const double* xo = fb_X + ((size_t)bc * (H + 1) + t) * PDP_N;
+      const double* g = fb_gains + ((size_t)b * H + t) * ((PDP_N + 1) * PDP_M);
+      const double* xo = fb_X + ((size_t)b * (H + 1) + t) * PDP_N;
       #pragma unroll
       for (int a = 0; a < PDP_M; ++a) u[a] = fma(fb_a, g[PDP_N * PDP_M + a], u[a]);
       #pragma unroll
@@ -84,86 +52,60 @@ pdp_k_rollout_costate(int B, int H, const double* __restrict__ x0, const double*
         #pragma unroll
         for (int a = 0; a < PDP_M; ++a) u[a] = fma(g[l * PDP_M + a], dx, u[a]);
       }
-      if (live) {
-        #pragma unroll
-        for (int i = 0; i < PDP_M; ++i) Uout[((size_t)b * H + t) * PDP_M + i] = u[i];
-      }
-    }
-    {
-      const int tt = t % PDP_KT;
       #pragma unroll
-      for (int i = 0; i < PDP_N; ++i) TA[(tt * PDP_N + i) * 33 + lane] = x[i];
-      if (tt == PDP_KT - 1) {
-        __syncwarp();
-        pdp_tile_store(TA, X, (size_t)(H + 1) * PDP_N, b0, nvalid, t - (PDP_KT - 1), PDP_KT, lane);
-        __syncwarp();
-      }
+      for (int i = 0; i < PDP_M; ++i) Uout[((size_t)b * H + t) * PDP_M + i] = u[i];
     }
+    #pragma unroll
+    for (int i = 0; i < PDP_N; ++i) Xb[t * PDP_N + i] = x[i];
     pdp_f_path_cost(x, u, th, tmp);
     J += tmp[0];
     pdp_f_dyn(x, u, th, xn);
     #pragma unroll
     for (int i = 0; i < PDP_N; ++i) x[i] = xn[i];
   }
-  {
-    // tail: the remaining steps of the last partial tile plus the terminal state x_H
-    const int done = (H / PDP_KT) * PDP_KT;
-    const int tt = H - done;                                        // 0 .. KT-1 rows already in the tile
-    #pragma unroll
-    for (int i = 0; i < PDP_N; ++i) TA[(tt * PDP_N + i) * 33 + lane] = x[i];
-    __syncwarp();
-    pdp_tile_store(TA, X, (size_t)(H + 1) * PDP_N, b0, nvalid, done, tt + 1, lane);
-    __syncwarp();
-  }
+  #pragma unroll
+  for (int i = 0; i < PDP_N; ++i) Xb[H * PDP_N + i] = x[i];
   pdp_f_final_cost(x, th, tmp);
   J += tmp[0];
-  if (cost && live) cost[b] = J;
+  if (cost) cost[b] = J;
   bool bad = !isfinite(J);
   if (Lam != nullptr) {
     double lam[PDP_N], ln[PDP_N], gu[PDP_M];
+    double* Lb = Lam + (size_t)b * H * PDP_N;
     pdp_f_dhx(x, th, lam);
-    const double* Ua = fb_gains ? Uout + (size_t)bc * H * PDP_M : Ub;      // the controls actually applied
-    __threadfence_block();                                                    // X / Uout written above are re-read below
-    double up[PDP_M];
+    const double* Ua = fb_gains ? Uout + (size_t)b * H * PDP_M : Ub;      // the controls actually applied
+    double xp[PDP_N], up[PDP_M];          // prefetch of (x_{t-1}, u_{t-1}) while step t is being processed
+    #pragma unroll
+    for (int i = 0; i < PDP_N; ++i) xp[i] = Xb[(H - 1) * PDP_N + i];
     #pragma unroll
     for (int i = 0; i < PDP_M; ++i) up[i] = Ua[(H - 1) * PDP_M + i];
     #pragma unroll 1
-    for (int tc = ((H - 1) / PDP_KT) * PDP_KT; tc >= 0; tc -= PDP_KT) {
-      const int nt = (tc + PDP_KT < H ? PDP_KT : H - tc);
-      __syncwarp();
-      pdp_tile_load(TB, X, (size_t)(H + 1) * PDP_N, b0, nvalid, tc, nt, lane);   // x_tc .. x_{tc+nt-1}
-      __syncwarp();
-      #pragma unroll 1
-      for (int t = tc + nt - 1; t >= tc; --t) {
-        const int tt = t - tc;
+    for (int t = H - 1; t >= 0; --t) {
+      #pragma unroll
+      for (int i = 0; i < PDP_N; ++i) Lb[t * PDP_N + i] = lam[i];
+      #pragma unroll
+      for (int i = 0; i < PDP_N; ++i) x[i] = xp[i];
+      #pragma unroll
+      for (int i = 0; i < PDP_M; ++i) u[i] = up[i];
+      if (t > 0) {
         #pragma unroll
-        for (int i = 0; i < PDP_N; ++i) TA[(tt * PDP_N + i) * 33 + lane] = lam[i];
+        for (int i = 0; i < PDP_N; ++i) xp[i] = Xb[(t - 1) * PDP_N + i];
         #pragma unroll
-        for (int i = 0; i < PDP_N; ++i) x[i] = TB[(tt * PDP_N + i) * 33 + lane];
-        #pragma unroll
-        for (int i = 0; i < PDP_M; ++i) u[i] = up[i];
-        if (t > 0) {
-          #pragma unroll
-          for (int i = 0; i < PDP_M; ++i) up[i] = Ua[(t - 1) * PDP_M + i];
-        }
-        if (dHu != nullptr) {
-          pdp_f_dHu(x, u, lam, th, gu);
-          if (live) {
-            #pragma unroll
-            for (int i = 0; i < PDP_M; ++i) dHu[((size_t)b * H + t) * PDP_M + i] = gu[i];
-          }
-        }
-        if (t > 0) {
-          pdp_f_dHx(x, u, lam, th, ln);
-          #pragma unroll
-          for (int i = 0; i < PDP_N; ++i) lam[i] = ln[i];
-        }
+        for (int i = 0; i < PDP_M; ++i) up[i] = Ua[(t - 1) * PDP_M + i];
       }
-      __syncwarp();
-      pdp_tile_store(TA, Lam, (size_t)H * PDP_N, b0, nvalid, tc, nt, lane);
+      if (dHu != nullptr) {
+        pdp_f_dHu(x, u, lam, th, gu);
+        #pragma unroll
+        for (int i = 0; i < PDP_M; ++i) dHu[((size_t)b * H + t) * PDP_M + i] = gu[i];
+      }
+      if (t > 0) {
+        pdp_f_dHx(x, u, lam, th, ln);
+        #pragma unroll
+        for (int i = 0; i < PDP_N; ++i) lam[i] = ln[i];
+      }
     }
   }
-  if (status && bad && live) atomicOr(&status[b], 1);
+  if (status && bad) atomicOr(&status[b], 1);
 }
 
 // =====================================================================================================
@@ -391,17 +333,8 @@ extern "C" int pdpmod_rollout_costate(int B, int H, const double* x0, const doub
                                       const double* fb_gains, const double* fb_X, const double* fb_alpha, double* Uout,
                                       cudaStream_t st) {
   if (B <= 0) return 0;
-  static bool cfg_dev[64] = {false};
-  int dev_ = 0;
-  cudaGetDevice(&dev_);
-  const size_t smem = (size_t)4 * 2 * PDP_TILE * sizeof(double);
-  if (!cfg_dev[dev_ & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(pdp_k_rollout_costate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    cfg_dev[dev_ & 63] = true;
-  }
-  pdp_k_rollout_costate<<<(B + 127) / 128, 128, smem, st>>>(B, H, x0, theta, theta_stride, U, X, Lam, cost, dHu, status,
-                                                            fb_gains, fb_X, fb_alpha, Uout);
+  pdp_k_rollout_costate<<<(B + 127) / 128, 128, 0, st>>>(B, H, x0, theta, theta_stride, U, X, Lam, cost, dHu, status,
+                                                         fb_gains, fb_X, fb_alpha, Uout);
   return (int)cudaGetLastError();
 }
 
