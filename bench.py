@@ -374,7 +374,7 @@ def main():
     ap.add_argument("--ref-per-core", type=int, default=48,
                     help="trajectories per host core in one CPU-baseline step (about 2 s of work per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-chunks", type=int, default=8)
+    ap.add_argument("--e2e-chunks", type=int, default=4)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
