@@ -42,3 +42,18 @@ cp.setDyn(rocket.X + 0.1 * rocket.f)
 cp.setPathCost(rocket.path_cost)
 cp.setFinalCost(rocket.final_cost)
 print("rocket recmat", cp._oc_system().module_path)
+
+# neural-dynamics SysID module of tests/test_gpu_modes.py::test_sysid_neural_dynamics_matches_oracle
+from casadi import SX, mtimes, tanh, vcat  # noqa: E402
+arm = JinEnv.RobotArm()
+arm.initDyn(g=0)
+inp = vertcat(arm.X, arm.U)
+M1, b1 = SX.sym('M1', 6, 6), SX.sym('b1', 6)
+M2, b2 = SX.sym('M2', 4, 6), SX.sym('b2', 4)
+net = mtimes(M2, tanh(mtimes(M1, inp) + b1)) + b2
+sid = PDP.SysID()
+sid.setAuxvarVariable(vcat([M1.reshape((-1, 1)), b1.reshape((-1, 1)), M2.reshape((-1, 1)), b2.reshape((-1, 1))]))
+sid.setStateVariable(arm.X)
+sid.setControlVariable(arm.U)
+sid.setDyn(net)
+print("neural sysid", sid._system().module_path)
