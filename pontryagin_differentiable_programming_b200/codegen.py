@@ -176,30 +176,6 @@ class _SlotLoader:
         return self.loaded[e]
 
 
-def _interleave(entries, acc_of):
-    """Reorder (accumulator, ...) update entries so that consecutive updates hit different accumulators
-    (longest-idle first) while keeping each accumulator's own summation order: more independent FP64
-    chains in flight, identical floating-point result."""
-    queues: Dict[int, List] = {}
-    order: List[int] = []
-    for e in entries:
-        a = acc_of(e)
-        if a not in queues:
-            queues[a] = []
-            order.append(a)
-        queues[a].append(e)
-    last = {a: -1 for a in order}
-    out = []
-    t = 0
-    while any(queues[a] for a in order):
-        cand = [a for a in order if queues[a]]
-        a = min(cand, key=lambda c: (last[c], -len(queues[c])))
-        out.append(queues[a].pop(0))
-        last[a] = t
-        t += 1
-    return out
-
-
 def _odd(n):
     return n if n % 2 == 1 else n + 1
 
@@ -506,8 +482,6 @@ class OCModuleSource:
     def source(self) -> str:
         n, m, r, ns = self.n, self.m, self.r, self.ns
         nm = n + m
-        kh = 0
-        nhs = 0
         zt_size = _even(ns * self.ldz)
         ks_size = _even(m * self.ldk)
         auxc_size = _even(max(self.chunk * self.auxld, n * n + n * r))
@@ -528,7 +502,7 @@ class OCModuleSource:
             "LDK": self.ldk, "OFF_ZT": off_zt, "OFF_KS": off_ks, "OFF_QUU": off_quu, "OFF_TH": off_th,
             "FLD": fld, "FOFF_KS": foff_ks, "FOFF_TH": foff_th, "FOFF_DL": foff_dl,
             "FWARP_DOUBLES": fwarp_doubles, "WPBF": getattr(self, "wpbf", 4), "MINBF": getattr(self, "min_blocks_f", 1),
-            "WARP_DOUBLES": warp_doubles, "NTH": self.nth, "MINB": getattr(self, "min_blocks", 1), "NHS": nhs, "KH": kh, "GREC": (n + r) * m,
+            "WARP_DOUBLES": warp_doubles, "NTH": self.nth, "MINB": getattr(self, "min_blocks", 1), "GREC": (n + r) * m,
             "NDENSE": n * n + n * m + n * r + n * n + n * m + n * r + m * n + m * m + m * r,
         }
         header = ["// GENERATED by pontryagin_differentiable_programming_b200/codegen.py -- do not edit",
@@ -540,8 +514,6 @@ class OCModuleSource:
             hid += [self.H_idx[j][l] if j < ns else self.zero_slot for j in range(WARP)]
         tables.append("__device__ const unsigned short pdp_hidx[%d] = {%s};" % (len(hid), ", ".join(map(str, hid))))
         tabload = "\n".join("  const int ho%d = pdp_hidx[%d + lane];" % (l, l * WARP) for l in range(nm))
-        hinit = ""
-        scatter = ""
         ydecl = "double " + ", ".join("y%d = 0.0" % k for k in range(n)) + ";"
         # terminal init: lane i<n takes row i of hxx, lane n+m+c takes column c of hxe
         term_init = []
@@ -561,7 +533,7 @@ class OCModuleSource:
         x0store = "\n".join("    o[%d] = x%d;" % (i * r, i) for i in range(n))
 
         rep = {
-            "@@TABLOAD@@": tabload, "@@HINIT@@": hinit, "@@SCATTER@@": scatter, "@@YDECL@@": ydecl,
+            "@@TABLOAD@@": tabload, "@@YDECL@@": ydecl,
             "@@TERM_INIT@@": "\n".join(term_init), "@@BACKWARD_STEP@@": self._backward_step(),
             "@@XDECL@@": xdecl, "@@XINIT@@": xinit, "@@GNDECL@@": gndecl, "@@GNLOAD@@": gnload, "@@GCUR@@": gcur,
             "@@KS_STORE@@": ks_store, "@@FORWARD_STEP@@": self._forward_step(), "@@XSTORE@@": xstore, "@@USTORE@@": ustore,

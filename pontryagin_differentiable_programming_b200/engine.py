@@ -204,56 +204,6 @@ class OCSystem:
             res["loss_dp"] = ldp
         return res
 
-    def sweep_pipelined(self, x0, theta, U, out, Xref=None, Uref=None, status=None, n_parts=2):
-        """Same work as :meth:`sweep` into the preallocated ``out`` buffers, but the batch is cut into ``n_parts``
-        contiguous parts issued on alternating side streams, so the latency-bound rollout/costate kernel of one part
-        overlaps the Riccati kernels of the other.  Returns with the work ordered into the current stream."""
-        require_cuda()
-        dev = x0.device
-        B = U.shape[0]
-        if n_parts <= 1 or B < 2 * n_parts:
-            return self.sweep(x0, theta, U, Xref=Xref, Uref=Uref, status=status, out=out)
-        if getattr(self, "_side", None) is None:
-            self._side = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
-        cur = torch.cuda.current_stream(dev)
-        start = torch.cuda.Event()
-        start.record(cur)
-        bounds = [(B * c) // n_parts for c in range(n_parts + 1)]
-        shared_theta = theta.dim() == 1 or theta.shape[0] == 1
-        for c in range(n_parts):
-            lo, hi = bounds[c], bounds[c + 1]
-            st = self._side[c % 2]
-            if c < 2:
-                st.wait_event(start)
-            with torch.cuda.stream(st):
-                part_out = {k: v[lo:hi] for k, v in out.items()}
-                self._part_sweep(x0[lo:hi], theta if shared_theta else theta[lo:hi], U[lo:hi],
-                                 None if Xref is None else Xref[lo:hi], None if Uref is None else Uref[lo:hi],
-                                 None if status is None else status[lo:hi], part_out, c)
-        for st in self._side:
-            done = torch.cuda.Event()
-            done.record(st)
-            cur.wait_event(done)
-        return out
-
-    def _part_sweep(self, x0, theta, U, Xref, Uref, status, out, slot):
-        dev = x0.device
-        B, H = U.shape[0], U.shape[1]
-        theta, ts = self._theta(theta, B, dev)
-        need = self.handle.workspace_bytes(backend.OP_SWEEP, B, H)
-        key = ("part", slot, dev)
-        ws = self._ws.get(key)
-        if ws is None or ws.numel() < need:
-            ws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
-            self._ws[key] = ws
-        st = torch.cuda.current_stream(dev).cuda_stream
-        ldp = out.get("loss_dp") if Xref is not None else None
-        with torch.cuda.device(dev):
-            backend.check(self.handle.lib.pdp_sweep(self.handle.ptr, B, H, _ptr(x0), _ptr(theta), ts, _ptr(U), _ptr(out["X"]),
-                                                    _ptr(out["Lam"]), _ptr(out["cost"]), _ptr(out.get("dX")),
-                                                    _ptr(out.get("dU")), _ptr(Xref), _ptr(Uref), _ptr(ldp), _ptr(ws),
-                                                    ws.numel(), _ptr(status), st), "pdp_sweep")
-
     def sweep_host(self, x0_h, theta_h, U_h, Xref_h, Uref_h, loss_dp_h, cost_h=None, keep_dtraj=True, n_chunks=4,
                    device=None):
         """End-to-end sweep from PINNED HOST tensors: per sub-batch H2D of (x0, theta, U, Xref, Uref) -> rollout /

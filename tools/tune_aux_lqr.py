@@ -18,9 +18,6 @@ sys.path.insert(0, ROOT)
 VARIANTS = [(16, 4, 3, 4, 4, True, False, False), (16, 4, 3, 4, 4, True, True, False), (16, 4, 3, 4, 4, True, False, True),
             (16, 4, 3, 4, 4, True, True, True), (16, 4, 1, 4, 4, True, True, True), (16, 4, 4, 4, 4, True, True, True),
             (16, 4, 4, 4, 4, False, True, True)]
-_OLD = ([(8, 4, mb, 4, 4, kf) for mb in (1, 3, 4) for kf in (True, False)] +
-            [(8, 4, 3, 4, mf, True) for mf in (2, 3)] + [(16, 4, 3, 4, 4, True), (4, 4, 3, 4, 4, True), (8, 2, 6, 2, 8, True)])
-
 
 def make(ch, wpb, mb, wpbf=4, mbf=1, kf=True, frcp=False, early=False, verbose=False):
     from JinEnv import JinEnv
