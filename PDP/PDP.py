@@ -193,11 +193,12 @@ class OCSys:
 
     # -------------------------------------------------------------------------------- legacy API
     def ocSolver(self, ini_state, horizon, auxvar_value=1, print_level=0, costate_option=0, control_init=None,
-                 n_starts=8):
+                 n_starts=1):
         """Solve the OC problem for one initial state (reference PDP.py:121-220 used IPOPT; here the batched
         CUDA Newton/DDP solver).  Returns the same dict; ``costate_traj_opt[t] = lambda_{t+1}`` for either
         ``costate_option`` (the PMP recursion and the NLP multipliers coincide at a stationary point).
-        Additive keyword arguments: ``control_init`` (H x m warm start) and ``n_starts`` (seeded multi-start)."""
+        Additive keyword arguments: ``control_init`` (H x m warm start) and ``n_starts`` (> 1: seeded multi-start in
+        one batch, best stationary point wins; the default 1 is the reference's cold start from all-zero controls)."""
         self._check_defined()
         dev = _device()
         x0 = _dev_tensor(_flat(ini_state, self.n_state, "ini_state")[None, :], dev)

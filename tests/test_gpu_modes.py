@@ -224,8 +224,10 @@ def test_k2_rocket_demo_is_the_stationary_point_reached_from_a_warm_start():
     assert abs(sol["cost"].item() - g2["rocket_0_cost"][0]) < 1e-7 * abs(sol["cost"].item())
     assert np.max(np.abs(sol["control_traj_opt"] - Ud)) < 2e-5 * np.max(np.abs(Ud))
     assert np.max(np.abs(sol["costate_traj_opt"] - Ld)) < 5e-5 * np.max(np.abs(Ld))
-    cold = oc.ocSolver(Xd[0], Ud.shape[0], g2["rocket_true_parameter"])        # multi-start cold solve: a stationary point
+    cold = oc.ocSolver(Xd[0], Ud.shape[0], g2["rocket_true_parameter"])        # cold start: some stationary point
     assert np.isfinite(cold["cost"].item()) and cold["cost"].item() < 6000.0
+    multi = oc.ocSolver(Xd[0], Ud.shape[0], g2["rocket_true_parameter"], n_starts=8)   # best of 8 seeded starts
+    assert multi["cost"].item() <= cold["cost"].item() + 1e-6
 
 
 @pytest.mark.parametrize("env", ["pendulum", "quadrotor", "robotarm", "cartpole"])
