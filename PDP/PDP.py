@@ -16,7 +16,6 @@ list are broadcast over the horizon; ``getAuxSys`` calls ``diffPMP`` on demand.
 import numpy
 import numpy as np  # noqa: F401  (the reference leaks ``np`` through ``from casadi import *``)
 
-from pontryagin_differentiable_programming_b200 import symbolic as _sym
 from pontryagin_differentiable_programming_b200.symbolic import (  # noqa: F401
     SX, MX, DM, Function, dot, jacobian, mtimes, tanh, vcat, vertcat)
 

@@ -80,6 +80,17 @@ def alg_flops_sweep(n, m, r, H):
     return H * (back + fwd + 400)
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes (read + write) per launch of ``kernel`` from the committed `ncu --set full` capture of this same
+    command (profiles/r1_final_ncu_traffic.json, C3 at 16 384 trajectories); None if no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "r1_final_ncu_traffic.json")
+    try:
+        d = json.load(open(p))
+        return float(d[kernel]["dram_bytes_read"]) + float(d[kernel]["dram_bytes_write"]), d.get("source")
+    except Exception:
+        return None, None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -207,7 +218,7 @@ def run_reference(args):
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-    from pontryagin_differentiable_programming_b200 import backend, systems
+    from pontryagin_differentiable_programming_b200 import systems
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -323,6 +334,7 @@ def run_gpu(args):
         achieved = kbytes / (k_ms * 1e-3) / 1e9
         h2d = sum(int(p.numel()) * 8 for p in pinned)
         d2h = int(ldp_host.numel() + cost_host.numel()) * 8
+        traffic, traffic_src = ncu_traffic("pdp_k_aux_lqr_bwd") if B == 16384 and H == 50 else (None, None)
         line = {
             "metric": "PDP sweeps/sec (fwd+aux-LQR bwd)", "value": value, "unit": "sweeps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
@@ -337,7 +349,7 @@ def run_gpu(args):
                                       "the sweep is still the reference's algebra (parity above); 0 at OC optima (tests)",
                        "e2e_matches_device_path": e2e_ok},
             "roofline": {"kernel": "pdp_k_aux_lqr_bwd", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "alg_bytes_per_launch": kbytes, "kernel_ms": k_ms,
                          "kernel_share_of_step": k_ms / (ms_total / args.steps),
                          "fp64_tflops_alg_bwd": alg_flops_bwd(n, m, r, H) * B / (k_ms * 1e-3) / 1e12,

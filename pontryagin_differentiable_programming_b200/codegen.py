@@ -273,7 +273,6 @@ class OCModuleSource:
         self.auxld = _pad_ld(self.nvar)
         self.ldz = _odd(n)
         self.ldk = _even(n)
-        self.ldq = _even(n + m)
 
     # ---- device functions ----------------------------------------------------------------------
     def _device_functions(self) -> str:
@@ -730,7 +729,7 @@ class LQRModuleSource(OCModuleSource):
         self.src_off = src
         self.nvar = len(src)
         self.auxld = _pad_ld(self.nvar)
-        self.ldz, self.ldk, self.ldq = _odd(n), _even(n), _even(n + m)
+        self.ldz, self.ldk = _odd(n), _even(n)
 
     def _device_functions(self) -> str:
         return ""

@@ -58,8 +58,6 @@ _TABLE: Dict[tuple, Node] = {}
 _COUNTER = [0]
 _SYM_COUNTER = [0]
 
-_UNARY = ("neg", "sq", "sin", "cos", "tan", "tanh", "exp", "log", "sqrt", "fabs")
-_COMMUTATIVE = ("add", "mul")
 
 
 def _mk(op, args=(), val=None):
