@@ -418,3 +418,57 @@ def test_sysid_neural_dynamics_matches_oracle():
     loss_ref, dp_ref = ref.step(inputs, states, th)
     assert abs(loss - loss_ref) < 1e-11 * abs(loss_ref)
     assert _rel(dp, dp_ref) < 1e-10
+
+
+def test_legacy_getauxsys_of_sysid_and_controlplanning():
+    """SysID.getAuxSys / ControlPlanning.getAuxSys (pdp_eval_function kernels) and the chained legacy calls
+    integrateDyn -> getAuxSys -> integrateAuxSys reproduce the oracle's step-by-step restatement."""
+    from PDP import PDP
+    from JinEnv import JinEnv
+    _dev()
+    g = np.load(os.path.join(G, "k1_iodata.npz"))
+    uav = JinEnv.Quadrotor()
+    uav.initDyn(c=0.01)
+    sid = PDP.SysID()
+    sid.setAuxvarVariable(uav.dyn_auxvar)
+    sid.setStateVariable(uav.X)
+    sid.setControlVariable(uav.U)
+    sid.setDyn(uav.X + 0.1 * uav.f)
+    e = envs.quadrotor(c=0.01)
+    ref = pdp_oracle.OracleSysID(e["X"], e["U"], e["dyn_params"], e["X"] + 0.1 * e["f"])
+    inputs, states = g["quadrotor_inputs"][0], g["quadrotor_states"][0]
+    theta = g["quadrotor_true_parameter"] * 1.1
+    X = sid.integrateDyn(states[0], inputs, theta)
+    assert np.max(np.abs(X - ref.integrateDyn(states[0], inputs, theta))) < 1e-12
+    aux = sid.getAuxSys(X, inputs, theta)
+    S_ref = ref.sens(X, inputs, theta)
+    sol = sid.integrateAuxSys(aux["dynF"], aux["dynE"], np.zeros((13, 5)))
+    assert _rel(np.stack(sol["state_traj"]), np.stack(S_ref)) < 1e-11
+    F0 = np.asarray(ref.dfx_fn(X[3], inputs[3], theta), dtype=float).reshape(13, 13)
+    assert np.max(np.abs(aux["dynF"][3] - F0)) < 1e-13
+    # ControlPlanning with a polynomial policy on the cart-pole
+    cart = JinEnv.CartPole()
+    cart.initDyn(mc=0.1, mp=0.1, l=1)
+    cart.initCost(wx=0.1, wq=0.6, wdx=0.1, wdq=0.1, wu=0.3)
+    H, dt = 15, 0.05
+    oc = PDP.ControlPlanning()
+    oc.setStateVariable(cart.X)
+    oc.setControlVariable(cart.U)
+    oc.setDyn(cart.X + dt * cart.f)
+    oc.setPathCost(cart.path_cost)
+    oc.setFinalCost(cart.final_cost)
+    oc.init_step(H)
+    ec = envs.cartpole(mc=0.1, mp=0.1, l=1, wx=0.1, wq=0.6, wdx=0.1, wdq=0.1, wu=0.3)
+    cp = pdp_oracle.OracleCP(ec["X"], ec["U"], ec["X"] + dt * ec["f"], ec["path_cost"], ec["final_cost"])
+    cp.set_poly(np.linspace(0, H, 6))
+    th = np.random.default_rng(2).standard_normal(oc.n_auxvar)
+    x0 = [0.05, -0.1, 0.02, 0.0]
+    traj = oc.integrateSys(x0, H, th)
+    cost, grad, Xr, Ur, dXr, dUr = cp.step(np.array(x0), H, th, return_traj=True)
+    assert _rel(traj["state_traj"], Xr) < 1e-12 and abs(traj["cost"] - cost) < 1e-11 * abs(cost)
+    aux = oc.getAuxSys(traj["state_traj"], traj["control_traj"], th)
+    sol = oc.integrateAuxSys(aux["dynF"], aux["dynG"], aux["dUx"], aux["dUe"], np.zeros((4, oc.n_auxvar)))
+    assert _rel(np.stack(sol["state_traj"]), dXr) < 1e-10
+    assert _rel(np.stack(sol["control_traj"]), dUr) < 1e-10
+    loss, dth = oc.step(x0, H, th)
+    assert abs(loss - cost) < 1e-11 * abs(cost) and _rel(dth, grad) < 1e-10
