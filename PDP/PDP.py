@@ -502,6 +502,12 @@ class ControlPlanning:
         self.auxvar = SX.sym('U', self.n_auxvar)
         self._interval = numpy.repeat(numpy.arange(self.whorizon), numpy.diff(self.time_grid))
 
+    def _interval_sums(self, per_step, n_blocks):
+        """Sum the per-step gradient dH/du over every interval of the time grid (on the device)."""
+        torch = _torch()
+        idx = torch.as_tensor(self._interval, device=per_step.device, dtype=torch.long)
+        return torch.zeros((n_blocks, self.n_control), dtype=per_step.dtype, device=per_step.device).index_add_(0, idx, per_step)
+
     def _expand_controls(self, auxvar_value):
         Uw = _flat(auxvar_value, self.n_auxvar, "auxvar_value").reshape(self.whorizon, self.n_control)
         return Uw[self._interval]
@@ -518,10 +524,8 @@ class ControlPlanning:
         U = self._expand_controls(auxvar_value)
         x0 = _dev_tensor(_flat(ini_state, self.n_state, "ini_state")[None], dev)
         cost, dHu, _ = self.recmat_step_batched(x0, _dev_tensor(U[None], dev))
-        g = dHu[0].cpu().numpy()
-        dw = numpy.zeros((self.whorizon, self.n_control))
-        numpy.add.at(dw, self._interval, g)
-        return float(cost[0].item()), dw.reshape(-1)
+        dw = self._interval_sums(dHu[0], self.whorizon)
+        return float(cost[0].item()), dw.cpu().numpy().reshape(-1)
 
     def recmat_unwarp(self, ini_state, horizon, auxvar_value):
         dev = _device()
@@ -572,9 +576,8 @@ class ControlPlanning:
         Uw = self._warp_controls(auxvar_value)
         x0 = _dev_tensor(_flat(ini_state, self.n_state, "ini_state")[None], dev)
         cost, dHu, _ = self.recmat_step_batched(x0, _dev_tensor(Uw[self._interval][None], dev))
-        dw = numpy.zeros((self.whorizon + 1, self.n_control))
-        numpy.add.at(dw, self._interval, dHu[0].cpu().numpy())
-        return cost.cpu().numpy().reshape(1, 1), dw.reshape(-1)
+        dw = self._interval_sums(dHu[0], self.whorizon + 1)
+        return cost.cpu().numpy().reshape(1, 1), dw.cpu().numpy().reshape(-1)
 
     def warp_unwarp(self, ini_state, horizon, auxvar_value):
         dev = _device()
