@@ -268,11 +268,71 @@ class OCModuleSource:
                     node = self.ddHue.at(l - n, j - nm)
                 self.H_idx[j][l] = slots.exact(node)
         self.zero_slot = slots.exact(S.ZERO)
+        self._place_h_slots(slots)
         self.slots = slots
         self.nvar = len(slots)
         self.auxld = _pad_ld(self.nvar)
         self.ldz = _odd(n)
         self.ldk = _even(n)
+
+    def _h_conflict_cost(self, phys):
+        """Extra shared-memory wavefronts of the per-lane indexed Hamiltonian loads: a 64-bit warp load is served
+        per half-warp, one wavefront per distinct word that shares a 16-way bank-pair with another distinct word."""
+        ns, nm = self.ns, self.n + self.m
+        cost = 0
+        for l in range(nm):
+            for half in (0, 1):
+                banks: Dict[int, set] = {}
+                for j in range(16 * half, 16 * half + 16):
+                    a = phys[self.H_idx[j][l]] if j < ns else phys[self.zero_slot]
+                    banks.setdefault(a % 16, set()).add(a)
+                cost += max(len(v) for v in banks.values()) - 1
+        return cost
+
+    def _place_h_slots(self, slots: "SlotTable", pad: int = 6, sweeps: int = 40):
+        """Renumber the slots used only by the Hamiltonian stack (the [F|G|E] slots keep their order: the forward
+        kernel evaluates just that prefix) so that the lanes of one indexed load hit distinct bank-pairs.
+        Deterministic pairwise-swap descent; a few padding slots give it room."""
+        lo = self.nvar_s
+        movable = list(range(lo, len(slots.nodes)))
+        if len(movable) < 2:
+            return
+        positions = list(range(lo, len(slots.nodes) + pad))
+        phys = {e: e for e in range(len(slots.nodes))}          # slot id -> physical index
+        occupant = {p: (p if p < len(slots.nodes) else None) for p in positions}
+        best = self._h_conflict_cost(phys)
+        for _ in range(sweeps):
+            improved = False
+            for e in movable:
+                if best == 0:
+                    break
+                for p in positions:
+                    q = phys[e]
+                    if p == q:
+                        continue
+                    other = occupant[p]
+                    phys[e] = p
+                    if other is not None:
+                        phys[other] = q
+                    c = self._h_conflict_cost(phys)
+                    if c < best:
+                        best, improved = c, True
+                        occupant[p], occupant[q] = e, other
+                    else:
+                        phys[e] = q
+                        if other is not None:
+                            phys[other] = p
+            if not improved or best == 0:
+                break
+        # apply: rebuild the node list in physical order (padding slots hold 0.0) and remap the index tables
+        size = max(phys.values()) + 1
+        nodes = [S.ZERO] * size
+        for e, p in phys.items():
+            nodes[p] = slots.nodes[e]
+        slots.nodes[:] = nodes
+        self.H_idx = [[phys[e] for e in row] for row in self.H_idx]
+        self.zero_slot = phys[self.zero_slot]
+        self.h_conflicts = best
 
     # ---- device functions ----------------------------------------------------------------------
     def _device_functions(self) -> str:
