@@ -9,6 +9,37 @@ K_ROLLOUT_AUXEVAL = r'''
 //   restates reference OCSys.ocSolver's rollout semantics at given controls (PDP.py:158-175) and the PMP
 //   costate recursion (PDP.py:203-209): Lam[t] = lambda_{t+1}, lambda_H = dh/dx(x_H).
 // =====================================================================================================
+
+// Row I/O of the thread-per-trajectory kernel.  A thread's 8-byte accesses each cost one 32-byte sector request;
+// rows are only 8-byte aligned (n doubles per row), so pick the 16-byte pairing that matches the row's parity.
+template <int LEN>
+__device__ __forceinline__ void pdp_row_store(double* __restrict__ g, const double* x) {
+  if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+    #pragma unroll
+    for (int i = 0; i + 1 < LEN; i += 2) *reinterpret_cast<double2*>(g + i) = make_double2(x[i], x[i + 1]);
+    if (LEN & 1) g[LEN - 1] = x[LEN - 1];
+  } else {
+    g[0] = x[0];
+    #pragma unroll
+    for (int i = 1; i + 1 < LEN; i += 2) *reinterpret_cast<double2*>(g + i) = make_double2(x[i], x[i + 1]);
+    if (!(LEN & 1)) g[LEN - 1] = x[LEN - 1];
+  }
+}
+
+template <int LEN>
+__device__ __forceinline__ void pdp_row_load(double* x, const double* g) {
+  if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+    #pragma unroll
+    for (int i = 0; i + 1 < LEN; i += 2) { const double2 v = *reinterpret_cast<const double2*>(g + i); x[i] = v.x; x[i + 1] = v.y; }
+    if (LEN & 1) x[LEN - 1] = g[LEN - 1];
+  } else {
+    x[0] = g[0];
+    #pragma unroll
+    for (int i = 1; i + 1 < LEN; i += 2) { const double2 v = *reinterpret_cast<const double2*>(g + i); x[i] = v.x; x[i + 1] = v.y; }
+    if (!(LEN & 1)) x[LEN - 1] = g[LEN - 1];
+  }
+}
+
 extern "C" __global__ void __launch_bounds__(128)
 pdp_k_rollout_costate(int B, int H, const double* __restrict__ x0, const double* __restrict__ theta, int theta_stride,
                       const double* __restrict__ U, double* __restrict__ X, double* __restrict__ Lam,
@@ -31,15 +62,13 @@ pdp_k_rollout_costate(int B, int H, const double* __restrict__ x0, const double*
   const double* Ub = U + (size_t)b * H * PDP_M;
   const double fb_a = fb_gains ? fb_alpha[b] : 0.0;
   double un[PDP_M];                       // software prefetch: the next step's control is in flight during this step
-  #pragma unroll
-  for (int i = 0; i < PDP_M; ++i) un[i] = Ub[i];
+  pdp_row_load<PDP_M>(un, Ub);
   #pragma unroll 1
   for (int t = 0; t < H; ++t) {
     #pragma unroll
     for (int i = 0; i < PDP_M; ++i) u[i] = un[i];
     if (t + 1 < H) {
-      #pragma unroll
-      for (int i = 0; i < PDP_M; ++i) un[i] = Ub[(t + 1) * PDP_M + i];
+      pdp_row_load<PDP_M>(un, Ub + (t + 1) * PDP_M);
     }
     if (fb_gains != nullptr) {
       const double* g = fb_gains + ((size_t)b * H + t) * ((PDP_N + 1) * PDP_M);
@@ -55,16 +84,14 @@ pdp_k_rollout_costate(int B, int H, const double* __restrict__ x0, const double*
       #pragma unroll
       for (int i = 0; i < PDP_M; ++i) Uout[((size_t)b * H + t) * PDP_M + i] = u[i];
     }
-    #pragma unroll
-    for (int i = 0; i < PDP_N; ++i) Xb[t * PDP_N + i] = x[i];
+    pdp_row_store<PDP_N>(Xb + t * PDP_N, x);
     pdp_f_path_cost(x, u, th, tmp);
     J += tmp[0];
     pdp_f_dyn(x, u, th, xn);
     #pragma unroll
     for (int i = 0; i < PDP_N; ++i) x[i] = xn[i];
   }
-  #pragma unroll
-  for (int i = 0; i < PDP_N; ++i) Xb[H * PDP_N + i] = x[i];
+  pdp_row_store<PDP_N>(Xb + H * PDP_N, x);
   pdp_f_final_cost(x, th, tmp);
   J += tmp[0];
   if (cost) cost[b] = J;
@@ -75,23 +102,18 @@ pdp_k_rollout_costate(int B, int H, const double* __restrict__ x0, const double*
     pdp_f_dhx(x, th, lam);
     const double* Ua = fb_gains ? Uout + (size_t)b * H * PDP_M : Ub;      // the controls actually applied
     double xp[PDP_N], up[PDP_M];          // prefetch of (x_{t-1}, u_{t-1}) while step t is being processed
-    #pragma unroll
-    for (int i = 0; i < PDP_N; ++i) xp[i] = Xb[(H - 1) * PDP_N + i];
-    #pragma unroll
-    for (int i = 0; i < PDP_M; ++i) up[i] = Ua[(H - 1) * PDP_M + i];
+    pdp_row_load<PDP_N>(xp, Xb + (H - 1) * PDP_N);
+    pdp_row_load<PDP_M>(up, Ua + (H - 1) * PDP_M);
     #pragma unroll 1
     for (int t = H - 1; t >= 0; --t) {
-      #pragma unroll
-      for (int i = 0; i < PDP_N; ++i) Lb[t * PDP_N + i] = lam[i];
+      pdp_row_store<PDP_N>(Lb + t * PDP_N, lam);
       #pragma unroll
       for (int i = 0; i < PDP_N; ++i) x[i] = xp[i];
       #pragma unroll
       for (int i = 0; i < PDP_M; ++i) u[i] = up[i];
       if (t > 0) {
-        #pragma unroll
-        for (int i = 0; i < PDP_N; ++i) xp[i] = Xb[(t - 1) * PDP_N + i];
-        #pragma unroll
-        for (int i = 0; i < PDP_M; ++i) up[i] = Ua[(t - 1) * PDP_M + i];
+        pdp_row_load<PDP_N>(xp, Xb + (t - 1) * PDP_N);
+        pdp_row_load<PDP_M>(up, Ua + (t - 1) * PDP_M);
       }
       if (dHu != nullptr) {
         pdp_f_dHu(x, u, lam, th, gu);
