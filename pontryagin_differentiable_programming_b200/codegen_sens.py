@@ -121,9 +121,8 @@ class SensModuleSource:
         else:
             L.append(ind + "double " + ", ".join("d%d = 0.0" % i for i in range(n)) + ";")
             L.append(ind + "if (Xobs) {")
-            L.append(ind + "  double xo[%d]; pdp_row_load<%d>(xo, Xobs + ((size_t)b * (H + 1) + t) * %d);" % (n, n, n))
             for i in range(n):
-                L.append(ind + "  d%d = xs%d - xo[%d];" % (i, i, i))
+                L.append(ind + "  d%d = xs%d - Xobs[((size_t)b * (H + 1) + t) * %d + %d];" % (i, i, n, i))
             L.append(ind + "  if (grp == 0) { " + " ".join("loss = fma(d%d, d%d, loss);" % (i, i) for i in range(n)) + " }")
             L.append(ind + "}")
             wx = ["d%d" % i for i in range(n)]
@@ -211,9 +210,8 @@ class SensModuleSource:
         else:
             L.append(ind + "double " + ", ".join("d%d = 0.0" % i for i in range(n)) + ";")
             L.append(ind + "if (Xobs) {")
-            L.append(ind + "  double xo[%d]; pdp_row_load<%d>(xo, Xobs + ((size_t)b * (H + 1) + H) * %d);" % (n, n, n))
             for i in range(n):
-                L.append(ind + "  d%d = xs%d - xo[%d];" % (i, i, i))
+                L.append(ind + "  d%d = xs%d - Xobs[((size_t)b * (H + 1) + H) * %d + %d];" % (i, i, n, i))
             L.append(ind + "  if (grp == 0) { " + " ".join("loss = fma(d%d, d%d, loss);" % (i, i) for i in range(n)) + " }")
             L.append(ind + "}")
             wx = ["d%d" % i for i in range(n)]
@@ -246,22 +244,6 @@ class SensModuleSource:
                "#define PDP_NG %d" % len(self.groups), "#define PDP_GMAX %d" % self.gmax, "#define PDP_BLOCK %d" % self.block]
         body = []
         body.append(r'''
-// 16-byte paired row loads (rows are only 8-byte aligned; the pairing follows the row's address parity) -- a thread's
-// 8-byte accesses would each be a separate 32-byte sector request.
-template <int LEN>
-__device__ __forceinline__ void pdp_row_load(double* x, const double* g) {
-  if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
-    #pragma unroll
-    for (int i = 0; i + 1 < LEN; i += 2) { const double2 v = *reinterpret_cast<const double2*>(g + i); x[i] = v.x; x[i + 1] = v.y; }
-    if (LEN & 1) x[LEN - 1] = g[LEN - 1];
-  } else {
-    x[0] = g[0];
-    #pragma unroll
-    for (int i = 1; i + 1 < LEN; i += 2) { const double2 v = *reinterpret_cast<const double2*>(g + i); x[i] = v.x; x[i + 1] = v.y; }
-    if (!(LEN & 1)) x[LEN - 1] = g[LEN - 1];
-  }
-}
-
 // One thread per (trajectory, column group); the group's columns of X_t (n x r) live in shared memory.
 extern "C" __global__ void __launch_bounds__(PDP_BLOCK)
 pdp_k_sens_fwd(int B, int H, const double* __restrict__ x0, const double* __restrict__ theta, int theta_stride,
@@ -286,8 +268,7 @@ pdp_k_sens_fwd(int B, int H, const double* __restrict__ x0, const double* __rest
             body.append("    for (int t = 0; t < H; ++t) {")
             body.append("      const double tt = (double)t; (void)tt;")
             if not cp:
-                body.append("      double uin[%d]; pdp_row_load<%d>(uin, inputs + ((size_t)b * H + t) * %d);" % (m, m, m))
-                body.append("      " + " ".join("const double u%d = uin[%d];" % (a, a) for a in range(m)))
+                body.append("      " + " ".join("const double u%d = inputs[((size_t)b * H + t) * %d + %d];" % (a, m, a) for a in range(m)))
             body.append(self._group_step(g, cols))
             body.append("    }")
             body.append("    {")

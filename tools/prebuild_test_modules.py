@@ -57,3 +57,31 @@ sid.setStateVariable(arm.X)
 sid.setControlVariable(arm.U)
 sid.setDyn(net)
 print("neural sysid", sid._system().module_path)
+
+# modules of tests/test_gpu_modes.py::test_legacy_getauxsys_of_sysid_and_controlplanning
+uav = JinEnv.Quadrotor()
+uav.initDyn(c=0.01)
+sid2 = PDP.SysID()
+sid2.setAuxvarVariable(uav.dyn_auxvar)
+sid2.setStateVariable(uav.X)
+sid2.setControlVariable(uav.U)
+sid2.setDyn(uav.X + 0.1 * uav.f)
+sid2._system()
+for fn in (sid2.dfx_fn, sid2.dfe_fn):
+    engine.GpuFunction(fn)
+engine.DenseLQR.get(13, 1, 5)
+engine.DenseLQR.get(4, 1, 6)
+cart = JinEnv.CartPole()
+cart.initDyn(mc=0.1, mp=0.1, l=1)
+cart.initCost(wx=0.1, wq=0.6, wdx=0.1, wdq=0.1, wu=0.3)
+cpl = PDP.ControlPlanning()
+cpl.setStateVariable(cart.X)
+cpl.setControlVariable(cart.U)
+cpl.setDyn(cart.X + 0.05 * cart.f)
+cpl.setPathCost(cart.path_cost)
+cpl.setFinalCost(cart.final_cost)
+cpl.init_step(15)
+cpl._cp_system()
+for nm in ("dfx_fn", "dfu_fn", "dpolicy_dx_fn", "dpolicy_de_fn"):
+    engine.GpuFunction(getattr(cpl, nm))
+print("legacy-chain modules built")
