@@ -234,10 +234,9 @@ def run_gpu(args):
     sys_ = systems.quadrotor_irl(0.1)
     n, m, r = sys_.n, sys_.m, sys_.r
 
-    # same global batch for every GPU count: rank g takes trajectories [g*B, (g+1)*B)
-    x0, theta, U, Xref, Uref = synth_quadrotor(B * world, H, seed=0)
-    sl = slice(rank * B, (rank + 1) * B)
-    host = [np.ascontiguousarray(a[sl]) for a in (x0, theta, U, Xref, Uref)]
+    # the global batch is the concatenation of per-rank blocks of B trajectories, block g seeded with (0, g): every
+    # GPU count sees the same trajectories in block g, and no rank has to materialise the other ranks' blocks
+    host = [np.ascontiguousarray(a) for a in synth_quadrotor(B, H, seed=(0, rank))]
     pinned = [torch.from_numpy(a).pin_memory() for a in host]
     d_x0, d_th, d_U, d_Xr, d_Ur = [p.to(dev) for p in pinned]
     out = {"X": torch.empty((B, H + 1, n), dtype=torch.float64, device=dev),
