@@ -22,7 +22,7 @@ def main():
     ap.add_argument("--traj", type=int, default=32768, help="global number of recorded trajectories")
     ap.add_argument("--horizon", type=int, default=100)
     ap.add_argument("--iters", type=int, default=200)
-    ap.add_argument("--lr", type=float, default=1e-5)
+    ap.add_argument("--lr", type=float, default=1e-4, help="initial step; halved whenever the loss rises")
     args = ap.parse_args()
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", 1), ("RANK", 0), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -37,14 +37,22 @@ def main():
     x0 = torch.tensor([-8, -6, 9., 0, 0, 0, 1, 0, 0, 0, 0, 0, 0], dtype=torch.float64).repeat(B, 1).to(dev)
     theta_true = torch.tensor([1, 1, 1, 1, 0.4], dtype=torch.float64, device=dev)
     states = sys_.step(inputs, None, theta_true, x0=x0, want_traj=True)["X"]           # the "recorded" data
-    trainer = irl.SysIDTrainer(sys_, inputs, states, args.lr / 1.0)
-    theta = theta_true + torch.tensor([0.25, -0.2, 0.15, 0.2, -0.1], dtype=torch.float64, device=dev)
+    trainer = irl.SysIDTrainer(sys_, inputs, states, args.lr)
+    theta = theta_true + torch.tensor([0.1, -0.08, 0.06, 0.08, -0.04], dtype=torch.float64, device=dev)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
+    prev = float("inf")
     for k in range(args.iters):
-        loss, theta = trainer.step(theta)
+        loss, dp = trainer.gradient(theta)               # same on every rank (all-reduced), so is the step control
+        lv = loss.item()
+        if not (lv <= prev * 1.0001):                     # the plain GD of the reference diverges for long horizons:
+            trainer.lr *= 0.5                             # halve the step and retry from the last good iterate
+            theta = good
+            continue
+        prev, good = lv, theta
+        theta = theta - trainer.lr * dp
         if rank == 0 and (k % 50 == 0 or k == args.iters - 1):
-            print("iter %4d  loss %.6e  |theta - true| %.5f" % (k, loss.item(), (theta - theta_true).norm().item()))
+            print("iter %4d  loss %.6e  |theta - true| %.5f  lr %.2e" % (k, lv, (good - theta_true).norm().item(), trainer.lr))
     torch.cuda.synchronize()
     if rank == 0:
         dt = (time.perf_counter() - t0) / args.iters

@@ -15,9 +15,10 @@ sys.path.insert(0, ROOT)
 # (chunk, bwd warps/block, bwd min blocks, fwd warps/block, fwd min blocks)
 # (chunk, bwd warps/block, bwd min blocks, fwd warps/block, fwd min blocks, keep [F|G] slots in registers A->C)
 # (chunk, bwd warps/block, bwd min blocks, fwd warps/block, fwd min blocks, keep_fg, fast_rcp, early_solve)
-VARIANTS = [(16, 4, 3, 4, 4, True, False, False), (16, 4, 3, 4, 4, True, True, False), (16, 4, 3, 4, 4, True, False, True),
-            (16, 4, 3, 4, 4, True, True, True), (16, 4, 1, 4, 4, True, True, True), (16, 4, 4, 4, 4, True, True, True),
-            (16, 4, 4, 4, 4, False, True, True)]
+VARIANTS = [(16, 4, 3, 4, 4, True, True, True), (17, 4, 3, 4, 4, True, True, True), (25, 4, 2, 4, 4, True, True, True),
+            (25, 4, 3, 4, 4, True, True, True), (17, 4, 3, 4, 3, True, True, True), (10, 4, 3, 4, 4, True, True, True),
+            (17, 2, 6, 2, 8, True, True, True)]
+
 
 def make(ch, wpb, mb, wpbf=4, mbf=1, kf=True, frcp=False, early=False, verbose=False):
     from JinEnv import JinEnv
