@@ -56,10 +56,12 @@ int pdp_rollout_costate(pdp_system_t* sys, int B, int H, const double* x0, const
 /* Closed-loop rollout used by the batched ocSolver's line search (replaces IPOPT's iterations inside
  * OCSys.ocSolver, PDP/PDP.py:178-182): u_t = Uref[t] + alpha_b k_t + K_t (x_t - Xref[t]) with the gains
  * (K_t | k_t) of a one-column Riccati sweep, laid out [B,H,n+1,m] as pdp_aux_lqr_backward leaves them in its
- * workspace.  Writes the applied controls to Uout[B,H,m] and X / Lam / cost / dHu like pdp_rollout_costate. */
+ * workspace.  Writes the applied controls to Uout[B,H,m] and X / Lam / cost / dHu like pdp_rollout_costate.
+ * group > 1: B = group x (source trajectories); candidate b reads x0/theta/Uref/Xref/gains of trajectory b/group and
+ * its own alpha[b] (a whole back-tracking line search in one launch); outputs are indexed by b. */
 int pdp_rollout_feedback(pdp_system_t* sys, int B, int H, const double* x0, const double* theta, int theta_stride,
                          const double* Uref, const double* Xref, const double* gains, const double* alpha, double* Uout,
-                         double* X, double* Lam, double* cost, double* dHu, int* status, pdp_stream_t stream);
+                         double* X, double* Lam, double* cost, double* dHu, int group, int* status, pdp_stream_t stream);
 
 /* Fused OCSys.getAuxSys (PDP/PDP.py:272-314) + LQR.lqrSolver (PDP/PDP.py:446-615).
  *   X,U,Lam,theta as above; X0aux[B|1,n,r] initial condition of the auxiliary system (NULL = zeros,

@@ -63,7 +63,7 @@ def load_library(build_if_missing=True):
         lib.pdp_eval_function.argtypes = [vp, i, ctypes.POINTER(dp), ctypes.POINTER(i), ctypes.POINTER(dp), vp]
         lib.pdp_eval_function.restype = i
         lib.pdp_lqr_dense.restype = i
-        lib.pdp_rollout_feedback.argtypes = [vp, i, i, dp, dp, i, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp, vp]
+        lib.pdp_rollout_feedback.argtypes = [vp, i, i, dp, dp, i, dp, dp, dp, dp, dp, dp, dp, dp, dp, i, dp, vp]
         lib.pdp_rollout_feedback.restype = i
         lib.pdp_aux_lqr_backward.argtypes = [vp, i, i, dp, dp, dp, dp, i, dp, sz, dp, vp]
         lib.pdp_aux_lqr_backward.restype = i

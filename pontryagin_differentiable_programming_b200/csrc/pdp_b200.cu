@@ -27,7 +27,7 @@ int fail(int code, const char* fmt, ...) {
 
 using fn_info = void (*)(int*);
 using fn_rollout = int (*)(int, int, const double*, const double*, int, const double*, double*, double*, double*, double*, int*,
-                           const double*, const double*, const double*, double*, cudaStream_t);
+                           const double*, const double*, const double*, double*, int, cudaStream_t);
 using fn_aux_eval = int (*)(int, int, const double*, const double*, const double*, const double*, int, double*, double*,
                             cudaStream_t);
 using fn_aux_lqr = int (*)(int, int, const double*, const double*, const double*, const double*, int, const double*, int,
@@ -132,7 +132,7 @@ int pdp_rollout_costate(pdp_system_t* sys, int B, int H, const double* x0, const
   if (B == 0) return PDP_OK;  /* empty batch: nothing to do, pointers may be NULL */
   if (B < 0 || H < 1 || !x0 || !theta || !U || !X) return fail(PDP_ERR_ARG, "pdp_rollout_costate: bad argument");
   if (dHu && !Lam) return fail(PDP_ERR_ARG, "pdp_rollout_costate: dHu needs Lam");
-  int e = sys->rollout(B, H, x0, theta, theta_stride, U, X, Lam, cost, dHu, status, nullptr, nullptr, nullptr, nullptr,
+  int e = sys->rollout(B, H, x0, theta, theta_stride, U, X, Lam, cost, dHu, status, nullptr, nullptr, nullptr, nullptr, 1,
                        (cudaStream_t)stream);
   if (e) return fail(PDP_ERR_CUDA, "pdp_rollout_costate: CUDA error %d (%s)", e, cudaGetErrorString((cudaError_t)e));
   return PDP_OK;
@@ -140,13 +140,14 @@ int pdp_rollout_costate(pdp_system_t* sys, int B, int H, const double* x0, const
 
 int pdp_rollout_feedback(pdp_system_t* sys, int B, int H, const double* x0, const double* theta, int theta_stride,
                          const double* Uref, const double* Xref, const double* gains, const double* alpha, double* Uout,
-                         double* X, double* Lam, double* cost, double* dHu, int* status, pdp_stream_t stream) {
+                         double* X, double* Lam, double* cost, double* dHu, int group, int* status, pdp_stream_t stream) {
   if (!sys || !sys->rollout) return fail(PDP_ERR_UNSUPPORTED, "pdp_rollout_feedback: module has no rollout kernel");
   if (B == 0) return PDP_OK;  /* empty batch: nothing to do, pointers may be NULL */
   if (B < 0 || H < 1 || !x0 || !theta || !Uref || !Xref || !gains || !alpha || !Uout || !X)
     return fail(PDP_ERR_ARG, "pdp_rollout_feedback: bad argument");
   if (dHu && !Lam) return fail(PDP_ERR_ARG, "pdp_rollout_feedback: dHu needs Lam");
-  int e = sys->rollout(B, H, x0, theta, theta_stride, Uref, X, Lam, cost, dHu, status, gains, Xref, alpha, Uout,
+  if (group < 1 || B % group != 0) return fail(PDP_ERR_ARG, "pdp_rollout_feedback: B must be a multiple of group");
+  int e = sys->rollout(B, H, x0, theta, theta_stride, Uref, X, Lam, cost, dHu, status, gains, Xref, alpha, Uout, group,
                        (cudaStream_t)stream);
   if (e) return fail(PDP_ERR_CUDA, "pdp_rollout_feedback: CUDA error %d (%s)", e, cudaGetErrorString((cudaError_t)e));
   return PDP_OK;

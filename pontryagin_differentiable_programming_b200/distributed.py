@@ -20,9 +20,8 @@ def shard_bounds(global_batch: int, rank: int, world: int):
 def reduce_loss_dp(loss_dp_local: torch.Tensor, group=None):
     """loss_dp_local[B_local, r+1] (per-trajectory loss and half-gradient) -> (mean loss, mean dp[r])
     over the global batch.  One all-reduce of r+2 float64 values; identity when not initialised."""
-    partial = torch.cat([loss_dp_local.sum(dim=0),
-                         torch.tensor([float(loss_dp_local.shape[0])], dtype=loss_dp_local.dtype,
-                                      device=loss_dp_local.device)])
+    count = torch.full((1,), float(loss_dp_local.shape[0]), dtype=loss_dp_local.dtype, device=loss_dp_local.device)
+    partial = torch.cat([loss_dp_local.sum(dim=0), count])       # (fill kernel, not a host copy: graph-capturable)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=group)
     count = partial[-1]

@@ -97,23 +97,30 @@ class OCSystem:
             out["dHu"] = dHu
         return out
 
-    def rollout_feedback(self, x0, theta, Uref, Xref, gains, alpha, want_dHu=True, status=None):
-        """Closed-loop rollout u_t = Uref[t] + alpha_b k_t + K_t (x_t - Xref[t]); gains[B,H,n+1,m] (or the raw
-        workspace of a one-column Riccati sweep).  -> dict U (applied), X, Lam, cost[, dHu]."""
+    def rollout_feedback(self, x0, theta, Uref, Xref, gains, alpha, want_dHu=True, want_costate=True, status=None,
+                         group=1):
+        """Closed-loop rollout u_t = Uref[t] + alpha k_t + K_t (x_t - Xref[t]); gains[B,H,n+1,m] (or the raw
+        workspace of a one-column Riccati sweep).  ``group`` > 1: ``alpha`` has B*group entries and candidate
+        ``b*group + j`` rolls trajectory ``b`` out with ``alpha[b*group + j]`` (a whole line search in one launch).
+        -> dict U (applied), X, cost [, Lam, dHu], leading dimension B*group."""
         require_cuda()
         dev = x0.device
         B, H = Uref.shape[0], Uref.shape[1]
         theta, ts = self._theta(theta, B, dev)
+        Bx = B * int(group)
         mk = lambda *shape: torch.empty(shape, dtype=torch.float64, device=dev)
-        X, Lam, cost, Uout = mk(B, H + 1, self.n), mk(B, H, self.n), mk(B), mk(B, H, self.m)
-        dHu = mk(B, H, self.m) if want_dHu else None
+        X, cost, Uout = mk(Bx, H + 1, self.n), mk(Bx), mk(Bx, H, self.m)
+        Lam = mk(Bx, H, self.n) if (want_costate or want_dHu) else None
+        dHu = mk(Bx, H, self.m) if want_dHu else None
         st = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
-            backend.check(self.handle.lib.pdp_rollout_feedback(self.handle.ptr, B, H, _ptr(x0), _ptr(theta), ts, _ptr(Uref),
+            backend.check(self.handle.lib.pdp_rollout_feedback(self.handle.ptr, Bx, H, _ptr(x0), _ptr(theta), ts, _ptr(Uref),
                                                                _ptr(Xref), _ptr(gains), _ptr(alpha), _ptr(Uout), _ptr(X),
-                                                               _ptr(Lam), _ptr(cost), _ptr(dHu), _ptr(status), st),
+                                                               _ptr(Lam), _ptr(cost), _ptr(dHu), int(group), _ptr(status), st),
                           "pdp_rollout_feedback")
-        out = {"U": Uout, "X": X, "Lam": Lam, "cost": cost}
+        out = {"U": Uout, "X": X, "cost": cost}
+        if Lam is not None:
+            out["Lam"] = Lam
         if want_dHu:
             out["dHu"] = dHu
         return out

@@ -42,6 +42,44 @@ class IRLTrainer:
         loss, dp = self.gradient(theta)
         return loss, theta.reshape(-1) - self.lr * dp
 
+    # ------------------------------------------------------------------ CUDA-graph path
+    def _iteration_fixed(self, theta, n_newton):
+        th = theta.reshape(1, -1)
+        sol = ocsolver.solve_fixed(self.sys, self.x0, self.H, th, self._fixed_state, n_iter=n_newton)
+        res = self.sys.sweep(self.x0, th, sol["U"], Xref=self.Xd, Uref=self.Ud, want_traj=False)
+        loss, dp = distributed.reduce_loss_dp(res["loss_dp"], self.group)
+        return loss, theta.reshape(-1) - self.lr * dp, sol["grad_norm"].max()
+
+    def step_graph(self, theta, n_newton=3):
+        """The same iteration as :meth:`step` replayed from ONE captured CUDA graph (fixed ``n_newton`` Newton
+        iterations with single-launch line searches, fused sweep, update): no host round-trips inside.  The first call
+        brings the warm start in with the adaptive solver, warms the kernels up and captures.  Returns
+        (loss, theta_next, max residual |dH/du| of the inner solves) as device tensors valid until the next call."""
+        dev = self.Xd.device
+        if getattr(self, "_graph", None) is None:
+            if torch.distributed.is_available() and torch.distributed.is_initialized() and \
+                    torch.distributed.get_world_size(self.group) > 1:
+                raise RuntimeError("step_graph captures a single-GPU iteration; use step() for sharded runs")
+            self._theta_in = theta.detach().reshape(-1).to(dev, torch.float64).clone()
+            sol = ocsolver.solve(self.sys, self.x0, self.H, self._theta_in.reshape(1, -1))     # cold start, adaptive
+            self._fixed_state = ocsolver.FixedSolverState(self.x0.shape[0], self.H, self.sys.m, dev)
+            self._fixed_state.U.copy_(sol["U"])
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                saved = (self._fixed_state.U.clone(), self._fixed_state.s_newton.clone(), self._fixed_state.mu.clone())
+                for _ in range(2):                                                               # warm-up outside capture
+                    self._iteration_fixed(self._theta_in, n_newton)
+                for dst, src in zip((self._fixed_state.U, self._fixed_state.s_newton, self._fixed_state.mu), saved):
+                    dst.copy_(src)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._g_out = self._iteration_fixed(self._theta_in, n_newton)
+        self._theta_in.copy_(theta.reshape(-1))
+        self._graph.replay()
+        return self._g_out
+
 
 class SysIDTrainer:
     """System-identification mode for a compiled ``SysIDSystem`` (reference PDP.py:1261-1296 + the GD loop)."""

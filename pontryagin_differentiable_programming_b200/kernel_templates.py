@@ -45,21 +45,24 @@ pdp_k_rollout_costate(int B, int H, const double* __restrict__ x0, const double*
                       const double* __restrict__ U, double* __restrict__ X, double* __restrict__ Lam,
                       double* __restrict__ cost, double* __restrict__ dHu, int* __restrict__ status,
                       const double* __restrict__ fb_gains, const double* __restrict__ fb_X,
-                      const double* __restrict__ fb_alpha, double* __restrict__ Uout)
+                      const double* __restrict__ fb_alpha, double* __restrict__ Uout, int fb_group)
 {
   // Optional closed-loop mode (batched ocSolver line search): with fb_gains != NULL the applied control is
   //   u_t = U[t] + alpha_b * k_t + K_t (x_t - fb_X[t])   (gains in the (K|k) record layout of the Riccati
-  // sweep with one column) and is written to Uout.
+  // sweep with one column) and is written to Uout.  With fb_group > 1 the launch holds fb_group candidates per source
+  // trajectory (thread b reads x0 / theta / U / fb_X / fb_gains of trajectory b / fb_group and its own alpha): a whole
+  // back-tracking line search in one launch.
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
+  const int bs = (fb_gains != nullptr && fb_group > 1) ? b / fb_group : b;     // source trajectory of this thread
   double x[PDP_N], xn[PDP_N], th[PDP_NTH], u[PDP_M], tmp[1];
   #pragma unroll
-  for (int i = 0; i < PDP_NTH; ++i) th[i] = theta[(size_t)b * theta_stride + i];
+  for (int i = 0; i < PDP_NTH; ++i) th[i] = theta[(size_t)bs * theta_stride + i];
   #pragma unroll
-  for (int i = 0; i < PDP_N; ++i) x[i] = x0[(size_t)b * PDP_N + i];
+  for (int i = 0; i < PDP_N; ++i) x[i] = x0[(size_t)bs * PDP_N + i];
   double J = 0.0;
   double* Xb = X + (size_t)b * (H + 1) * PDP_N;
-  const double* Ub = U + (size_t)b * H * PDP_M;
+  const double* Ub = U + (size_t)bs * H * PDP_M;
   const double fb_a = fb_gains ? fb_alpha[b] : 0.0;
   double un[PDP_M];                       // software prefetch: the next step's control is in flight during this step
   pdp_row_load<PDP_M>(un, Ub);
@@ -71,8 +74,8 @@ pdp_k_rollout_costate(int B, int H, const double* __restrict__ x0, const double*
       pdp_row_load<PDP_M>(un, Ub + (t + 1) * PDP_M);
     }
     if (fb_gains != nullptr) {
-      const double* g = fb_gains + ((size_t)b * H + t) * ((PDP_N + 1) * PDP_M);
-      const double* xo = fb_X + ((size_t)b * (H + 1) + t) * PDP_N;
+      const double* g = fb_gains + ((size_t)bs * H + t) * ((PDP_N + 1) * PDP_M);
+      const double* xo = fb_X + ((size_t)bs * (H + 1) + t) * PDP_N;
       #pragma unroll
       for (int a = 0; a < PDP_M; ++a) u[a] = fma(fb_a, g[PDP_N * PDP_M + a], u[a]);
       #pragma unroll
@@ -353,10 +356,10 @@ extern "C" void pdpmod_info(int* out) {
 extern "C" int pdpmod_rollout_costate(int B, int H, const double* x0, const double* theta, int theta_stride, const double* U,
                                       double* X, double* Lam, double* cost, double* dHu, int* status,
                                       const double* fb_gains, const double* fb_X, const double* fb_alpha, double* Uout,
-                                      cudaStream_t st) {
+                                      int fb_group, cudaStream_t st) {
   if (B <= 0) return 0;
   pdp_k_rollout_costate<<<(B + 127) / 128, 128, 0, st>>>(B, H, x0, theta, theta_stride, U, X, Lam, cost, dHu, status,
-                                                         fb_gains, fb_X, fb_alpha, Uout);
+                                                         fb_gains, fb_X, fb_alpha, Uout, fb_group);
   return (int)cudaGetLastError();
 }
 

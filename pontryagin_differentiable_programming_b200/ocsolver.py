@@ -171,3 +171,74 @@ def solve_multistart(oc: OCSystem, x0, horizon, theta, n_starts=8, seed=0, **opt
     out["iters"] = sol["iters"]
     out["start"] = best
     return out
+
+
+DEFAULT_ALPHAS = (1.0, 0.5, 0.25, 0.125, 0.0625, 0.03125, 0.015625, 0.0078125)
+
+
+class FixedSolverState:
+    """Per-problem solver state that persists across calls of :func:`solve_fixed` (warm start, Hessian mode, shift)."""
+
+    def __init__(self, B, H, m, device, alphas=None):
+        z = lambda *s: torch.zeros(s, dtype=torch.float64, device=device)
+        self.U = z(B, H, m)
+        self.s_newton = torch.ones(B, dtype=torch.float64, device=device)
+        self.mu = z(B)
+        # constants created here (outside any graph capture: host -> device copies cannot be captured)
+        self.alphas = tuple(DEFAULT_ALPHAS if alphas is None else alphas)
+        self.a_row = torch.tensor(self.alphas, dtype=torch.float64, device=device)
+        self.a_tab = self.a_row.repeat(B).contiguous()
+        self.rows = torch.arange(B, device=device)
+
+
+def solve_fixed(oc: OCSystem, x0, horizon, theta, state: FixedSolverState, n_iter=3, tol=1e-8):
+    """Fixed-shape variant of :func:`solve` for CUDA-graph capture: ``n_iter`` Newton/DDP iterations, each with the
+    WHOLE back-tracking line search evaluated in one launch (``len(alphas)`` closed-loop candidates per problem),
+    no host synchronisation and no data-dependent control flow.  Warm-starts from and updates ``state`` in place.
+    Returns the final dict X, U, Lam, cost, dHu, grad_norm (all device tensors)."""
+    require_cuda()
+    dev = x0.device
+    B, H = x0.shape[0], int(horizon)
+    nt = newton_system(oc)
+    if theta.dim() == 1:
+        theta = theta.unsqueeze(0)
+    if theta.shape[0] == 1 and B > 1:
+        theta = theta.expand(B, -1)
+    theta = theta.contiguous()
+    A = len(state.alphas)
+    a_row, a_tab, rows = state.a_row, state.a_tab, state.rows
+    ext = torch.empty((B, oc.r + 2), dtype=torch.float64, device=dev)
+    ext[:, :oc.r] = theta
+    status = torch.zeros(B, dtype=torch.int32, device=dev)
+    U, s_newton, mu = state.U, state.s_newton, state.mu
+    for _ in range(n_iter):
+        cur = oc.rollout_costate(x0, theta, U, want_dHu=True)
+        gnorm = cur["dHu"].abs().amax(dim=(1, 2))
+        active = gnorm > tol * (1.0 + cur["Lam"].abs().amax(dim=(1, 2)))
+        ext[:, oc.r] = s_newton
+        ext[:, oc.r + 1] = mu
+        status.zero_()
+        dU, _, gains = nt.direction(cur["X"], U, cur["Lam"], ext, status)
+        slope = (cur["dHu"] * dU).sum(dim=(1, 2))
+        bad = (status != 0) | ~torch.isfinite(slope) | (slope >= 0)
+        trial = oc.rollout_feedback(x0, theta, U, cur["X"], gains, a_tab, want_dHu=False, want_costate=False, group=A)
+        costs = trial["cost"].view(B, A)
+        ok = torch.isfinite(costs) & (costs <= cur["cost"][:, None] + 1e-4 * a_row[None, :] * slope[:, None])
+        ok = ok & active[:, None] & ~bad[:, None]
+        any_ok = ok.any(dim=1)
+        first = torch.argmax(ok.to(torch.int8), dim=1)                 # alphas are descending: the largest accepted step
+        Usel = trial["U"].view(B, A, H, oc.m)[rows, first]
+        U = torch.where(any_ok[:, None, None], Usel, U)
+        failed = active & ~any_ok
+        was_gn = s_newton == 0
+        mu = torch.where(failed & was_gn, torch.clamp(mu * 10.0, min=1e-6), torch.where(failed, mu, mu * 0.1))
+        mu = torch.where(mu < 1e-12, torch.zeros_like(mu), mu)
+        s_newton = torch.where(failed, torch.zeros_like(s_newton), s_newton)
+        s_newton = torch.where(any_ok & (a_row[first] >= 0.5), torch.ones_like(s_newton), s_newton)
+    state.U.copy_(U)
+    state.s_newton.copy_(s_newton)
+    state.mu.copy_(mu)
+    final = oc.rollout_costate(x0, theta, state.U, want_dHu=True)
+    final["U"] = state.U
+    final["grad_norm"] = final["dHu"].abs().amax(dim=(1, 2))
+    return final

@@ -472,3 +472,27 @@ def test_legacy_getauxsys_of_sysid_and_controlplanning():
     assert _rel(np.stack(sol["control_traj"]), dUr) < 1e-10
     loss, dth = oc.step(x0, H, th)
     assert abs(loss - cost) < 1e-11 * abs(cost) and _rel(dth, grad) < 1e-10
+
+
+def test_graph_captured_irl_iteration_matches_eager():
+    """IRLTrainer.step_graph (fixed-shape solver with single-launch line search, one CUDA graph per iteration)
+    follows the eager trainer and the shipped quadrotor trace."""
+    from pontryagin_differentiable_programming_b200 import irl, systems
+    dev = _dev()
+    g2 = np.load(os.path.join(G, "k2_demos.npz"))
+    g3 = np.load(os.path.join(G, "k3_irl_traces.npz"))
+    sys_ = systems.quadrotor_irl(float(g2["quadrotor_dt"][0]))
+    Xd = _t(np.stack([g2["quadrotor_%d_X" % i] for i in range(2)]), dev)
+    Ud = _t(np.stack([g2["quadrotor_%d_U" % i] for i in range(2)]), dev)
+    lr = float(g3["quadrotor_0_lr"][0])
+    eager, graph = irl.IRLTrainer(sys_, Xd, Ud, lr), irl.IRLTrainer(sys_, Xd, Ud, lr)
+    theta_e = theta_g = _t(g3["quadrotor_0_theta"][0], dev)
+    for k in range(4):
+        loss_e, theta_e = eager.step(theta_e)
+        loss_g, theta_g, resid = graph.step_graph(theta_g)
+        theta_g = theta_g.clone()
+        assert abs(loss_g.item() - loss_e.item()) < 1e-6 * abs(loss_e.item())
+        assert torch.max(torch.abs(theta_g - theta_e)).item() < 1e-9
+        assert resid.item() < 1e-4
+        if k == 0:
+            assert abs(loss_g.item() - g3["quadrotor_0_loss"][0]) < 1e-5 * g3["quadrotor_0_loss"][0]
