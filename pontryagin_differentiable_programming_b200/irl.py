@@ -54,7 +54,10 @@ class IRLTrainer:
         """The same iteration as :meth:`step` replayed from ONE captured CUDA graph (fixed ``n_newton`` Newton
         iterations with single-launch line searches, fused sweep, update): no host round-trips inside.  The first call
         brings the warm start in with the adaptive solver, warms the kernels up and captures.  Returns
-        (loss, theta_next, max residual |dH/du| of the inner solves) as device tensors valid until the next call."""
+        (loss, theta_next, max residual |dH/du| of the inner solves) as device tensors valid until the next call.
+        ``n_newton`` is baked into the graph: pick it for the largest parameter step the run will take (the early,
+        large updates of the quadrotor example need ~10; 3 is enough once the loss has settled) and monitor the returned
+        residual - converged problems cost nothing extra because their iterations are no-ops."""
         dev = self.Xd.device
         if getattr(self, "_graph", None) is None:
             if torch.distributed.is_available() and torch.distributed.is_initialized() and \
@@ -73,6 +76,8 @@ class IRLTrainer:
                 for dst, src in zip((self._fixed_state.U, self._fixed_state.s_newton, self._fixed_state.mu), saved):
                     dst.copy_(src)
             torch.cuda.current_stream(dev).wait_stream(side)
+            # the captured launches hold raw pointers into the system's workspaces: keep them alive with the graph
+            self._graph_keepalive = (tuple(self.sys._ws.values()), ocsolver.newton_system(self.sys)._ws)
             self._graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._graph):
                 self._g_out = self._iteration_fixed(self._theta_in, n_newton)

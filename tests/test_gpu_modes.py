@@ -489,10 +489,12 @@ def test_graph_captured_irl_iteration_matches_eager():
     theta_e = theta_g = _t(g3["quadrotor_0_theta"][0], dev)
     for k in range(4):
         loss_e, theta_e = eager.step(theta_e)
-        loss_g, theta_g, resid = graph.step_graph(theta_g)
+        loss_g, theta_g, resid = graph.step_graph(theta_g, n_newton=12)     # the first updates move theta a lot
         theta_g = theta_g.clone()
         assert abs(loss_g.item() - loss_e.item()) < 1e-6 * abs(loss_e.item())
         assert torch.max(torch.abs(theta_g - theta_e)).item() < 1e-9
         assert resid.item() < 1e-4
         if k == 0:
             assert abs(loss_g.item() - g3["quadrotor_0_loss"][0]) < 1e-5 * g3["quadrotor_0_loss"][0]
+        if k == 1:
+            assert abs(loss_g.item() - g3["quadrotor_0_loss"][1]) < 1e-5 * g3["quadrotor_0_loss"][1]

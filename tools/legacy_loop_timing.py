@@ -57,7 +57,7 @@ def legacy_iteration(current_parameter, n_starts):
 
 
 rows = []
-for n_starts in (8, 1):
+for n_starts in (1,):
     theta = theta0.copy()
     legacy_iteration(theta, n_starts)                       # compile / warm
     torch.cuda.synchronize()
@@ -85,6 +85,20 @@ torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / K
 rows.append({"path": "IRLTrainer (device-resident, warm-started solver, 2 demos)", "s_per_iter": dt, "iters_per_s": 1 / dt,
              "loss_after": float(loss)})
+for n_newton in (3, 10):
+    gtr = irl.IRLTrainer(oc._system(), Xd, Ud, lr)
+    th_g = torch.as_tensor(theta0.ravel(), device=dev)
+    for _ in range(3):                                                 # capture + the large first updates
+        th_g = gtr.step_graph(th_g, n_newton=n_newton)[1].clone()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        out = gtr.step_graph(th_g, n_newton=n_newton)
+        th_g.copy_(out[1])
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / K
+    rows.append({"path": "IRLTrainer.step_graph (one CUDA graph per iteration, n_newton=%d)" % n_newton, "s_per_iter": dt,
+                 "iters_per_s": 1 / dt, "loss_after": float(out[0]), "resid": float(out[2])})
 rows.append({"path": "reference as shipped (author's machine, PDP_results_trial_*.mat time_passed)", "iters_per_s": 2.4})
 for r in rows:
     print(json.dumps(r))
