@@ -193,8 +193,10 @@ class OCModuleSource:
 
     def __init__(self, state: SX, control: SX, auxvar: SX, dyn: SX, path_cost: SX, final_cost: SX,
                  chunk: int = 8, warps_per_block: int = 4, min_blocks: int = 1, fwd_warps_per_block: int = 4,
-                 fwd_min_blocks: int = 1, keep_fg: bool = True, fast_rcp: bool = False, early_solve: bool = False):
+                 fwd_min_blocks: int = 1, keep_fg: bool = True, fast_rcp: bool = False, early_solve: bool = False,
+                 fwd_pack: int = 0, fwd_chunk: int = 0):
         self.keep_fg = bool(keep_fg)
+        self.fwd_pack, self.fwd_chunk = int(fwd_pack), int(fwd_chunk)
         self.fast_rcp, self.early_solve = bool(fast_rcp), bool(early_solve)
         self.min_blocks = int(min_blocks)
         self.wpbf, self.min_blocks_f = int(fwd_warps_per_block), int(fwd_min_blocks)
@@ -499,18 +501,44 @@ class OCModuleSource:
                 out.append("%s%s[%d] = %s;" % (ind, ptr, a, names[a]))
         return "\n".join(out)
 
+    fwd_smem_budget = 18 * 1024
+
+    def _fwd_shape(self):
+        """(trajectories per warp, chunk length) of the forward kernel: lane g*r + c owns column c of trajectory g.
+        The chunk is capped so that one warp's regions stay within ``fwd_smem_budget`` bytes of shared memory
+        (18 KB: twelve warps per SM)."""
+        fg = getattr(self, "fwd_pack", 0) or max(1, min(WARP // max(self.r, 1), 4))
+        fg = max(1, min(fg, WARP // max(self.r, 1), WARP))
+        ch = getattr(self, "fwd_chunk", 0)
+        if not ch:
+            per_step = _pad_ld(self.nvar_s) + self.n + self.m
+            fit = (self.fwd_smem_budget // (8 * fg) - self.n * self.m - max(self.nth, 1) - 16) // per_step
+            ch = min(WARP // fg if fg > 1 else self.chunk, max(fit, 1))
+        ch = max(1, min(ch, WARP // fg))
+        return fg, ch
+
     def _forward_step(self) -> str:
         n, m, r, ns = self.n, self.m, self.r, self.ns
         L: List[str] = []
         ind = "      "
-        L.append(ind + "// U(:,c) = k(:,c) + K X(:,c)   (lane n+c owns column c); two partial sums per row shorten the chains")
+        L.append(ind + "// U(:,c) = k(:,c) + K X(:,c); K staged as [l][a] per trajectory; two partial sums per row shorten the chains")
         half = (n + 1) // 2
         for a in range(m):
             L.append(ind + "double u%d = g%d, ub%d = 0.0;" % (a, a, a))
-        for a in range(m):
-            for l in range(n):
-                tgt = "u%d" % a if l < half else "ub%d" % a
-                L.append(ind + "%s = fma(KS[%d], x%d, %s);" % (tgt, a * self.ldk + l, l, tgt))
+        for l in range(n):
+            a = 0
+            while a < m:
+                if m % 2 == 0:
+                    L.append(ind + "{ const double2 kk = *reinterpret_cast<const double2*>(KS + %d);" % (l * m + a))
+                    for d, comp in ((0, "x"), (1, "y")):
+                        tgt = "u%d" % (a + d) if l < half else "ub%d" % (a + d)
+                        L.append(ind + "  %s = fma(kk.%s, x%d, %s);" % (tgt, comp, l, tgt))
+                    L.append(ind + "}")
+                    a += 2
+                else:
+                    tgt = "u%d" % a if l < half else "ub%d" % a
+                    L.append(ind + "%s = fma(KS[%d], x%d, %s);" % (tgt, l * m + a, l, tgt))
+                    a += 1
         for a in range(m):
             L.append(ind + "u%d += ub%d;" % (a, a))
         L.append(ind + "// X+(:,c) = F X(:,c) + G U(:,c) + E(:,c)")
@@ -537,6 +565,36 @@ class OCModuleSource:
                 L.append(ind + "n%d += (col == %d) ? %s : 0.0;" % (i, c, val))
         return "\n".join(L)
 
+    def _fwd_gain_prefetch(self, fg):
+        """K of the FG trajectories is fetched cooperatively (unit q = lane + 32 j), the k column by its owner lane."""
+        n, m, r = self.n, self.m, self.r
+        kw = n * m
+        vec = (m % 2 == 0)
+        unit = 2 if vec else 1
+        per = kw // unit
+        nq = (fg * per + WARP - 1) // WARP
+        ty = "double2" if vec else "double"
+        setup, load, store = [], [], []
+        for j in range(nq):
+            setup.append("  const int kq%d = lane + %d;" % (j, WARP * j))
+            setup.append("  const bool kv%d = kq%d < %d;" % (j, j, fg * per))
+            setup.append("  const int kg%d = kv%d ? kq%d / %d : 0, ke%d = kq%d - (kq%d / %d) * %d;" % (j, j, j, per, j, j, j, per, per))
+            setup.append("  const double* kp%d = gains + (size_t)((b0 + kg%d < B) ? b0 + kg%d : B - 1) * H * PDP_GREC + ke%d * %d;"
+                         % (j, j, j, j, unit))
+            setup.append("  double* kd%d = wbase + kg%d * PDP_FTS + PDP_FOFF_KS + ke%d * %d;" % (j, j, j, unit))
+            setup.append("  %s kn%d = %s;" % (ty, j, "make_double2(0.0, 0.0)" if vec else "0.0"))
+            load.append("        if (kv%d) kn%d = *reinterpret_cast<const %s*>(kp%d + ro);" % (j, j, ty, j))
+            store.append("      if (kv%d) *reinterpret_cast<%s*>(kd%d) = kn%d;" % (j, ty, j, j))
+        gl = ["        const size_t ro = (size_t)(t + 1) * PDP_GREC;", "        if (col >= 0) {",
+              "          const double* gp = gains + (size_t)bg * H * PDP_GREC + ro + (PDP_N + col) * PDP_M;"]
+        if vec:
+            gl += ["          { const double2 gg = *reinterpret_cast<const double2*>(gp + %d); gn%d = gg.x; gn%d = gg.y; }" % (a, a, a + 1)
+                   for a in range(0, m, 2)]
+        else:
+            gl += ["          gn%d = gp[%d];" % (a, a) for a in range(m)]
+        gl.append("        }")
+        return "\n".join(setup), "\n".join(gl + load), "\n".join(store)
+
     # ---- whole translation unit ----------------------------------------------------------------
     def source(self) -> str:
         n, m, r, ns = self.n, self.m, self.r, self.ns
@@ -549,17 +607,21 @@ class OCModuleSource:
         off_quu = off_ks + ks_size
         off_th = off_quu + _even(m * m)
         warp_doubles = _even(off_th + max(self.nth, 1))
-        # forward kernel: [CH][FLD] dynamics slots | OUT | KS | TH | DLC
+        # forward kernel, per trajectory region: [CHF][FLD] dynamics slots | K [l][a] | TH | residuals [CHF][n+m]
+        fg, chf = self._fwd_shape()
         fld = _pad_ld(self.nvar_s)
-        foff_ks = _even(self.chunk * fld)
-        foff_th = foff_ks + ks_size
-        foff_dl = foff_th + _even(max(self.nth, 1))
-        fwarp_doubles = _even(foff_dl + max(self.chunk * nm, n))
+        foff_ks = _even(chf * fld)
+        foff_th = foff_ks + _even(n * m)
+        foff_dl = foff_th + _even(max(self.nth, 1))               # residuals x - xref [CHF*n], u - uref [CHF*m]
+        foff_du = foff_dl + chf * n
+        fts = _pad_ld(foff_du + chf * m)
+        fwarp_doubles = max(fg * fts, WARP)
         defs = {
             "N": n, "M": m, "R": r, "NS": ns, "NM": nm, "NVAR": self.nvar, "NVAR_S": self.nvar_s,
             "AUXLD": self.auxld, "CH": self.chunk, "WPB": self.wpb, "LDZ": self.ldz,
             "LDK": self.ldk, "OFF_ZT": off_zt, "OFF_KS": off_ks, "OFF_QUU": off_quu, "OFF_TH": off_th,
-            "FLD": fld, "FOFF_KS": foff_ks, "FOFF_TH": foff_th, "FOFF_DL": foff_dl,
+            "FLD": fld, "FOFF_KS": foff_ks, "FOFF_TH": foff_th, "FOFF_DL": foff_dl, "FG": fg, "CHF": chf, "FTS": fts,
+            "FOFF_DU": foff_du,
             "FWARP_DOUBLES": fwarp_doubles, "WPBF": getattr(self, "wpbf", 4), "MINBF": getattr(self, "min_blocks_f", 1),
             "WARP_DOUBLES": warp_doubles, "NTH": self.nth, "MINB": getattr(self, "min_blocks", 1), "GREC": (n + r) * m,
             "NDENSE": n * n + n * m + n * r + n * n + n * m + n * r + m * n + m * m + m * r,
@@ -580,12 +642,11 @@ class OCModuleSource:
             term_init.append("    y%d = (lane < %d) ? TB[lane * %d + %d] : ((lane >= %d && lane < %d) ? TB[%d + %d * %d + (lane - %d)] : 0.0);"
                              % (k, n, n, k, nm, ns, n * n, k, r, nm))
         xdecl = "double " + ", ".join("x%d" % k for k in range(n)) + ";"
-        xinit = "\n".join("    x%d = (X0a != nullptr && col >= 0) ? X0a[(size_t)(x0a_stride ? b : 0) * %d + %d * %d + col] : 0.0;"
+        xinit = "\n".join("    x%d = (X0a != nullptr && col >= 0) ? X0a[(size_t)(x0a_stride ? bg : 0) * %d + %d * %d + col] : 0.0;"
                           % (k, n * r, k, r) for k in range(n))
         gndecl = "double " + ", ".join("gn%d = 0.0" % a for a in range(m)) + ";"
         gcur = "      const double " + ", ".join("g%d = gn%d" % (a, a) for a in range(m)) + ";"
-        gnload = self._gload()
-        ks_store = "\n".join("        KS[%d + lane] = g%d;" % (a * self.ldk, a) for a in range(m))
+        kq_setup, gnload, ks_store = self._fwd_gain_prefetch(fg)
         xstore = "\n".join("          o[%d] = n%d;" % (i * r, i) for i in range(n))
         ustore = "\n".join("          o[%d] = u%d;" % (a * r, a) for a in range(m))
         xcopy = "\n".join("      x%d = n%d;" % (k, k) for k in range(n))
@@ -594,12 +655,13 @@ class OCModuleSource:
         rep = {
             "@@TABLOAD@@": tabload, "@@YDECL@@": ydecl,
             "@@TERM_INIT@@": "\n".join(term_init), "@@BACKWARD_STEP@@": self._backward_step(),
-            "@@XDECL@@": xdecl, "@@XINIT@@": xinit, "@@GNDECL@@": gndecl, "@@GNLOAD@@": gnload, "@@GCUR@@": gcur,
+            "@@XDECL@@": xdecl, "@@XINIT@@": xinit, "@@GNDECL@@": gndecl, "@@GNLOAD@@": gnload, "@@GCUR@@": gcur, "@@KQ_SETUP@@": kq_setup,
             "@@KS_STORE@@": ks_store, "@@FORWARD_STEP@@": self._forward_step(), "@@XSTORE@@": xstore, "@@USTORE@@": ustore,
             "@@XCOPY@@": xcopy, "@@X0STORE@@": x0store,
-            "@@DPACC@@": "\n".join(["        dpacc = fma(dl[%d], x%d, dpacc);" % (i, i) for i in range(n)] +
-                                    ["        dpacc = fma(dl[%d], u%d, dpacc);" % (n + a, a) for a in range(m)]),
-            "@@DPTERM@@": "\n".join("      dpacc = fma(dl[%d], x%d, dpacc);" % (i, i) for i in range(n)),
+            "@@DPACC@@": "\n".join(["        dpacc = fma(dlx[%d], x%d, dpacc);" % (i, i) for i in range(n)] +
+                                    ["        dpacc = fma(dlu[%d], u%d, dpacc);" % (a, a) for a in range(m)]),
+            "@@DPTERM@@": "\n".join("      { const double d = xh[%d] - xrh[%d]; dpacc = fma(d, x%d, dpacc); lt = fma(d, d, lt); }"
+                                     % (i, i, i) for i in range(n)),
             "@@XCHK@@": "\n".join("    chk += x%d;" % k for k in range(n)),
         }
         rep.update(self._eval_macros())
@@ -626,15 +688,9 @@ class OCModuleSource:
       if (lane < PDP_CH && te < H)
         pdp_f_aux_slots(Xb + (size_t)te * PDP_N, Ub + (size_t)te * PDP_M, Lb + (size_t)te * PDP_N, TH, auxc + lane * PDP_AUXLD);
     }""",
-            "@@EVAL_DYN@@": "        pdp_f_dyn_slots(Xb + (size_t)te * PDP_N, Ub + (size_t)te * PDP_M, TH, auxc + lane * PDP_FLD);",
+            "@@EVAL_DYN@@": "        pdp_f_dyn_slots(X + ((size_t)be * (H + 1) + te) * PDP_N, U + ((size_t)be * H + te) * PDP_M, the, eo);",
+            "@@EVAL_DYN_COOP@@": "",
         }
-
-    def _gload(self):
-        m = self.m
-        if m % 2 == 0:
-            return "\n".join("        { const double2 gg = *reinterpret_cast<const double2*>(gp + %d); gn%d = gg.x; gn%d = gg.y; }" % (a, a, a + 1)
-                             for a in range(0, m, 2))
-        return "\n".join("        gn%d = gp[%d];" % (a, a) for a in range(m))
 
     def key(self) -> str:
         return hashlib.sha256(self.source().encode()).hexdigest()[:20]
@@ -733,6 +789,7 @@ class LQRModuleSource(OCModuleSource):
     unused, exactly like the reference (PDP.py:569,572,598 use transpose(Hxu))."""
 
     kind_id = 4
+    fwd_smem_budget = 40 * 1024
 
     def __init__(self, n: int, m: int, r: int, chunk: int = 2, warps_per_block: int = 4):
         self.n, self.m, self.r = int(n), int(m), int(r)
@@ -812,7 +869,16 @@ class LQRModuleSource(OCModuleSource):
         return {
             "@@EVAL_TERM@@": "  for (int i = lane; i < PDP_N * PDP_N + PDP_N * PDP_R; i += 32) TB[i] = termrec[(size_t)b * (PDP_N * PDP_N + PDP_N * PDP_R) + i];",
             "@@EVAL_AUX_CHUNK@@": gather % {"NV": "PDP_NVAR"},
-            "@@EVAL_DYN@@": "        for (int e = 0; e < PDP_NVAR_S; ++e) auxc[lane * PDP_FLD + e] = auxrec[((size_t)b * H + te) * PDP_NDENSE + pdp_slot_src[e]];",
+            "@@EVAL_DYN@@": "",
+            "@@EVAL_DYN_COOP@@": """    {
+      const int nst = (tc + PDP_CHF < H ? PDP_CHF : H - tc);
+      for (int idx = lane; idx < PDP_FG * nst * PDP_NVAR_S; idx += 32) {
+        const int gg = idx / (nst * PDP_NVAR_S), rem = idx - gg * (nst * PDP_NVAR_S);
+        const int l = rem / PDP_NVAR_S, e = rem - l * PDP_NVAR_S;
+        const int bb = (b0 + gg < B) ? b0 + gg : B - 1;
+        wbase[gg * PDP_FTS + l * PDP_FLD + e] = auxrec[((size_t)bb * H + tc + l) * PDP_NDENSE + pdp_slot_src[e]];
+      }
+    }""",
         }
 
 

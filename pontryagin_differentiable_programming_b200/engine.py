@@ -36,9 +36,11 @@ class OCSystem:
     """Compiled optimal-control system: rollout/costate, fused getAuxSys+lqrSolver, dense aux eval."""
 
     def __init__(self, state, control, auxvar, dyn, path_cost, final_cost, chunk=17, warps_per_block=4, min_blocks=3,
-                 fwd_warps_per_block=4, fwd_min_blocks=3, keep_fg=True, fast_rcp=True, early_solve=True, verbose=False):
+                 fwd_warps_per_block=1, fwd_min_blocks=8, keep_fg=True, fast_rcp=True, early_solve=True, verbose=False,
+                 fwd_pack=0, fwd_chunk=0):
         self.src = codegen.OCModuleSource(state, control, auxvar, dyn, path_cost, final_cost, chunk, warps_per_block,
-                                          min_blocks, fwd_warps_per_block, fwd_min_blocks, keep_fg, fast_rcp, early_solve)
+                                          min_blocks, fwd_warps_per_block, fwd_min_blocks, keep_fg, fast_rcp, early_solve,
+                                          fwd_pack, fwd_chunk)
         self.n, self.m, self.r = self.src.n, self.src.m, self.src.r
         self.module_path = build.compile_module(self.src.source(), self.src.key(), verbose=verbose)
         self._handle = None

@@ -167,7 +167,8 @@ K_AUX_LQR = r'''
 //         Y     <- Q(:,0:n) + Q(:,n:n+m) K
 //       and the gains (K_t|k_t) are spilled to HBM.
 //   3b  pdp_k_aux_lqr_fwd: forward pass  U_t = K_t X_t + k_t,  X_{t+1} = F_t X_t + G_t U_t + E_t
-//       -> dX/dtheta, dU/dtheta (and/or the fused IRL loss / chain rule), lane n+c owns column c.
+//       -> dX/dtheta, dU/dtheta (and/or the fused IRL loss / chain rule); PDP_FG trajectories per warp,
+//       lane g*r+c owns column c of trajectory g.
 //   The auxiliary matrices are evaluated in chunks of PDP_CH steps with lanes = time steps; they never
 //   exist in HBM.  Two kernels (not one) so that each gets its own register allocation / occupancy.
 // =====================================================================================================
@@ -227,83 +228,110 @@ pdp_k_aux_lqr_fwd(int B, int H, const double* __restrict__ X, const double* __re
                   const double* __restrict__ Xref, const double* __restrict__ Uref, double* __restrict__ loss_dp,
                   const double* __restrict__ auxrec, int* __restrict__ status)
 {
+  // One warp carries PDP_FG trajectories: lane g*r + c owns column c of trajectory b0+g, so one shared-memory
+  // wavefront (K entry, Jacobian slot) feeds FG*r lanes instead of r.  Each trajectory has its own region
+  // [CHF][FLD] slots | K | theta | [CHF][n+m] residuals, PDP_FTS doubles apart (= 2 mod 16: distinct bank groups).
   extern __shared__ __align__(16) double pdp_smem[];
   const int lane = threadIdx.x & 31;
-  const int b = blockIdx.x * PDP_WPBF + (threadIdx.x >> 5);
-  if (b >= B) return;
-  double* auxc = pdp_smem + (size_t)(threadIdx.x >> 5) * PDP_FWARP_DOUBLES;  // [CH][FLD] dynamics-Jacobian slots
-  double* KS = auxc + PDP_FOFF_KS;                                           // K (m x n)
-  double* TH = auxc + PDP_FOFF_TH;                                           // theta
-  double* DLC = auxc + PDP_FOFF_DL;                                          // [CH][n+m] (x - xref | u - uref)
-  const double* Xb = X + (size_t)b * (H + 1) * PDP_N;
-  const double* Ub = U + (size_t)b * H * PDP_M;
-  (void)Xb; (void)Ub;
-  if (theta != nullptr) for (int i = lane; i < PDP_NTH; i += 32) TH[i] = theta[(size_t)b * theta_stride + i];
-  const int col = (lane >= PDP_N && lane < PDP_N + PDP_R) ? lane - PDP_N : -1;
-  const int fslot = lane < PDP_N + PDP_R ? lane : -1;
+  const int b0 = (blockIdx.x * PDP_WPBF + (threadIdx.x >> 5)) * PDP_FG;
+  if (b0 >= B) return;
+  double* wbase = pdp_smem + (size_t)(threadIdx.x >> 5) * PDP_FWARP_DOUBLES;
+  const int grp = lane / PDP_R;
+  const bool owner = grp < PDP_FG;
+  const int g = owner ? grp : 0;
+  const int col = owner ? lane - grp * PDP_R : -1;
+  const bool live = owner && (b0 + g < B);
+  const int bg = (b0 + g < B) ? b0 + g : B - 1;                 // idle / tail lanes shadow a valid trajectory
+  double* reg = wbase + g * PDP_FTS;
+  const double* KS = reg + PDP_FOFF_KS;
+  // evaluation mapping: lane ge*CHF + se evaluates step tc+se of trajectory b0+ge
+  const int ge_ = lane / PDP_CHF;
+  const bool evl = ge_ < PDP_FG;
+  const int ge = evl ? ge_ : 0;
+  const int se = lane - ge_ * PDP_CHF;
+  const int be = (b0 + ge < B) ? b0 + ge : B - 1;
+  double* ereg = wbase + ge * PDP_FTS;
+  (void)ereg; (void)be; (void)se;
+#if PDP_NTH > 0
+  if (theta != nullptr)
+    for (int i = lane; i < PDP_FG * PDP_NTH; i += 32) {
+      const int tg = i / PDP_NTH, ti = i - tg * PDP_NTH;
+      const int tb = (b0 + tg < B) ? b0 + tg : B - 1;
+      wbase[tg * PDP_FTS + PDP_FOFF_TH + ti] = theta[(size_t)tb * theta_stride + ti];
+    }
+#endif
   @@XDECL@@
   {
 @@XINIT@@
   }
-  double* dXb = dX ? dX + (size_t)b * (H + 1) * PDP_N * PDP_R : nullptr;
-  double* dUb = dU ? dU + (size_t)b * H * PDP_M * PDP_R : nullptr;
+  double* dXb = dX ? dX + (size_t)bg * (H + 1) * PDP_N * PDP_R : nullptr;
+  double* dUb = dU ? dU + (size_t)bg * H * PDP_M * PDP_R : nullptr;
   __syncwarp();
-  if (dXb != nullptr && col >= 0) {
+  if (dXb != nullptr && live) {
     double* o = dXb + col;
 @@X0STORE@@
   }
   const bool fused = (loss_dp != nullptr) && (Xref != nullptr);
-  const double* Xr = fused ? Xref + (size_t)b * (H + 1) * PDP_N : nullptr;
-  const double* Ur = (fused && Uref != nullptr) ? Uref + (size_t)b * H * PDP_M : nullptr;
   double dpacc = 0.0, lossacc = 0.0;
-  // software prefetch of the gain record of the next step
+  double lacc[PDP_FG];
+  #pragma unroll
+  for (int gg = 0; gg < PDP_FG; ++gg) lacc[gg] = 0.0;
+  // software prefetch of the gain records (k column of this lane, K spread over the warp) one step ahead
   @@GNDECL@@
-  if (fslot >= 0) {
-    const double* gp = gains + ((size_t)b * H) * PDP_GREC + fslot * PDP_M;
+@@KQ_SETUP@@
+  {
+    const int t = -1;
+    (void)t;
 @@GNLOAD@@
   }
   #pragma unroll 1
-  for (int tc = 0; tc < H; tc += PDP_CH) {
+  for (int tc = 0; tc < H; tc += PDP_CHF) {
+    const int nst = (tc + PDP_CHF < H ? PDP_CHF : H - tc);
+    (void)nst;
+@@EVAL_DYN_COOP@@
     {
-      const int te = tc + lane;
-      if (lane < PDP_CH && te < H) {
+      const int te = tc + se;
+      if (evl && te < H) {
+        double* eo = ereg + se * PDP_FLD;
+        const double* the = ereg + PDP_FOFF_TH;
+        (void)the; (void)eo;
 @@EVAL_DYN@@
         if (fused) {
-          // loss / chain rule of the IRL scripts (reference Examples/IRL/quadrotor/uav_PDP.py:67-75)
+          // loss / chain rule of the IRL scripts (reference Examples/IRL/quadrotor/uav_PDP.py:67-75), per evaluation lane
+          const double* xe = X + ((size_t)be * (H + 1) + te) * PDP_N;
+          const double* xr = Xref + ((size_t)be * (H + 1) + te) * PDP_N;
           #pragma unroll
           for (int i = 0; i < PDP_N; ++i) {
-            const double d = Xb[(size_t)te * PDP_N + i] - Xr[(size_t)te * PDP_N + i];
-            DLC[lane * PDP_NM + i] = d; lossacc = fma(d, d, lossacc);
+            const double d = xe[i] - xr[i];
+            ereg[PDP_FOFF_DL + se * PDP_N + i] = d; lossacc = fma(d, d, lossacc);
           }
           #pragma unroll
           for (int i = 0; i < PDP_M; ++i) {
-            const double d = Ur ? Ub[(size_t)te * PDP_M + i] - Ur[(size_t)te * PDP_M + i] : 0.0;
-            DLC[lane * PDP_NM + PDP_N + i] = d; lossacc = fma(d, d, lossacc);
+            const double d = Uref ? U[((size_t)be * H + te) * PDP_M + i] - Uref[((size_t)be * H + te) * PDP_M + i] : 0.0;
+            ereg[PDP_FOFF_DU + se * PDP_M + i] = d; lossacc = fma(d, d, lossacc);
           }
         }
       }
     }
     __syncwarp();
-    const int tend = tc + PDP_CH < H ? tc + PDP_CH : H;
+    const int tend = tc + PDP_CHF < H ? tc + PDP_CHF : H;
     #pragma unroll 1
     for (int t = tc; t < tend; ++t) {
-      const double* ar = auxc + (t - tc) * PDP_FLD;
+      const double* ar = reg + (t - tc) * PDP_FLD;
 @@GCUR@@
-      if (fslot >= 0 && t + 1 < H) {
-        const double* gp = gains + ((size_t)b * H + t + 1) * PDP_GREC + fslot * PDP_M;
-@@GNLOAD@@
-      }
-      if (lane < PDP_N) {
 @@KS_STORE@@
+      if (t + 1 < H) {
+@@GNLOAD@@
       }
       __syncwarp();
 @@FORWARD_STEP@@
       if (fused) {
-        const double* dl = DLC + (t - tc) * PDP_NM;
+        const double* dlx = reg + PDP_FOFF_DL + (t - tc) * PDP_N;
+        const double* dlu = reg + PDP_FOFF_DU + (t - tc) * PDP_M;
 @@DPACC@@
       }
-      if (col >= 0) {
-        // each lane stores its column straight from registers (72-byte runs; L2 merges the partial sectors)
+      if (live) {
+        // each lane stores its column straight from registers (8r-byte runs; L2 merges the partial sectors)
         if (dXb != nullptr) {
           double* o = dXb + (size_t)(t + 1) * (PDP_N * PDP_R) + col;
 @@XSTORE@@
@@ -320,25 +348,28 @@ pdp_k_aux_lqr_fwd(int B, int H, const double* __restrict__ X, const double* __re
   {
     double chk = 0.0;
 @@XCHK@@
-    if (status && col >= 0 && !isfinite(chk)) atomicOr(&status[b], 1);
+    if (status && live && !isfinite(chk)) atomicOr(&status[bg], 1);
   }
   if (fused) {
-    // terminal term of the chain rule and of the loss
+    // terminal term of the chain rule and of the loss; the residual sums were accumulated lane-wise per trajectory
     #pragma unroll
-    for (int i = 0; i < PDP_N; ++i) {
-      const double d = Xb[(size_t)H * PDP_N + i] - Xr[(size_t)H * PDP_N + i];
-      if (lane == 0) lossacc = fma(d, d, lossacc);
-      DLC[i] = d;
+    for (int gg = 0; gg < PDP_FG; ++gg) {
+      if (evl && ge == gg) lacc[gg] += lossacc;
+      #pragma unroll
+      for (int o = 16; o > 0; o >>= 1) lacc[gg] += __shfl_xor_sync(0xffffffffu, lacc[gg], o);
     }
-    __syncwarp();
-    {
-      const double* dl = DLC;
+    if (owner) {
+      const double* xh = X + ((size_t)bg * (H + 1) + H) * PDP_N;
+      const double* xrh = Xref + ((size_t)bg * (H + 1) + H) * PDP_N;
+      double lt = lacc[0];
+      #pragma unroll
+      for (int gg = 1; gg < PDP_FG; ++gg) if (g == gg) lt = lacc[gg];
 @@DPTERM@@
+      if (live) {
+        if (col == 0) loss_dp[(size_t)bg * (PDP_R + 1)] = lt;
+        loss_dp[(size_t)bg * (PDP_R + 1) + 1 + col] = dpacc;
+      }
     }
-    #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) lossacc += __shfl_xor_sync(0xffffffffu, lossacc, o);
-    if (lane == 0) loss_dp[(size_t)b * (PDP_R + 1)] = lossacc;
-    if (col >= 0) loss_dp[(size_t)b * (PDP_R + 1) + 1 + col] = dpacc;
   }
 }
 '''
@@ -396,7 +427,7 @@ extern "C" int pdpmod_aux_lqr(int B, int H, const double* X, const double* U, co
     pdp_k_aux_lqr_bwd<<<(B + PDP_WPB - 1) / PDP_WPB, PDP_WPB * 32, smem_b, st>>>(B, H, X, U, Lam, theta, theta_stride, gains,
                                                                                auxrec, termrec, status);
   if (phases & 2)
-    pdp_k_aux_lqr_fwd<<<(B + PDP_WPBF - 1) / PDP_WPBF, PDP_WPBF * 32, smem_f, st>>>(B, H, X, U, theta, theta_stride, X0a,
+    pdp_k_aux_lqr_fwd<<<(B + PDP_WPBF * PDP_FG - 1) / (PDP_WPBF * PDP_FG), PDP_WPBF * 32, smem_f, st>>>(B, H, X, U, theta, theta_stride, X0a,
                                                                                   x0a_stride, dX, dU, gains, Xref, Uref,
                                                                                   loss_dp, auxrec, status);
   return (int)cudaGetLastError();

@@ -11,7 +11,7 @@ import bench
 from pontryagin_differentiable_programming_b200 import systems
 dev = torch.device('cuda:0')
 s = systems.quadrotor_irl(0.1)
-x0, th, U, Xr, Ur = [torch.as_tensor(np.ascontiguousarray(a), device=dev) for a in bench.synth_quadrotor(9, 19, seed=4)]
+x0, th, U, Xr, Ur = [torch.as_tensor(np.ascontiguousarray(a), device=dev) for a in bench.synth_quadrotor(10, 19, seed=4)]
 r = s.sweep(x0, th, U, Xref=Xr, Uref=Ur)
 torch.cuda.synchronize()
 print('sweep ok', float(r['loss_dp'][0, 0]))

@@ -15,12 +15,13 @@ sys.path.insert(0, ROOT)
 # (chunk, bwd warps/block, bwd min blocks, fwd warps/block, fwd min blocks)
 # (chunk, bwd warps/block, bwd min blocks, fwd warps/block, fwd min blocks, keep [F|G] slots in registers A->C)
 # (chunk, bwd warps/block, bwd min blocks, fwd warps/block, fwd min blocks, keep_fg, fast_rcp, early_solve)
-VARIANTS = [(16, 4, 3, 4, 4, True, True, True), (17, 4, 3, 4, 4, True, True, True), (25, 4, 2, 4, 4, True, True, True),
-            (25, 4, 3, 4, 4, True, True, True), (17, 4, 3, 4, 3, True, True, True), (10, 4, 3, 4, 4, True, True, True),
-            (17, 2, 6, 2, 8, True, True, True)]
+# ... + (fwd_pack = trajectories per warp of the forward kernel, fwd_chunk)
+VARIANTS = [(17, 4, 3, 1, 8, True, True, True, 3, 10), (17, 4, 3, 1, 6, True, True, True, 3, 10),
+            (17, 4, 3, 2, 4, True, True, True, 3, 10), (17, 4, 3, 4, 2, True, True, True, 3, 10),
+            (17, 4, 3, 1, 12, True, True, True, 3, 10), (17, 4, 3, 4, 3, True, True, True, 1, 17)]
 
 
-def make(ch, wpb, mb, wpbf=4, mbf=1, kf=True, frcp=False, early=False, verbose=False):
+def make(ch, wpb, mb, wpbf=4, mbf=1, kf=True, frcp=False, early=False, fpack=0, fchunk=0, verbose=False):
     from JinEnv import JinEnv
     from pontryagin_differentiable_programming_b200 import engine
     from pontryagin_differentiable_programming_b200.symbolic import vertcat
@@ -29,7 +30,8 @@ def make(ch, wpb, mb, wpbf=4, mbf=1, kf=True, frcp=False, early=False, verbose=F
     env.initCost(wthrust=0.1)
     return engine.OCSystem(env.X, env.U, vertcat(env.dyn_auxvar, env.cost_auxvar), env.X + 0.1 * env.f, env.path_cost,
                            env.final_cost, chunk=ch, warps_per_block=wpb, min_blocks=mb, fwd_warps_per_block=wpbf,
-                           fwd_min_blocks=mbf, keep_fg=kf, fast_rcp=frcp, early_solve=early, verbose=verbose)
+                           fwd_min_blocks=mbf, keep_fg=kf, fast_rcp=frcp, early_solve=early, verbose=verbose,
+                           fwd_pack=fpack, fwd_chunk=fchunk)
 
 
 def main():
@@ -68,7 +70,7 @@ def main():
                 e1.record()
                 torch.cuda.synchronize()
                 ms[phase] = e0.elapsed_time(e1) / 10
-            rows.append({"chunk": v[0], "wpb": v[1], "minb": v[2], "wpbf": v[3], "minbf": v[4], "keep_fg": v[5], "fast_rcp": v[6], "early_solve": v[7], "bwd_ms": ms["backward"],
+            rows.append({"chunk": v[0], "wpb": v[1], "minb": v[2], "wpbf": v[3], "minbf": v[4], "keep_fg": v[5], "fast_rcp": v[6], "early_solve": v[7], "fwd_pack": v[8], "fwd_chunk": v[9], "bwd_ms": ms["backward"],
                          "fwd_ms": ms["forward"], "sweeps_per_s": B / (ms["backward"] + ms["forward"]) * 1e3})
             print(json.dumps(rows[-1]), flush=True)
             del out
