@@ -194,9 +194,10 @@ class OCModuleSource:
     def __init__(self, state: SX, control: SX, auxvar: SX, dyn: SX, path_cost: SX, final_cost: SX,
                  chunk: int = 8, warps_per_block: int = 4, min_blocks: int = 1, fwd_warps_per_block: int = 4,
                  fwd_min_blocks: int = 1, keep_fg: bool = True, fast_rcp: bool = False, early_solve: bool = False,
-                 fwd_pack: int = 0, fwd_chunk: int = 0):
+                 fwd_pack: int = 0, fwd_chunk: int = 0, bwd_pack: int = 1):
         self.keep_fg = bool(keep_fg)
         self.fwd_pack, self.fwd_chunk = int(fwd_pack), int(fwd_chunk)
+        self.bwd_pack = int(bwd_pack)
         self.fast_rcp, self.early_solve = bool(fast_rcp), bool(early_solve)
         self.min_blocks = int(min_blocks)
         self.wpbf, self.min_blocks_f = int(fwd_warps_per_block), int(fwd_min_blocks)
@@ -229,6 +230,10 @@ class OCModuleSource:
         self.ddhxe = S.jacobian(self.dhx, self.th)
         self._customise()
         self.ns = self.n + self.m + self.r
+        if self.bwd_pack == 2 and not (self.n <= 16 and self.m + self.r <= 16):
+            self.bwd_pack = 1          # the two-rows-per-lane layout needs n <= 16 and m + r <= 16
+        if self.bwd_pack == 2:
+            self.chunk = min(self.chunk, 16)
         self._layout()
 
     def _customise(self):
@@ -281,11 +286,17 @@ class OCModuleSource:
         """Extra shared-memory wavefronts of the per-lane indexed Hamiltonian loads: a 64-bit warp load is served
         per half-warp, one wavefront per distinct word that shares a 16-way bank-pair with another distinct word."""
         ns, nm = self.ns, self.n + self.m
+        if getattr(self, "bwd_pack", 1) == 2:
+            # two-trajectory kernel: one load serves rows 0..n-1 (slot 0) or rows n..ns-1 (slot 1) of a half-warp;
+            # idle team lanes repeat the group's first row
+            groups = [list(range(self.n)), list(range(self.n, ns))]
+        else:
+            groups = [list(range(16)), list(range(16, 32))]
         cost = 0
         for l in range(nm):
-            for half in (0, 1):
+            for rows in groups:
                 banks: Dict[int, set] = {}
-                for j in range(16 * half, 16 * half + 16):
+                for j in rows:
                     a = phys[self.H_idx[j][l]] if j < ns else phys[self.zero_slot]
                     banks.setdefault(a % 16, set()).add(a)
                 cost += max(len(v) for v in banks.values()) - 1
@@ -490,6 +501,160 @@ class OCModuleSource:
             L.append(ind + "y%d = q%d;" % (l, l))
         return "\n".join(L)
 
+    def _ldlt_lines(self, L, ind, late_lines):
+        """Uniform LDL^T of Quu (read from QUU) with the reciprocal pivots r_j; ``late_lines`` (independent FMAs)
+        are sliced in after every pivot so the scheduler can overlap them with the serial chain."""
+        m = self.m
+        for i in range(m):
+            for j in range(i + 1):
+                L.append(ind + "double a%d%d = QUU[%d];" % (i, j, i * m + j))
+        for j in range(m):
+            expr = "a%d%d" % (j, j)
+            for k in range(j):
+                expr = "fma(-l%d%d * l%d%d, d%d, %s)" % (j, k, j, k, k, expr)
+            L.append(ind + "const double d%d = %s;" % (j, expr))
+            L.append(ind + "bad |= !(d%d > 0.0);" % j)
+            if getattr(self, "fast_rcp", False):
+                L.append(ind + "double r%d; asm(\"rcp.approx.ftz.f64 %%0, %%1;\" : \"=d\"(r%d) : \"d\"(d%d));" % (j, j, j))
+                L.append(ind + "r%d = fma(r%d, fma(-d%d, r%d, 1.0), r%d);" % (j, j, j, j, j))
+                L.append(ind + "r%d = fma(r%d, fma(-d%d, r%d, 1.0), r%d);" % (j, j, j, j, j))
+            else:
+                L.append(ind + "const double r%d = 1.0 / d%d;" % (j, j))
+            for i in range(j + 1, m):
+                expr = "a%d%d" % (i, j)
+                for k in range(j):
+                    expr = "fma(-l%d%d * l%d%d, d%d, %s)" % (i, k, j, k, k, expr)
+                L.append(ind + "const double l%d%d = (%s) * r%d;" % (i, j, expr, j))
+            if late_lines:
+                take = (len(late_lines) + (m - j) - 1) // (m - j)
+                L.extend(late_lines[:take])
+                del late_lines[:take]
+
+    def _solve_lines(self, L, ind, rhs, tag):
+        """v = -(L D L^T)^{-1} rhs for the right-hand side names ``rhs``; results in v<tag>_i."""
+        m = self.m
+        for i in range(m):
+            expr = "-%s" % rhs[i]
+            for k in range(i):
+                expr = "fma(-l%d%d, w%s_%d, %s)" % (i, k, tag, k, expr)
+            L.append(ind + "const double w%s_%d = %s;" % (tag, i, expr))
+        for i in reversed(range(m)):
+            expr = "w%s_%d * r%d" % (tag, i, i)
+            for k in range(i + 1, m):
+                expr = "fma(-l%d%d, v%s_%d, %s)" % (k, i, tag, k, expr)
+            L.append(ind + "const double v%s_%d = %s;" % (tag, i, expr))
+
+    def _hidx8(self) -> bool:
+        """Two-trajectory kernel: pack four 8-bit Hamiltonian slot indices per register (needs < 256 slots)."""
+        return self.nvar <= 255
+
+    def _backward_step2(self) -> str:
+        """Riccati step of the two-trajectories-per-warp kernel: team lane tl owns stack rows tl (slot 0: P) and
+        n + tl (slot 1: control rows, then the columns of W).  Same phases A-E as :meth:`_backward_step`."""
+        n, m, r, ns = self.n, self.m, self.r, self.ns
+        nm = n + m
+        L: List[str] = []
+        ind = "      "
+        L.append(ind + "// A: Z(i,:) = P(i,:) * [F|G|E]  -- structural non-zeros only; each half-warp reads its own trajectory's slots")
+        L.append(ind + "double " + ", ".join("z%d" % j for j in range(ns)) + ";")
+        needed = {e[1] for row in self.S_ent for e in row if e[0] == "v"}
+        load = _SlotLoader(L, "ar", needed, ind, "sa")
+        acc = _Acc("z", ns, L, ind)
+        for k in range(n):
+            for j in range(ns):
+                acc.add(j, "y0_%d" % k, self.S_ent[k][j], load)
+        acc.finish()
+        L.append(ind + "// B: transpose through shared memory: slot 0 picks up column tl of Z, slot 1 column n + tl (+ its W column)")
+        L.append(ind + "if (tl < %d) {" % n)
+        for j in range(ns):
+            L.append(ind + "  ZT[%d + tl] = z%d;" % (j * self.ldz, j))
+        L.append(ind + "}")
+        L.append(ind + "__syncwarp();")
+        L.append(ind + "double " + ", ".join("c0_%d, c1_%d" % (k, k) for k in range(n)) + ";")
+        L.append(ind + "{ const double* zr = ZT + r0 * %d;" % self.ldz)
+        for k in range(n):
+            L.append(ind + "  c0_%d = zr[%d];" % (k, k))
+        L.append(ind + "}")
+        L.append(ind + "{ const double* zr = ZT + r1 * %d;" % self.ldz)
+        for k in range(n):
+            L.append(ind + "  c1_%d = zr[%d];" % (k, k))
+        L.append(ind + "}")
+        L.append(ind + "if (wrow) {")
+        for k in range(n):
+            L.append(ind + "  c1_%d += y1_%d;" % (k, k))
+        L.append(ind + "}")
+        L.append(ind + "// C: Q(j,:) = Hstack(j,:) + Z(:,j)^T [F|G] for both rows (one operand load, two FMAs)")
+        L.append(ind + "double " + ", ".join("q0_%d, q1_%d" % (l, l) for l in range(nm)) + ";")
+        for l in range(nm):
+            if self._hidx8():
+                w, sh = l // 2, 16 * (l % 2)
+                L.append(ind + "q0_%d = ar[(ho%d >> %d) & 0xffu]; q1_%d = ar[(ho%d >> %d) & 0xffu];" % (l, w, sh, l, w, sh + 8))
+            else:
+                L.append(ind + "q0_%d = ar[ho%d & 0xffffu]; q1_%d = ar[ho%d >> 16];" % (l, l, l, l))
+        if not getattr(self, "keep_fg", True):
+            needed = {self.S_ent[k][l][1] for k in range(n) for l in range(nm) if self.S_ent[k][l][0] == "v"}
+            load = _SlotLoader(L, "ar", needed, ind, "sc")
+        acc0, acc1 = _Acc("q0_", nm, L, ind), _Acc("q1_", nm, L, ind)
+        acc0.touched = [True] * nm
+        acc1.touched = [True] * nm
+        early = getattr(self, "early_solve", False)
+        first_cols = range(n, nm) if early else range(nm)
+        for k in range(n):
+            for l in first_cols:
+                acc0.add(l, "c0_%d" % k, self.S_ent[k][l], load)
+                acc1.add(l, "c1_%d" % k, self.S_ent[k][l], load)
+        late_lines: List[str] = []
+        if early:
+            late0, late1 = _Acc("q0_", nm, late_lines, ind), _Acc("q1_", nm, late_lines, ind)
+            late0.touched = [True] * nm
+            late1.touched = [True] * nm
+            lload = load       # operand loads are appended to L here, i.e. ahead of the pivots the FMAs are sliced between
+            for k in range(n):
+                for l in range(n):
+                    late0.add(l, "c0_%d" % k, self.S_ent[k][l], lload)
+                    late1.add(l, "c1_%d" % k, self.S_ent[k][l], lload)
+        L.append(ind + "// D: Quu = slot-1 rows of team lanes < m; every lane factors it (LDL^T, uniform per half) and solves for its two columns")
+        L.append(ind + "if (tl < %d) {" % m)
+        for a in range(m):
+            L.append(ind + "  QUU[tl * %d + %d] = q1_%d;" % (m, a, n + a))
+        L.append(ind + "}")
+        L.append(ind + "__syncwarp();")
+        self._ldlt_lines(L, ind, late_lines)
+        self._solve_lines(L, ind, ["q0_%d" % (n + i) for i in range(m)], "0")
+        self._solve_lines(L, ind, ["q1_%d" % (n + i) for i in range(m)], "1")
+        L.append(ind + "// E: spill (K|k) for the forward pass, broadcast K, rank-m update of both rows")
+        L.append(ind + "if (tl < %d) {" % n)
+        for a in range(m):
+            L.append(ind + "  KS[%d + tl] = v0_%d;" % (a * self.ldk, a))
+        L.append(ind + "}")
+        L.append(ind + "if (live) {")
+        L.append(ind + "  double* gp = gains + ((size_t)b * H + t) * %d;" % ((n + r) * m))
+        L.append(ind + "  if (gslot0 >= 0) {")
+        L.append(self._vec_store("(gp + gslot0 * %d)" % m, ["v0_%d" % a for a in range(m)], ind + "    "))
+        L.append(ind + "  }")
+        L.append(ind + "  if (gslot1 >= 0) {")
+        L.append(self._vec_store("(gp + gslot1 * %d)" % m, ["v1_%d" % a for a in range(m)], ind + "    "))
+        L.append(ind + "  }")
+        L.append(ind + "}")
+        L.append(ind + "__syncwarp();")
+        for a in range(m):
+            if self.ldk % 2 == 0:
+                for l in range(0, n - 1, 2):
+                    L.append(ind + "{ const double2 kk = *reinterpret_cast<const double2*>(KS + %d); "
+                             "q0_%d = fma(q0_%d, kk.x, q0_%d); q1_%d = fma(q1_%d, kk.x, q1_%d); "
+                             "q0_%d = fma(q0_%d, kk.y, q0_%d); q1_%d = fma(q1_%d, kk.y, q1_%d); }"
+                             % (a * self.ldk + l, l, n + a, l, l, n + a, l, l + 1, n + a, l + 1, l + 1, n + a, l + 1))
+                if n % 2 == 1:
+                    L.append(ind + "{ const double kk = KS[%d]; q0_%d = fma(q0_%d, kk, q0_%d); q1_%d = fma(q1_%d, kk, q1_%d); }"
+                             % (a * self.ldk + n - 1, n - 1, n + a, n - 1, n - 1, n + a, n - 1))
+            else:
+                for l in range(n):
+                    L.append(ind + "{ const double kk = KS[%d]; q0_%d = fma(q0_%d, kk, q0_%d); q1_%d = fma(q1_%d, kk, q1_%d); }"
+                             % (a * self.ldk + l, l, n + a, l, l, n + a, l))
+        for l in range(n):
+            L.append(ind + "y0_%d = q0_%d; y1_%d = q1_%d;" % (l, l, l, l))
+        return "\n".join(L)
+
     def _vec_store(self, ptr, names, ind):
         m = len(names)
         out = []
@@ -607,6 +772,10 @@ class OCModuleSource:
         off_quu = off_ks + ks_size
         off_th = off_quu + _even(m * m)
         warp_doubles = _even(off_th + max(self.nth, 1))
+        bp = getattr(self, "bwd_pack", 1)
+        half_stride = _pad_ld(warp_doubles)       # two-trajectory kernel: per-trajectory regions = 2 (mod 16) doubles apart
+        if bp == 2:
+            warp_doubles = 2 * half_stride
         # forward kernel, per trajectory region: [CHF][FLD] dynamics slots | K [l][a] | TH | residuals [CHF][n+m]
         fg, chf = self._fwd_shape()
         fld = _pad_ld(self.nvar_s)
@@ -625,22 +794,50 @@ class OCModuleSource:
             "FWARP_DOUBLES": fwarp_doubles, "WPBF": getattr(self, "wpbf", 4), "MINBF": getattr(self, "min_blocks_f", 1),
             "WARP_DOUBLES": warp_doubles, "NTH": self.nth, "MINB": getattr(self, "min_blocks", 1), "GREC": (n + r) * m,
             "NDENSE": n * n + n * m + n * r + n * n + n * m + n * r + m * n + m * m + m * r,
+            "BP": bp, "HS": half_stride,
         }
         header = ["// GENERATED by pontryagin_differentiable_programming_b200/codegen.py -- do not edit",
                   "#include <cuda_runtime.h>", "#include <math.h>", "#include <stdint.h>"]
         header += ["#define PDP_%s %d" % kv for kv in defs.items()]
         tables = []
         hid = []
-        for l in range(nm):
-            hid += [self.H_idx[j][l] if j < ns else self.zero_slot for j in range(WARP)]
-        tables.append("__device__ const unsigned short pdp_hidx[%d] = {%s};" % (len(hid), ", ".join(map(str, hid))))
-        tabload = "\n".join("  const int ho%d = pdp_hidx[%d + lane];" % (l, l * WARP) for l in range(nm))
-        ydecl = "double " + ", ".join("y%d = 0.0" % k for k in range(n)) + ";"
-        # terminal init: lane i<n takes row i of hxx, lane n+m+c takes column c of hxe
-        term_init = []
-        for k in range(n):
-            term_init.append("    y%d = (lane < %d) ? TB[lane * %d + %d] : ((lane >= %d && lane < %d) ? TB[%d + %d * %d + (lane - %d)] : 0.0);"
-                             % (k, n, n, k, nm, ns, n * n, k, r, nm))
+        if bp == 2:
+            # packed per-lane slot indices: low half = row of slot 0, high half = row of slot 1 (idle lanes repeat a row)
+            def pair(l, lane):
+                tl = lane & 15
+                ra, rb = (tl if tl < n else 0), n + (tl if tl < m + r else 0)
+                return self.H_idx[ra][l], self.H_idx[rb][l]
+            if self._hidx8():
+                nw = (nm + 1) // 2
+                for w in range(nw):
+                    for lane in range(WARP):
+                        a0, a1 = pair(2 * w, lane)
+                        b0, b1 = pair(2 * w + 1, lane) if 2 * w + 1 < nm else (0, 0)
+                        hid.append(a0 | (a1 << 8) | (b0 << 16) | (b1 << 24))
+            else:
+                nw = nm
+                for l in range(nm):
+                    for lane in range(WARP):
+                        a0, a1 = pair(l, lane)
+                        hid.append(a0 | (a1 << 16))
+            tables.append("__device__ const unsigned int pdp_hidx[%d] = {%s};" % (len(hid), ", ".join(map(str, hid))))
+            tabload = "\n".join("  const unsigned int ho%d = pdp_hidx[%d + lane];" % (w, w * WARP) for w in range(nw))
+            ydecl = "double " + ", ".join("y0_%d = 0.0, y1_%d = 0.0" % (k, k) for k in range(n)) + ";"
+            term_init = []
+            for k in range(n):
+                term_init.append("    if (tl < %d) y0_%d = TB[tl * %d + %d];" % (n, k, n, k))
+                term_init.append("    if (wrow) y1_%d = TB[%d + %d * %d + (tl - %d)];" % (k, n * n, k, r, m))
+        else:
+            for l in range(nm):
+                hid += [self.H_idx[j][l] if j < ns else self.zero_slot for j in range(WARP)]
+            tables.append("__device__ const unsigned short pdp_hidx[%d] = {%s};" % (len(hid), ", ".join(map(str, hid))))
+            tabload = "\n".join("  const int ho%d = pdp_hidx[%d + lane];" % (l, l * WARP) for l in range(nm))
+            ydecl = "double " + ", ".join("y%d = 0.0" % k for k in range(n)) + ";"
+            # terminal init: lane i<n takes row i of hxx, lane n+m+c takes column c of hxe
+            term_init = []
+            for k in range(n):
+                term_init.append("    y%d = (lane < %d) ? TB[lane * %d + %d] : ((lane >= %d && lane < %d) ? TB[%d + %d * %d + (lane - %d)] : 0.0);"
+                                 % (k, n, n, k, nm, ns, n * n, k, r, nm))
         xdecl = "double " + ", ".join("x%d" % k for k in range(n)) + ";"
         xinit = "\n".join("    x%d = (X0a != nullptr && col >= 0) ? X0a[(size_t)(x0a_stride ? bg : 0) * %d + %d * %d + col] : 0.0;"
                           % (k, n * r, k, r) for k in range(n))
@@ -654,7 +851,7 @@ class OCModuleSource:
 
         rep = {
             "@@TABLOAD@@": tabload, "@@YDECL@@": ydecl,
-            "@@TERM_INIT@@": "\n".join(term_init), "@@BACKWARD_STEP@@": self._backward_step(),
+            "@@TERM_INIT@@": "\n".join(term_init), "@@BACKWARD_STEP@@": self._backward_step2() if bp == 2 else self._backward_step(),
             "@@XDECL@@": xdecl, "@@XINIT@@": xinit, "@@GNDECL@@": gndecl, "@@GNLOAD@@": gnload, "@@GCUR@@": gcur, "@@KQ_SETUP@@": kq_setup,
             "@@KS_STORE@@": ks_store, "@@FORWARD_STEP@@": self._forward_step(), "@@XSTORE@@": xstore, "@@USTORE@@": ustore,
             "@@XCOPY@@": xcopy, "@@X0STORE@@": x0store,
@@ -678,16 +875,18 @@ class OCModuleSource:
         return []
 
     def _kernel_text(self):
-        return _K_ROLLOUT_AUXEVAL + _K_AUX_LQR + _K_LAUNCH_COMMON + _K_LAUNCH_LQR
+        bwd = _K_AUX_LQR_BWD2 if getattr(self, "bwd_pack", 1) == 2 else _K_AUX_LQR_BWD
+        return _K_ROLLOUT_AUXEVAL + _K_AUX_LQR_HEAD + bwd + _K_AUX_LQR_FWD + _K_LAUNCH_COMMON + _K_LAUNCH_LQR
 
     def _eval_macros(self):
+        el = "tl" if getattr(self, "bwd_pack", 1) == 2 else "lane"       # evaluation lane = time step of the chunk
         return {
-            "@@EVAL_TERM@@": "  if (lane == 0) pdp_f_terminal(Xb + (size_t)H * PDP_N, TH, TB);",
+            "@@EVAL_TERM@@": "  if (%s == 0) pdp_f_terminal(Xb + (size_t)H * PDP_N, TH, TB);" % el,
             "@@EVAL_AUX_CHUNK@@": """    {
-      const int te = tc + lane;
-      if (lane < PDP_CH && te < H)
-        pdp_f_aux_slots(Xb + (size_t)te * PDP_N, Ub + (size_t)te * PDP_M, Lb + (size_t)te * PDP_N, TH, auxc + lane * PDP_AUXLD);
-    }""",
+      const int te = tc + %(el)s;
+      if (%(el)s < PDP_CH && te < H)
+        pdp_f_aux_slots(Xb + (size_t)te * PDP_N, Ub + (size_t)te * PDP_M, Lb + (size_t)te * PDP_N, TH, auxc + %(el)s * PDP_AUXLD);
+    }""" % {"el": el},
             "@@EVAL_DYN@@": "        pdp_f_dyn_slots(X + ((size_t)be * (H + 1) + te) * PDP_N, U + ((size_t)be * H + te) * PDP_M, the, eo);",
             "@@EVAL_DYN_COOP@@": "",
         }
@@ -883,5 +1082,6 @@ class LQRModuleSource(OCModuleSource):
 
 
 from .kernel_templates import (  # noqa: E402
-    K_AUX_LQR as _K_AUX_LQR, K_LAUNCH_COMMON as _K_LAUNCH_COMMON, K_LAUNCH_LQR as _K_LAUNCH_LQR,
+    K_AUX_LQR_BWD as _K_AUX_LQR_BWD, K_AUX_LQR_BWD2 as _K_AUX_LQR_BWD2, K_AUX_LQR_FWD as _K_AUX_LQR_FWD,
+    K_AUX_LQR_HEAD as _K_AUX_LQR_HEAD, K_AUX_LQR as _K_AUX_LQR, K_LAUNCH_COMMON as _K_LAUNCH_COMMON, K_LAUNCH_LQR as _K_LAUNCH_LQR,
     K_ROLLOUT_AUXEVAL as _K_ROLLOUT_AUXEVAL)

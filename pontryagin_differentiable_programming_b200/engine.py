@@ -35,12 +35,24 @@ def _chk(t, shape, name, device):
 class OCSystem:
     """Compiled optimal-control system: rollout/costate, fused getAuxSys+lqrSolver, dense aux eval."""
 
-    def __init__(self, state, control, auxvar, dyn, path_cost, final_cost, chunk=17, warps_per_block=4, min_blocks=3,
-                 fwd_warps_per_block=1, fwd_min_blocks=8, keep_fg=True, fast_rcp=True, early_solve=True, verbose=False,
-                 fwd_pack=0, fwd_chunk=0):
+    # measured defaults of the backward Riccati kernel (profiles/README.md): the two-trajectories-per-warp kernel
+    # wherever the stack fits two rows per team lane (n <= 16, m + r <= 16), else one trajectory per warp
+    BWD_DEFAULTS = {2: dict(chunk=8, warps_per_block=1, min_blocks=8, keep_fg=False),
+                    1: dict(chunk=17, warps_per_block=4, min_blocks=3, keep_fg=True)}
+
+    def __init__(self, state, control, auxvar, dyn, path_cost, final_cost, chunk=None, warps_per_block=None,
+                 min_blocks=None, fwd_warps_per_block=1, fwd_min_blocks=8, keep_fg=None, fast_rcp=True, early_solve=True,
+                 verbose=False, fwd_pack=0, fwd_chunk=0, bwd_pack=2):
+        fits = state.numel() <= 16 and control.numel() + auxvar.numel() <= 16
+        bwd_pack = 2 if (int(bwd_pack) == 2 and fits) else 1
+        d = self.BWD_DEFAULTS[bwd_pack]
+        chunk = d["chunk"] if chunk is None else chunk
+        warps_per_block = d["warps_per_block"] if warps_per_block is None else warps_per_block
+        min_blocks = d["min_blocks"] if min_blocks is None else min_blocks
+        keep_fg = d["keep_fg"] if keep_fg is None else keep_fg
         self.src = codegen.OCModuleSource(state, control, auxvar, dyn, path_cost, final_cost, chunk, warps_per_block,
                                           min_blocks, fwd_warps_per_block, fwd_min_blocks, keep_fg, fast_rcp, early_solve,
-                                          fwd_pack, fwd_chunk)
+                                          fwd_pack, fwd_chunk, bwd_pack)
         self.n, self.m, self.r = self.src.n, self.src.m, self.src.r
         self.module_path = build.compile_module(self.src.source(), self.src.key(), verbose=verbose)
         self._handle = None

@@ -374,6 +374,72 @@ pdp_k_aux_lqr_fwd(int B, int H, const double* __restrict__ X, const double* __re
 }
 '''
 
+# ---- two-trajectories-per-warp variant of the backward kernel (PDP_BP == 2) --------------------------------
+K_AUX_LQR_BWD2 = r"""
+// Backward Riccati sweep, TWO TRAJECTORIES PER WARP: half-warp `half` carries trajectory b0 + half, and team lane
+// tl = lane & 15 owns TWO rows of the stack Y = [P ; . ; W^T]:
+//     slot 0: row tl            (tl < n : row tl of P)
+//     slot 1: row n + tl        (tl < m : control row,  m <= tl < m + r : column tl - m of W)
+// so every broadcast operand (Jacobian slot, K entry) feeds two DFMAs per lane, and the two half-warps fetch their
+// own trajectory's operand in the same shared-memory wavefront (the per-trajectory regions are PDP_HS doubles
+// apart, PDP_HS = 2 mod 16: distinct bank pairs).  Same algebra, same gain records as the one-trajectory kernel.
+extern "C" __global__ void __launch_bounds__(PDP_WPB * 32, PDP_MINB)
+pdp_k_aux_lqr_bwd(int B, int H, const double* __restrict__ X, const double* __restrict__ U, const double* __restrict__ Lam,
+                  const double* __restrict__ theta, int theta_stride, double* __restrict__ gains,
+                  const double* __restrict__ auxrec, const double* __restrict__ termrec, int* __restrict__ status)
+{
+  extern __shared__ __align__(16) double pdp_smem[];
+  const int lane = threadIdx.x & 31;
+  const int half = lane >> 4, tl = lane & 15;
+  const int b0 = (blockIdx.x * PDP_WPB + (threadIdx.x >> 5)) * 2;
+  if (b0 >= B) return;
+  const bool live = b0 + half < B;
+  const int b = live ? b0 + half : B - 1;                                    // a tail half shadows a valid trajectory
+  double* auxc = pdp_smem + (size_t)(threadIdx.x >> 5) * PDP_WARP_DOUBLES + half * PDP_HS;   // [CH][AUXLD]
+  double* ZT = auxc + PDP_OFF_ZT;                                            // Z^T staging
+  double* KS = auxc + PDP_OFF_KS;                                            // K (m x n)
+  double* QUU = auxc + PDP_OFF_QUU;                                          // m x m
+  double* TH = auxc + PDP_OFF_TH;                                            // theta
+  double* TB = auxc;                                                         // terminal buffer aliases the chunk buffer
+  const int r0 = tl < PDP_N ? tl : 0;                                        // stack row of slot 0
+  const int r1 = PDP_N + (tl < PDP_M + PDP_R ? tl : 0);                      // stack row of slot 1
+  const bool wrow = tl >= PDP_M && tl < PDP_M + PDP_R;                       // slot 1 holds a column of W
+  const int gslot0 = tl < PDP_N ? tl : -1;
+  const int gslot1 = wrow ? PDP_N + tl - PDP_M : -1;
+  const double* Xb = X + (size_t)b * (H + 1) * PDP_N;
+  const double* Ub = U + (size_t)b * H * PDP_M;
+  const double* Lb = Lam + (size_t)b * H * PDP_N;
+  (void)Xb; (void)Ub; (void)Lb; (void)r0; (void)r1;
+  bool bad = false;
+@@TABLOAD@@
+  if (theta != nullptr) for (int i = tl; i < PDP_NTH; i += 16) TH[i] = theta[(size_t)b * theta_stride + i];
+  __syncwarp();
+  // ---- terminal condition P = hxx(x_H), W = hxe(x_H)  (PDP.py:561-562)
+@@EVAL_TERM@@
+  __syncwarp();
+  @@YDECL@@
+  {
+@@TERM_INIT@@
+  }
+  __syncwarp();
+  #pragma unroll 1
+  for (int tc = ((H - 1) / PDP_CH) * PDP_CH; tc >= 0; tc -= PDP_CH) {
+    __syncwarp();            // every lane is done reading the previous chunk's slots
+@@EVAL_AUX_CHUNK@@
+    __syncwarp();
+    const int thi = (tc + PDP_CH < H ? tc + PDP_CH : H) - 1;
+    #pragma unroll 1
+    for (int t = thi; t >= tc; --t) {
+      const double* ar = auxc + (t - tc) * PDP_AUXLD;
+@@BACKWARD_STEP@@
+      __syncwarp();
+    }
+  }
+  if (status && bad && live && tl == 0) atomicOr(&status[b], 2);
+}
+
+"""
+
 K_LAUNCH_COMMON = r'''
 // =====================================================================================================
 // Host-side launchers (C ABI of the module; bound by csrc/pdp_b200.cpp through dlopen)
@@ -424,7 +490,7 @@ extern "C" int pdpmod_aux_lqr(int B, int H, const double* X, const double* U, co
     configured = true;
   }
   if (phases & 1)
-    pdp_k_aux_lqr_bwd<<<(B + PDP_WPB - 1) / PDP_WPB, PDP_WPB * 32, smem_b, st>>>(B, H, X, U, Lam, theta, theta_stride, gains,
+    pdp_k_aux_lqr_bwd<<<(B + PDP_WPB * PDP_BP - 1) / (PDP_WPB * PDP_BP), PDP_WPB * 32, smem_b, st>>>(B, H, X, U, Lam, theta, theta_stride, gains,
                                                                                auxrec, termrec, status);
   if (phases & 2)
     pdp_k_aux_lqr_fwd<<<(B + PDP_WPBF * PDP_FG - 1) / (PDP_WPBF * PDP_FG), PDP_WPBF * 32, smem_f, st>>>(B, H, X, U, theta, theta_stride, X0a,
@@ -433,3 +499,8 @@ extern "C" int pdpmod_aux_lqr(int B, int H, const double* X, const double* U, co
   return (int)cudaGetLastError();
 }
 '''
+
+
+_ib = K_AUX_LQR.index('extern "C" __global__ void __launch_bounds__(PDP_WPB * 32, PDP_MINB)')
+_if = K_AUX_LQR.index('extern "C" __global__ void __launch_bounds__(PDP_WPBF * 32, PDP_MINBF)')
+K_AUX_LQR_HEAD, K_AUX_LQR_BWD, K_AUX_LQR_FWD = K_AUX_LQR[:_ib], K_AUX_LQR[_ib:_if], K_AUX_LQR[_if:]

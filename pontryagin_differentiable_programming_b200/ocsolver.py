@@ -30,10 +30,13 @@ from .engine import OCSystem, _ptr, require_cuda
 class _NewtonSystem:
     def __init__(self, oc: OCSystem):
         s = oc.src
-        self.src = codegen.NewtonModuleSource(s.x, s.u, s.th, s.dyn, s.c, s.h, chunk=s.chunk, warps_per_block=s.wpb,
-                                              min_blocks=s.min_blocks, fwd_warps_per_block=s.wpbf,
-                                              fwd_min_blocks=s.min_blocks_f, keep_fg=s.keep_fg, fast_rcp=s.fast_rcp,
-                                              early_solve=s.early_solve)
+        pack = 2 if (s.bwd_pack == 2 or (s.n <= 16 and s.m + 1 <= 16)) else 1     # the Newton stack has one column
+        d = OCSystem.BWD_DEFAULTS[pack]
+        self.src = codegen.NewtonModuleSource(s.x, s.u, s.th, s.dyn, s.c, s.h, chunk=d["chunk"],
+                                              warps_per_block=d["warps_per_block"], min_blocks=d["min_blocks"],
+                                              fwd_warps_per_block=s.wpbf, fwd_min_blocks=s.min_blocks_f,
+                                              keep_fg=d["keep_fg"], fast_rcp=s.fast_rcp, early_solve=s.early_solve,
+                                              bwd_pack=pack)
         self.module_path = build.compile_module(self.src.source(), self.src.key())
         self._handle = None
         self.n, self.m, self.nth = self.src.n, self.src.m, self.src.nth

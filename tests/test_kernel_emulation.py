@@ -1,0 +1,95 @@
+"""CPU checks of the GENERATED Riccati kernels through the warp emulator (tools/warp_emu.py, test infrastructure).
+
+The emulator compiles the very CUDA text that nvcc compiles for sm_100a (kernels + device functions) with g++ and
+runs one warp as 32 host threads, so the lane layout, shared-memory indexing and synchronisation of both backward
+kernels (one / two trajectories per warp) and of the packed forward kernel are checked against the oracle without a
+GPU.  The `-m gpu` suite repeats the same comparisons on the real device through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import envs, pdp_oracle
+from tools import warp_emu
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+ORACLE_ENVS = {
+    "quadrotor": (envs.quadrotor, dict(c=0.01, wthrust=0.1)), "pendulum": (envs.pendulum, {}),
+    "rocket": (envs.rocket, dict(wthrust=0.1)), "cartpole": (envs.cartpole, dict(wu=0.1)),
+    "robotarm": (envs.robotarm, dict(g=0, wu=0.01))}
+
+
+def _rel(a, b):
+    return np.max(np.abs(a - b)) / max(1e-300, np.max(np.abs(b)))
+
+
+def _variant(base, **kw):
+    from pontryagin_differentiable_programming_b200 import codegen
+    cfg = dict(chunk=base.chunk, warps_per_block=base.wpb, min_blocks=base.min_blocks, fwd_warps_per_block=base.wpbf,
+               fwd_min_blocks=base.min_blocks_f, keep_fg=base.keep_fg, fast_rcp=base.fast_rcp,
+               early_solve=base.early_solve, fwd_pack=base.fwd_pack, fwd_chunk=base.fwd_chunk, bwd_pack=base.bwd_pack)
+    cfg.update(kw)
+    return codegen.OCModuleSource(base.x, base.u, base.th, base.dyn, base.c, base.h, **cfg)
+
+
+@pytest.mark.parametrize("env", ["quadrotor", "pendulum", "rocket", "cartpole", "robotarm"])
+def test_emulated_kernels_match_oracle_on_the_shipped_demos(env):
+    """Same data as tests/test_gpu_oc.py::test_demo_trajectories_backward_sweep_matches_oracle: the shipped IPOPT
+    demos (X, U, Lam) with a perturbed theta; both backward-kernel layouts must reproduce the oracle's literal
+    reference-form lqrSolver (PDP.py:446-615) to 1e-9 and agree with each other to round-off."""
+    from pontryagin_differentiable_programming_b200 import systems
+    g2 = np.load(os.path.join(G, "k2_demos.npz"))
+    dt = float(g2[env + "_dt"][0])
+    base = systems.OC_BUILDERS[env](dt).src
+    builder, kw = ORACLE_ENVS[env]
+    oc = pdp_oracle.build_oc(builder(**kw), dt)
+    nd = int(g2[env + "_n"])
+    theta = g2[env + "_true_parameter"] * 1.1
+    X = np.stack([g2["%s_%d_X" % (env, i)] for i in range(nd)])
+    U = np.stack([g2["%s_%d_U" % (env, i)] for i in range(nd)])
+    L = np.stack([g2["%s_%d_L" % (env, i)] for i in range(nd)])
+    if nd % 2 == 0:                      # an odd batch exercises the shadowing tail half-warp
+        X, U, L = (np.concatenate([a, a[:1]]) for a in (X, U, L))
+    assert base.bwd_pack == 2            # all five shipped systems fit the two-trajectory layout
+    gains = {}
+    for pack in (2, 1):
+        src = base if pack == 2 else _variant(base, bwd_pack=1, chunk=5, warps_per_block=2, min_blocks=1, keep_fg=True)
+        emu = warp_emu.Emulator(src)
+        gains[pack], status = emu.backward(X, U, L, theta)
+        assert not np.isnan(gains[pack]).any() and int(status.max()) == 0
+        dX, dU, _, st = emu.forward(X, U, theta, gains[pack])
+        assert int(st.max()) == 0
+        for i in range(X.shape[0]):
+            aux = oc.getAuxSys(X[i], U[i], L[i], theta)
+            sol = pdp_oracle.lqr_solve(aux, np.zeros((oc.n, oc.r)), U.shape[1])
+            assert _rel(dX[i], np.stack(sol["state_traj_opt"])) < 1e-9
+            assert _rel(dU[i], np.stack(sol["control_traj_opt"])) < 1e-9
+    assert _rel(gains[1], gains[2]) < 1e-11       # same algebra, row-for-row; only the operand order may differ
+
+
+def test_emulated_two_trajectory_kernel_chunk_tails_and_per_trajectory_theta():
+    """Horizon not a multiple of the chunk, chunk of one step, per-trajectory theta, fused IRL loss / chain rule."""
+    from pontryagin_differentiable_programming_b200 import systems
+    base = systems.quadrotor_irl(0.1).src
+    oc = pdp_oracle.build_oc(envs.quadrotor(c=0.01, wthrust=0.1), 0.1)
+    rng = np.random.default_rng(3)
+    B, H = 3, 11
+    x0 = np.tile(np.array([-8, -6, 9., 0, 0, 0, 1, 0, 0, 0, 0, 0, 0]), (B, 1)) + 0.05 * rng.standard_normal((B, 13))
+    theta = np.array([1, 1, 1, 1, 0.4, 1, 1, 5, 1.]) * (1 + 0.1 * rng.uniform(-1, 1, (B, 9)))
+    U = 2.5 + 0.5 * rng.standard_normal((B, H, 4))
+    ref = [pdp_oracle.pdp_sweep(oc, x0[b], U[b], theta[b]) for b in range(B)]
+    X = np.stack([r[0] for r in ref])
+    L = np.stack([r[1] for r in ref])
+    Xd = X + 0.1 * rng.standard_normal(X.shape)
+    Ud = U + 0.1 * rng.standard_normal(U.shape)
+    for kw in (dict(chunk=4), dict(chunk=1, early_solve=False, fast_rcp=False), dict(chunk=16, warps_per_block=2)):
+        emu = warp_emu.Emulator(_variant(base, **kw))
+        gains, _ = emu.backward(X, U, L, theta)
+        dX, dU, ldp, _ = emu.forward(X, U, theta, gains, Xref=Xd, Uref=Ud)
+        for b in range(B):
+            assert _rel(dX[b], np.asarray(ref[b][3])) < 1e-10
+            assert _rel(dU[b], np.asarray(ref[b][4])) < 1e-10
+            loss, dp = pdp_oracle.irl_loss_grad(X[b], U[b], Xd[b], Ud[b], ref[b][3], ref[b][4])
+            assert abs(ldp[b, 0] - loss) < 1e-12 * abs(loss)
+            assert _rel(ldp[b, 1:], np.asarray(dp).ravel()) < 1e-10

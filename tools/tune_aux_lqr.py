@@ -12,26 +12,30 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-# (chunk, bwd warps/block, bwd min blocks, fwd warps/block, fwd min blocks)
-# (chunk, bwd warps/block, bwd min blocks, fwd warps/block, fwd min blocks, keep [F|G] slots in registers A->C)
-# (chunk, bwd warps/block, bwd min blocks, fwd warps/block, fwd min blocks, keep_fg, fast_rcp, early_solve)
-# ... + (fwd_pack = trajectories per warp of the forward kernel, fwd_chunk)
-VARIANTS = [(17, 4, 3, 1, 8, True, True, True, 3, 10), (17, 4, 3, 1, 6, True, True, True, 3, 10),
-            (17, 4, 3, 2, 4, True, True, True, 3, 10), (17, 4, 3, 4, 2, True, True, True, 3, 10),
-            (17, 4, 3, 1, 12, True, True, True, 3, 10), (17, 4, 3, 4, 3, True, True, True, 1, 17)]
+# every variant: keyword overrides of BASE (= the shipped configuration of engine.OCSystem)
+BASE = dict(chunk=8, warps_per_block=1, min_blocks=8, fwd_warps_per_block=1, fwd_min_blocks=8, keep_fg=False,
+            fast_rcp=True, early_solve=True, fwd_pack=3, fwd_chunk=10, bwd_pack=2)
+V1 = dict(bwd_pack=1, chunk=17, warps_per_block=4, min_blocks=3, keep_fg=True)     # one trajectory per warp
+VARIANTS = [
+    V1,
+    {},                                                                    # shipped: two trajectories per warp
+    dict(chunk=5), dict(chunk=6), dict(chunk=7), dict(chunk=9),
+    dict(keep_fg=True), dict(chunk=7, keep_fg=True),
+    dict(warps_per_block=2, min_blocks=4), dict(chunk=7, early_solve=False),
+]
 
 
-def make(ch, wpb, mb, wpbf=4, mbf=1, kf=True, frcp=False, early=False, fpack=0, fchunk=0, verbose=False):
+def make(verbose=False, **kw):
     from JinEnv import JinEnv
     from pontryagin_differentiable_programming_b200 import engine
     from pontryagin_differentiable_programming_b200.symbolic import vertcat
+    cfg = dict(BASE)
+    cfg.update(kw)
     env = JinEnv.Quadrotor()
     env.initDyn(c=0.01)
     env.initCost(wthrust=0.1)
     return engine.OCSystem(env.X, env.U, vertcat(env.dyn_auxvar, env.cost_auxvar), env.X + 0.1 * env.f, env.path_cost,
-                           env.final_cost, chunk=ch, warps_per_block=wpb, min_blocks=mb, fwd_warps_per_block=wpbf,
-                           fwd_min_blocks=mbf, keep_fg=kf, fast_rcp=frcp, early_solve=early, verbose=verbose,
-                           fwd_pack=fpack, fwd_chunk=fchunk)
+                           env.final_cost, verbose=verbose, **cfg)
 
 
 def main():
@@ -43,7 +47,7 @@ def main():
     if args.build:
         for v in VARIANTS:
             print("== variant", v)
-            make(*v, verbose=True)
+            make(verbose=True, **v)
     if args.run:
         import numpy as np
         import torch
@@ -52,8 +56,9 @@ def main():
         B, H = args.batch, 50
         x0, theta, U, Xr, Ur = [torch.as_tensor(a, device=dev) for a in bench.synth_quadrotor(B, H)]
         rows = []
+        ref_dx = None
         for v in VARIANTS:
-            s = make(*v)
+            s = make(**v)
             ro = s.rollout_costate(x0, theta, U)
             out = {"dX": torch.empty((B, H + 1, 13, 9), dtype=torch.float64, device=dev),
                    "dU": torch.empty((B, H, 4, 9), dtype=torch.float64, device=dev),
@@ -70,8 +75,15 @@ def main():
                 e1.record()
                 torch.cuda.synchronize()
                 ms[phase] = e0.elapsed_time(e1) / 10
-            rows.append({"chunk": v[0], "wpb": v[1], "minb": v[2], "wpbf": v[3], "minbf": v[4], "keep_fg": v[5], "fast_rcp": v[6], "early_solve": v[7], "fwd_pack": v[8], "fwd_chunk": v[9], "bwd_ms": ms["backward"],
-                         "fwd_ms": ms["forward"], "sweeps_per_s": B / (ms["backward"] + ms["forward"]) * 1e3})
+            dx = out["dX"][:256].clone()
+            if ref_dx is None:
+                ref_dx = dx
+            err = float((dx - ref_dx).abs().max() / ref_dx.abs().max())       # parity against the first variant
+            row = dict(BASE)
+            row.update(v)
+            row.update({"bwd_ms": ms["backward"], "fwd_ms": ms["forward"], "rel_diff_vs_first": err,
+                        "sweeps_per_s": B / (ms["backward"] + ms["forward"]) * 1e3})
+            rows.append(row)
             print(json.dumps(rows[-1]), flush=True)
             del out
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

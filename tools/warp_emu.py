@@ -1,0 +1,190 @@
+"""CPU warp emulator for the generated Riccati kernels (TEST INFRASTRUCTURE, never on the product path).
+
+The build container has no GPU, so a new kernel variant could only be checked after a `gpurun` round trip.  This tool
+compiles the *generated CUDA source* of a module (`OCModuleSource.source()`, cut before the host launchers) with g++
+and runs one warp as 32 host threads: `__syncwarp()` is a pthread barrier, `__shfl_xor_sync` goes through a small
+exchange buffer, shared memory is a global array.  It executes exactly the statements the GPU executes (same
+generated text, same lane predicates, same shared-memory indices), so layout / indexing / synchronisation mistakes
+show up here in seconds.  It says nothing about performance, and races that a barrier would hide on the CPU are left
+to `tools/sanitize.sh` (compute-sanitizer racecheck on the GPU).
+
+    from tools import warp_emu
+    emu = warp_emu.Emulator(src)            # src: an OCModuleSource
+    gains = emu.backward(X, U, Lam, theta)  # numpy float64 in / out
+    dX, dU = emu.forward(X, U, theta, gains)
+"""
+from __future__ import annotations
+
+import ctypes
+import hashlib
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+
+PREAMBLE = r'''
+#include <math.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string.h>
+#include <pthread.h>
+#include <cmath>
+using std::isfinite;
+#define __global__
+#define __device__
+#define __forceinline__ inline
+#define __noinline__
+#define __restrict__
+#define __shared__
+#define __align__(x)
+#define __launch_bounds__(...)
+struct emu_dim3 { unsigned x, y, z; };
+static thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
+struct double2 { double x, y; };
+static inline double2 make_double2(double a, double b) { double2 v; v.x = a; v.y = b; return v; }
+extern "C" { alignas(16) double pdp_smem[1 << 18]; }
+static pthread_barrier_t emu_bar;
+static double emu_xch[32];
+static inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&emu_bar); }
+static inline double __shfl_xor_sync(unsigned, double v, int o) {
+  const int l = threadIdx.x & 31;
+  emu_xch[l] = v; pthread_barrier_wait(&emu_bar);
+  const double r = emu_xch[l ^ o]; pthread_barrier_wait(&emu_bar);
+  return r;
+}
+static inline double __shfl_sync(unsigned, double v, int src) {
+  const int l = threadIdx.x & 31;
+  emu_xch[l] = v; pthread_barrier_wait(&emu_bar);
+  const double r = emu_xch[src & 31]; pthread_barrier_wait(&emu_bar);
+  return r;
+}
+static inline int atomicOr(int* p, int v) { return __sync_fetch_and_or(p, v); }
+'''
+
+DRIVER = r'''
+struct emu_args {
+  int kernel, B, H, theta_stride, x0a_stride;
+  const double *X, *U, *Lam, *theta, *X0a, *Xref, *Uref;
+  double *gains, *dX, *dU, *loss_dp;
+  int* status;
+  unsigned bx, tx0, bdim;
+};
+static emu_args EA;
+static void* emu_lane(void* p) {
+  const unsigned lane = (unsigned)(uintptr_t)p;
+  threadIdx.x = EA.tx0 + lane; threadIdx.y = threadIdx.z = 0;
+  blockIdx.x = EA.bx; blockIdx.y = blockIdx.z = 0;
+  blockDim.x = EA.bdim; blockDim.y = blockDim.z = 1;
+  if (EA.kernel == 0)
+    EMU_BWD_KERNEL(EA.B, EA.H, EA.X, EA.U, EA.Lam, EA.theta, EA.theta_stride, EA.gains, nullptr, nullptr, EA.status);
+  else
+    pdp_k_aux_lqr_fwd(EA.B, EA.H, EA.X, EA.U, EA.theta, EA.theta_stride, EA.X0a, EA.x0a_stride, EA.dX, EA.dU, EA.gains,
+                      EA.Xref, EA.Uref, EA.loss_dp, nullptr, EA.status);
+  return nullptr;
+}
+static void emu_run(unsigned nblocks, unsigned warps_per_block) {
+  pthread_barrier_init(&emu_bar, nullptr, 32);
+  for (unsigned bx = 0; bx < nblocks; ++bx)
+    for (unsigned w = 0; w < warps_per_block; ++w) {
+      EA.bx = bx; EA.tx0 = w * 32; EA.bdim = warps_per_block * 32;
+      pthread_t th[32];
+      for (unsigned l = 0; l < 32; ++l) pthread_create(&th[l], nullptr, emu_lane, (void*)(uintptr_t)l);
+      for (unsigned l = 0; l < 32; ++l) pthread_join(th[l], nullptr);
+    }
+  pthread_barrier_destroy(&emu_bar);
+}
+extern "C" void emu_backward(int B, int H, const double* X, const double* U, const double* Lam, const double* theta,
+                             int theta_stride, double* gains, int* status) {
+  memset(&EA, 0, sizeof(EA));
+  EA.kernel = 0; EA.B = B; EA.H = H; EA.X = X; EA.U = U; EA.Lam = Lam; EA.theta = theta; EA.theta_stride = theta_stride;
+  EA.gains = gains; EA.status = status;
+  const unsigned per_block = EMU_BWD_TRAJ_PER_BLOCK;
+  emu_run((B + per_block - 1) / per_block, EMU_BWD_WPB);
+}
+extern "C" void emu_forward(int B, int H, const double* X, const double* U, const double* theta, int theta_stride,
+                            const double* X0a, int x0a_stride, double* dX, double* dU, const double* gains,
+                            const double* Xref, const double* Uref, double* loss_dp, int* status) {
+  memset(&EA, 0, sizeof(EA));
+  EA.kernel = 1; EA.B = B; EA.H = H; EA.X = X; EA.U = U; EA.theta = theta; EA.theta_stride = theta_stride;
+  EA.X0a = X0a; EA.x0a_stride = x0a_stride; EA.dX = dX; EA.dU = dU; EA.gains = (double*)gains;
+  EA.Xref = Xref; EA.Uref = Uref; EA.loss_dp = loss_dp; EA.status = status;
+  const unsigned per_block = PDP_WPBF * PDP_FG;
+  emu_run((B + per_block - 1) / per_block, PDP_WPBF);
+}
+extern "C" int emu_grec() { return PDP_GREC; }
+'''
+
+_RCP = re.compile(r'asm\("rcp\.approx\.ftz\.f64 %0, %1;" : "=d"\((\w+)\) : "d"\((\w+)\)\);')
+
+
+def translate(cuda_source: str) -> str:
+    """Generated CUDA translation unit -> C++ the emulator can compile (kernels + device functions only)."""
+    cut = cuda_source.find("// Host-side launchers")
+    if cut < 0:
+        raise ValueError("launcher marker not found in the generated source")
+    cut = cuda_source.rfind("// ====", 0, cut)
+    body = cuda_source[:cut]
+    body = body.replace("#include <cuda_runtime.h>", "")
+    body = _RCP.sub(lambda mo: "%s = 1.0 / %s;" % (mo.group(1), mo.group(2)), body)
+    if "asm(" in body:
+        raise ValueError("untranslated inline asm in the generated source")
+    return body
+
+
+class Emulator:
+    def __init__(self, src, bwd_kernel="pdp_k_aux_lqr_bwd", bwd_traj_per_block="PDP_WPB * PDP_BP", bwd_wpb="PDP_WPB",
+                 keep=False):
+        self.n, self.m, self.r = src.n, src.m, src.r
+        text = src.source() if hasattr(src, "source") else str(src)
+        cpp = (PREAMBLE + translate(text) + "\n#define EMU_BWD_KERNEL %s\n#define EMU_BWD_TRAJ_PER_BLOCK (%s)\n"
+               "#define EMU_BWD_WPB (%s)\n" % (bwd_kernel, bwd_traj_per_block, bwd_wpb) + DRIVER)
+        key = hashlib.sha256(cpp.encode()).hexdigest()[:16]
+        d = os.path.join(tempfile.gettempdir(), "pdp_warp_emu")
+        os.makedirs(d, exist_ok=True)
+        so = os.path.join(d, "emu_%s.so" % key)
+        if not os.path.isfile(so):
+            cc = os.path.join(d, "emu_%s.cpp" % key)
+            with open(cc, "w") as f:
+                f.write(cpp)
+            p = subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-w", "-ffp-contract=off",
+                                "-o", so + ".tmp", cc], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            if p.returncode != 0:
+                raise RuntimeError("g++ failed on the emulated kernel source (%s):\n%s" % (cc, p.stdout[-6000:]))
+            os.replace(so + ".tmp", so)
+        self.lib = ctypes.CDLL(so)
+        self.grec = int(self.lib.emu_grec())
+
+    @staticmethod
+    def _p(a):
+        return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+    def backward(self, X, U, Lam, theta):
+        B, H = U.shape[0], U.shape[1]
+        X, U, Lam = (np.ascontiguousarray(a, dtype=np.float64) for a in (X, U, Lam))
+        theta = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
+        ts = 0 if theta.shape[0] == 1 else theta.shape[1]
+        gains = np.full((B, H, self.grec), np.nan)
+        status = np.zeros(B, dtype=np.int32)
+        self.lib.emu_backward(B, H, self._p(X), self._p(U), self._p(Lam), self._p(theta), ts, self._p(gains),
+                              self._p(status))
+        return gains, status
+
+    def forward(self, X, U, theta, gains, Xref=None, Uref=None):
+        B, H = U.shape[0], U.shape[1]
+        n, m, r = self.n, self.m, self.r
+        X, U, gains = (np.ascontiguousarray(a, dtype=np.float64) for a in (X, U, gains))
+        theta = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
+        ts = 0 if theta.shape[0] == 1 else theta.shape[1]
+        dX = np.full((B, H + 1, n, r), np.nan)
+        dU = np.full((B, H, m, r), np.nan)
+        status = np.zeros(B, dtype=np.int32)
+        ldp = None
+        if Xref is not None:
+            Xref = np.ascontiguousarray(Xref, dtype=np.float64)
+            Uref = None if Uref is None else np.ascontiguousarray(Uref, dtype=np.float64)
+            ldp = np.full((B, r + 1), np.nan)
+        self.lib.emu_forward(B, H, self._p(X), self._p(U), self._p(theta), ts, None, 0, self._p(dX), self._p(dU),
+                             self._p(gains), self._p(Xref), self._p(Uref), self._p(ldp), self._p(status))
+        return dX, dU, ldp, status
