@@ -81,14 +81,18 @@ def alg_flops_sweep(n, m, r, H):
 
 
 def ncu_traffic(kernel):
-    """DRAM bytes (read + write) per launch of ``kernel`` from the committed `ncu --set full` capture of this same
-    command (profiles/r1_final_ncu_traffic.json, C3 at 16 384 trajectories); None if no capture is committed."""
-    p = os.path.join(ROOT, "profiles", "r1_final_ncu_traffic.json")
-    try:
-        d = json.load(open(p))
-        return float(d[kernel]["dram_bytes_read"]) + float(d[kernel]["dram_bytes_write"]), d.get("source")
-    except Exception:
-        return None, None
+    """DRAM bytes (read + write) per launch of ``kernel`` from the newest committed `ncu --set full` capture of this
+    same command (profiles/*_ncu_traffic.json, C3 at 16 384 trajectories); None if no capture is committed."""
+    for name in TRAFFIC_FILES:
+        try:
+            d = json.load(open(os.path.join(ROOT, "profiles", name)))
+            return float(d[kernel]["dram_bytes_read"]) + float(d[kernel]["dram_bytes_write"]), d.get("source")
+        except Exception:
+            continue
+    return None, None
+
+
+TRAFFIC_FILES = ("r1m_ncu_traffic.json", "r1_final_ncu_traffic.json")     # newest first
 
 
 def measured_peaks():

@@ -194,8 +194,12 @@ class OCModuleSource:
     def __init__(self, state: SX, control: SX, auxvar: SX, dyn: SX, path_cost: SX, final_cost: SX,
                  chunk: int = 8, warps_per_block: int = 4, min_blocks: int = 1, fwd_warps_per_block: int = 4,
                  fwd_min_blocks: int = 1, keep_fg: bool = True, fast_rcp: bool = False, early_solve: bool = False,
-                 fwd_pack: int = 0, fwd_chunk: int = 0, bwd_pack: int = 1):
+                 fwd_pack: int = 0, fwd_chunk: int = 0, bwd_pack: int = 1, fwd_vec: int = -1, prefetch: int = 2,
+                 prefetch_dist: int = 2, inline_eval: int = -1):
         self.keep_fg = bool(keep_fg)
+        self.inline_eval = int(inline_eval)
+        self.prefetch, self.prefetch_dist = int(prefetch), int(prefetch_dist)
+        self.fwd_vec = int(fwd_vec)
         self.fwd_pack, self.fwd_chunk = int(fwd_pack), int(fwd_chunk)
         self.bwd_pack = int(bwd_pack)
         self.fast_rcp, self.early_solve = bool(fast_rcp), bool(early_solve)
@@ -360,8 +364,12 @@ class OCModuleSource:
         # all aux slots / only the dynamics-Jacobian slots
         # the two slot evaluators are deliberately NOT inlined: they run once per chunk on a few lanes and would
         # otherwise dictate the register allocation (hence the occupancy) of the per-step hot loops
+        # (option inline_eval: the two-trajectory backward kernel runs at the 255-register cap anyway, so inlining costs
+        # no occupancy there -- but it does not pay either)
+        inl = getattr(self, "inline_eval", -1)
+        inl = False if inl < 0 else bool(inl)      # measured on the two-trajectory kernel: 0.6695 vs 0.6689 ms -- no gain
         parts.append(_emit_function("pdp_f_aux_slots", [x, u, lam, th], self.slots.nodes, lambda i: "out[%d]" % i,
-                                    qualifiers="__device__ __noinline__"))
+                                    qualifiers="__device__ __forceinline__" if inl else "__device__ __noinline__"))
         parts.append(_emit_function("pdp_f_dyn_slots", [x, u, th], self.slots.nodes[:self.nvar_s] or [S.ZERO],
                                     lambda i: "out[%d]" % i, qualifiers="__device__ __noinline__"))
         # terminal Hessians, dense row-major [hxx (n*n) | hxe (n*r)]
@@ -544,6 +552,10 @@ class OCModuleSource:
                 expr = "fma(-l%d%d, v%s_%d, %s)" % (k, i, tag, k, expr)
             L.append(ind + "const double v%s_%d = %s;" % (tag, i, expr))
 
+    def _zero_z_columns(self):
+        """Columns j of Z = P [F|G|E] that are structurally zero (no entry of column j of [F|G|E]); ns <= 32."""
+        return {j for j in range(self.ns) if all(self.S_ent[k][j][0] == "z" for k in range(self.n))}
+
     def _hidx8(self) -> bool:
         """Two-trajectory kernel: pack four 8-bit Hamiltonian slot indices per register (needs < 256 slots)."""
         return self.nvar <= 255
@@ -565,17 +577,19 @@ class OCModuleSource:
                 acc.add(j, "y0_%d" % k, self.S_ent[k][j], load)
         acc.finish()
         L.append(ind + "// B: transpose through shared memory: slot 0 picks up column tl of Z, slot 1 column n + tl (+ its W column)")
+        zero_cols = self._zero_z_columns()
         L.append(ind + "if (tl < %d) {" % n)
         for j in range(ns):
-            L.append(ind + "  ZT[%d + tl] = z%d;" % (j * self.ldz, j))
+            if j not in zero_cols:
+                L.append(ind + "  ZT[%d + tl] = z%d;" % (j * self.ldz, j))
         L.append(ind + "}")
         L.append(ind + "__syncwarp();")
         L.append(ind + "double " + ", ".join("c0_%d, c1_%d" % (k, k) for k in range(n)) + ";")
-        L.append(ind + "{ const double* zr = ZT + r0 * %d;" % self.ldz)
+        L.append(ind + "{ const double* zr = ZT + zr0 * %d;" % self.ldz)
         for k in range(n):
             L.append(ind + "  c0_%d = zr[%d];" % (k, k))
         L.append(ind + "}")
-        L.append(ind + "{ const double* zr = ZT + r1 * %d;" % self.ldz)
+        L.append(ind + "{ const double* zr = ZT + zr1 * %d;" % self.ldz)
         for k in range(n):
             L.append(ind + "  c1_%d = zr[%d];" % (k, k))
         L.append(ind + "}")
@@ -668,12 +682,18 @@ class OCModuleSource:
 
     fwd_smem_budget = 18 * 1024
 
+    def _fwd_group_stride(self):
+        """Lanes per trajectory group of the forward kernel: r rounded up to even (see the kernel template)."""
+        r = max(self.r, 1)
+        return min(r + (r & 1), WARP) if r < WARP else WARP
+
     def _fwd_shape(self):
         """(trajectories per warp, chunk length) of the forward kernel: lane g*r + c owns column c of trajectory g.
         The chunk is capped so that one warp's regions stay within ``fwd_smem_budget`` bytes of shared memory
         (18 KB: twelve warps per SM)."""
-        fg = getattr(self, "fwd_pack", 0) or max(1, min(WARP // max(self.r, 1), 4))
-        fg = max(1, min(fg, WARP // max(self.r, 1), WARP))
+        gs = self._fwd_group_stride()
+        fg = getattr(self, "fwd_pack", 0) or max(1, min(WARP // gs, 4))
+        fg = max(1, min(fg, WARP // gs, WARP))
         ch = getattr(self, "fwd_chunk", 0)
         if not ch:
             per_step = _pad_ld(self.nvar_s) + self.n + self.m
@@ -688,12 +708,21 @@ class OCModuleSource:
         ind = "      "
         L.append(ind + "// U(:,c) = k(:,c) + K X(:,c); K staged as [l][a] per trajectory; two partial sums per row shorten the chains")
         half = (n + 1) // 2
+        # operand loads: with several trajectories per warp every group of lanes reads its own trajectory's word; a
+        # 64-bit load serves up to four such groups in ONE shared-memory wavefront, a 128-bit load needs one pass per
+        # quarter-warp (measured: tools/microbench/smem_wavefronts.cu), so the packed kernel uses scalar loads
+        fv = getattr(self, "fwd_vec", -1)
+        vec = (self._fwd_shape()[0] == 1) if fv < 0 else bool(fv)
+        # (volatile pointers: nvcc would otherwise prove the alignment and fuse neighbouring loads back into LDS.128)
+        ks, arn = ("KS", "ar") if vec else ("vKS", "var")
+        if not vec:
+            L.append(ind + "const volatile double* vKS = KS; const volatile double* var = ar;")
         for a in range(m):
             L.append(ind + "double u%d = g%d, ub%d = 0.0;" % (a, a, a))
         for l in range(n):
             a = 0
             while a < m:
-                if m % 2 == 0:
+                if m % 2 == 0 and vec:
                     L.append(ind + "{ const double2 kk = *reinterpret_cast<const double2*>(KS + %d);" % (l * m + a))
                     for d, comp in ((0, "x"), (1, "y")):
                         tgt = "u%d" % (a + d) if l < half else "ub%d" % (a + d)
@@ -702,14 +731,14 @@ class OCModuleSource:
                     a += 2
                 else:
                     tgt = "u%d" % a if l < half else "ub%d" % a
-                    L.append(ind + "%s = fma(KS[%d], x%d, %s);" % (tgt, l * m + a, l, tgt))
+                    L.append(ind + "%s = fma(%s[%d], x%d, %s);" % (tgt, ks, l * m + a, l, tgt))
                     a += 1
         for a in range(m):
             L.append(ind + "u%d += ub%d;" % (a, a))
         L.append(ind + "// X+(:,c) = F X(:,c) + G U(:,c) + E(:,c)")
         L.append(ind + "double " + ", ".join("n%d" % i for i in range(n)) + ";")
-        needed = {e[1] for row in self.S_ent for e in row if e[0] == "v"}
-        load = _SlotLoader(L, "ar", needed, ind, "sf")
+        needed = {e[1] for row in self.S_ent for e in row if e[0] == "v"} if vec else set()
+        load = _SlotLoader(L, arn, needed, ind, "sf")
         acc = _Acc("n", n, L, ind)
         for i in range(n):
             for l in range(n):
@@ -764,7 +793,7 @@ class OCModuleSource:
     def source(self) -> str:
         n, m, r, ns = self.n, self.m, self.r, self.ns
         nm = n + m
-        zt_size = _even(ns * self.ldz)
+        zt_size = _even((ns + 1) * self.ldz)      # + one all-zero row (two-trajectory kernel, structurally zero columns)
         ks_size = _even(m * self.ldk)
         auxc_size = _even(max(self.chunk * self.auxld, n * n + n * r))
         off_zt = auxc_size
@@ -790,11 +819,13 @@ class OCModuleSource:
             "AUXLD": self.auxld, "CH": self.chunk, "WPB": self.wpb, "LDZ": self.ldz,
             "LDK": self.ldk, "OFF_ZT": off_zt, "OFF_KS": off_ks, "OFF_QUU": off_quu, "OFF_TH": off_th,
             "FLD": fld, "FOFF_KS": foff_ks, "FOFF_TH": foff_th, "FOFF_DL": foff_dl, "FG": fg, "CHF": chf, "FTS": fts,
-            "FOFF_DU": foff_du,
+            "FOFF_DU": foff_du, "FGS": self._fwd_group_stride(),
             "FWARP_DOUBLES": fwarp_doubles, "WPBF": getattr(self, "wpbf", 4), "MINBF": getattr(self, "min_blocks_f", 1),
             "WARP_DOUBLES": warp_doubles, "NTH": self.nth, "MINB": getattr(self, "min_blocks", 1), "GREC": (n + r) * m,
             "NDENSE": n * n + n * m + n * r + n * n + n * m + n * r + m * n + m * m + m * r,
             "BP": bp, "HS": half_stride,
+            "ZMASK": sum(1 << j for j in self._zero_z_columns()) if (bp == 2 and hasattr(self, "S_ent")) else 0,
+            "PF": getattr(self, "prefetch", 0), "PFD": max(1, getattr(self, "prefetch_dist", 3)),
         }
         header = ["// GENERATED by pontryagin_differentiable_programming_b200/codegen.py -- do not edit",
                   "#include <cuda_runtime.h>", "#include <math.h>", "#include <stdint.h>"]
@@ -889,6 +920,22 @@ class OCModuleSource:
     }""" % {"el": el},
             "@@EVAL_DYN@@": "        pdp_f_dyn_slots(X + ((size_t)be * (H + 1) + te) * PDP_N, U + ((size_t)be * H + te) * PDP_M, the, eo);",
             "@@EVAL_DYN_COOP@@": "",
+            "@@PREFETCH_AUX_CHUNK@@": "",      # measured: no gain (two-trajectory kernel) / a loss (one-trajectory kernel)
+            "@@PREFETCH_DYN_CHUNK@@": """#if PDP_PF
+    {
+      const int tp = tc + PDP_CHF + se;
+      if (evl && tp < H) {
+        const double* xp = X + ((size_t)be * (H + 1) + tp) * PDP_N;
+        const double* up = U + ((size_t)be * H + tp) * PDP_M;
+        pdp_prefetch(xp); pdp_prefetch(xp + (PDP_N - 1)); pdp_prefetch(up); pdp_prefetch(up + (PDP_M - 1));
+        if (fused) {
+          const double* xr = Xref + ((size_t)be * (H + 1) + tp) * PDP_N;
+          pdp_prefetch(xr); pdp_prefetch(xr + (PDP_N - 1));
+          if (Uref) { pdp_prefetch(Uref + ((size_t)be * H + tp) * PDP_M); pdp_prefetch(Uref + ((size_t)be * H + tp) * PDP_M + (PDP_M - 1)); }
+        }
+      }
+    }
+#endif""",
         }
 
     def key(self) -> str:
@@ -1069,6 +1116,8 @@ class LQRModuleSource(OCModuleSource):
             "@@EVAL_TERM@@": "  for (int i = lane; i < PDP_N * PDP_N + PDP_N * PDP_R; i += 32) TB[i] = termrec[(size_t)b * (PDP_N * PDP_N + PDP_N * PDP_R) + i];",
             "@@EVAL_AUX_CHUNK@@": gather % {"NV": "PDP_NVAR"},
             "@@EVAL_DYN@@": "",
+            "@@PREFETCH_AUX_CHUNK@@": "",
+            "@@PREFETCH_DYN_CHUNK@@": "",
             "@@EVAL_DYN_COOP@@": """    {
       const int nst = (tc + PDP_CHF < H ? PDP_CHF : H - tc);
       for (int idx = lane; idx < PDP_FG * nst * PDP_NVAR_S; idx += 32) {

@@ -172,6 +172,17 @@ K_AUX_LQR = r'''
 //   The auxiliary matrices are evaluated in chunks of PDP_CH steps with lanes = time steps; they never
 //   exist in HBM.  Two kernels (not one) so that each gets its own register allocation / occupancy.
 // =====================================================================================================
+// Software prefetch of rows that a later chunk / step will read (PDP_PF: 0 off, 1 into L1, 2 into L2): the per-chunk
+// evaluation and the per-step gain records are the only HBM reads of these kernels, and their latency is exposed at
+// 2 warps per scheduler.
+__device__ __forceinline__ void pdp_prefetch(const void* p) {
+#if PDP_PF == 1
+  asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+#elif PDP_PF == 2
+  asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+#endif
+}
+
 extern "C" __global__ void __launch_bounds__(PDP_WPB * 32, PDP_MINB)
 pdp_k_aux_lqr_bwd(int B, int H, const double* __restrict__ X, const double* __restrict__ U, const double* __restrict__ Lam,
                   const double* __restrict__ theta, int theta_stride, double* __restrict__ gains,
@@ -209,6 +220,7 @@ pdp_k_aux_lqr_bwd(int B, int H, const double* __restrict__ X, const double* __re
   for (int tc = ((H - 1) / PDP_CH) * PDP_CH; tc >= 0; tc -= PDP_CH) {
     __syncwarp();            // every lane is done reading the previous chunk's slots
 @@EVAL_AUX_CHUNK@@
+@@PREFETCH_AUX_CHUNK@@
     __syncwarp();
     const int thi = (tc + PDP_CH < H ? tc + PDP_CH : H) - 1;
     #pragma unroll 1
@@ -236,10 +248,13 @@ pdp_k_aux_lqr_fwd(int B, int H, const double* __restrict__ X, const double* __re
   const int b0 = (blockIdx.x * PDP_WPBF + (threadIdx.x >> 5)) * PDP_FG;
   if (b0 >= B) return;
   double* wbase = pdp_smem + (size_t)(threadIdx.x >> 5) * PDP_FWARP_DOUBLES;
-  const int grp = lane / PDP_R;
-  const bool owner = grp < PDP_FG;
-  const int g = owner ? grp : 0;
-  const int col = owner ? lane - grp * PDP_R : -1;
+  // lane g*PDP_FGS + c owns column c; the group stride PDP_FGS is r rounded up to EVEN so that both lanes of every
+  // even/odd lane pair read the same trajectory's operand: only then is a 64-bit shared-memory load with several
+  // group addresses served in one wavefront (measured with tools/microbench/smem_wavefronts.cu)
+  const int grp = lane / PDP_FGS;
+  const bool owner = grp < PDP_FG && lane - grp * PDP_FGS < PDP_R;
+  const int g = grp < PDP_FG ? grp : 0;
+  const int col = owner ? lane - grp * PDP_FGS : -1;
   const bool live = owner && (b0 + g < B);
   const int bg = (b0 + g < B) ? b0 + g : B - 1;                 // idle / tail lanes shadow a valid trajectory
   double* reg = wbase + g * PDP_FTS;
@@ -313,11 +328,17 @@ pdp_k_aux_lqr_fwd(int B, int H, const double* __restrict__ X, const double* __re
         }
       }
     }
+@@PREFETCH_DYN_CHUNK@@
     __syncwarp();
     const int tend = tc + PDP_CHF < H ? tc + PDP_CHF : H;
     #pragma unroll 1
     for (int t = tc; t < tend; ++t) {
       const double* ar = reg + (t - tc) * PDP_FLD;
+#if PDP_PF
+      // gain record of step t + PDP_PFD of this lane's trajectory: lane c of the group touches 128-byte line c
+      if (col >= 0 && col * 16 < PDP_GREC + 15 && t + PDP_PFD < H)
+        pdp_prefetch(gains + ((size_t)bg * H + t + PDP_PFD) * PDP_GREC + col * 16);
+#endif
 @@GCUR@@
 @@KS_STORE@@
       if (t + 1 < H) {
@@ -409,10 +430,15 @@ pdp_k_aux_lqr_bwd(int B, int H, const double* __restrict__ X, const double* __re
   const double* Xb = X + (size_t)b * (H + 1) * PDP_N;
   const double* Ub = U + (size_t)b * H * PDP_M;
   const double* Lb = Lam + (size_t)b * H * PDP_N;
-  (void)Xb; (void)Ub; (void)Lb; (void)r0; (void)r1;
+  // stack rows whose column of Z = P [F|G|E] is structurally zero (bit j of PDP_ZMASK) are never staged: their
+  // pick-up reads the all-zero row PDP_NS of the staging tile instead
+  const int zr0 = ((PDP_ZMASK >> r0) & 1u) ? PDP_NS : r0;
+  const int zr1 = ((PDP_ZMASK >> r1) & 1u) ? PDP_NS : r1;
+  (void)Xb; (void)Ub; (void)Lb; (void)zr0; (void)zr1;
   bool bad = false;
 @@TABLOAD@@
   if (theta != nullptr) for (int i = tl; i < PDP_NTH; i += 16) TH[i] = theta[(size_t)b * theta_stride + i];
+  if (tl < PDP_LDZ) ZT[PDP_NS * PDP_LDZ + tl] = 0.0;
   __syncwarp();
   // ---- terminal condition P = hxx(x_H), W = hxe(x_H)  (PDP.py:561-562)
 @@EVAL_TERM@@
@@ -426,6 +452,7 @@ pdp_k_aux_lqr_bwd(int B, int H, const double* __restrict__ X, const double* __re
   for (int tc = ((H - 1) / PDP_CH) * PDP_CH; tc >= 0; tc -= PDP_CH) {
     __syncwarp();            // every lane is done reading the previous chunk's slots
 @@EVAL_AUX_CHUNK@@
+@@PREFETCH_AUX_CHUNK@@
     __syncwarp();
     const int thi = (tc + PDP_CH < H ? tc + PDP_CH : H) - 1;
     #pragma unroll 1

@@ -1,0 +1,99 @@
+"""Read an `ncu --set full` report (brought back in gpurun_out/) and write the artefacts committed under profiles/:
+
+  python tools/ncu_summarise.py gpurun_out/prof.ncu-rep profiles/r1m
+
+  -> profiles/r1m_ncu_summary.csv   one row per metric, one column per captured kernel launch (the raw page, transposed)
+     profiles/r1m_ncu_traffic.json  DRAM bytes read / written and duration per kernel (bench.py: roofline.traffic)
+     profiles/r1m_ncu_source_mix.txt per-opcode executed instructions and shared-memory wavefronts of the Riccati kernels
+"""
+import collections
+import csv
+import io
+import json
+import subprocess
+import sys
+
+
+def raw_page(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    return rows[0], rows[1], rows[2:]
+
+
+def source_mix(rep, kernel):
+    p = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", kernel],
+                       capture_output=True, text=True)
+    if p.returncode != 0:
+        return None
+    rows = list(csv.reader(io.StringIO(p.stdout)))
+    hdr = None
+    for i, r in enumerate(rows):
+        if "Source" in r and any("Instructions Executed" == c for c in r):
+            hdr, body = r, rows[i + 1:]
+            break
+    if hdr is None:
+        return None
+    ci, cs = hdr.index("Source"), hdr.index("Instructions Executed")
+    cw = next((hdr.index(c) for c in hdr if c.startswith("L1 Wavefronts Shared") and "Excessive" not in c and "Ideal" not in c), None)
+    cwi = next((hdr.index(c) for c in hdr if c.startswith("L1 Wavefronts Shared Ideal")), None)
+    ex, wf, wfi = collections.Counter(), collections.Counter(), collections.Counter()
+    for r in body:
+        if len(r) <= max(ci, cs):
+            continue
+        toks = r[ci].split()
+        if not toks:
+            continue
+        op = toks[1] if toks[0].startswith("@") and len(toks) > 1 else toks[0]
+        op = op.rstrip(";")
+        try:
+            ex[op] += int(float(r[cs] or 0))
+            if cw is not None:
+                wf[op] += int(float(r[cw] or 0))
+            if cwi is not None:
+                wfi[op] += int(float(r[cwi] or 0))
+        except ValueError:
+            pass
+    return ex, wf, wfi
+
+
+def main():
+    rep, prefix = sys.argv[1], sys.argv[2]
+    names, units, rows = raw_page(rep)
+    kcol = names.index("Kernel Name")
+    kernels = [r[kcol] for r in rows]
+    with open(prefix + "_ncu_summary.csv", "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["metric", "unit"] + kernels)
+        for j, (nm, un) in enumerate(zip(names, units)):
+            if nm in ("ID", "Process ID", "Process Name", "Host Name", "Context", "Stream", "Device", "CC"):
+                continue
+            w.writerow([nm, un] + [r[j] for r in rows])
+
+    def val(r, metric):
+        j = names.index(metric)
+        v, u = float(r[j].replace(",", "")), units[j]
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1e3, "us": 1.0, "ns": 1e-3, "s": 1e6}
+        return v * scale.get(u, 1.0)
+
+    traffic = {"source": "%s_ncu_summary.csv (ncu --set full --clock-control none, bench.py --steps 1 --warmup 1, "
+                         "C3 B=16384, shipped configuration)" % prefix}
+    for r in rows:
+        traffic[r[kcol]] = {"dram_bytes_read": val(r, "dram__bytes_read.sum"), "dram_bytes_write": val(r, "dram__bytes_write.sum"),
+                            "gpu_time_us": val(r, "gpu__time_duration.sum")}
+    json.dump(traffic, open(prefix + "_ncu_traffic.json", "w"), indent=1)
+    with open(prefix + "_ncu_source_mix.txt", "w") as f:
+        for k in sorted(set(kernels)):
+            mix = source_mix(rep, k)
+            if mix is None:
+                f.write("== %s: no source page\n" % k)
+                continue
+            ex, wf, wfi = mix
+            f.write("== %s: warp-level executed instructions %d, shared-memory wavefronts %d (ideal %d)\n"
+                    % (k, sum(ex.values()), sum(wf.values()), sum(wfi.values())))
+            for op, c in ex.most_common(40):
+                f.write("  %-22s %12d  smem wavefronts %12d (ideal %d)\n" % (op, c, wf[op], wfi[op]))
+    print("wrote", prefix + "_ncu_{summary.csv,traffic.json,source_mix.txt}")
+
+
+if __name__ == "__main__":
+    main()

@@ -13,15 +13,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 # every variant: keyword overrides of BASE (= the shipped configuration of engine.OCSystem)
-BASE = dict(chunk=8, warps_per_block=1, min_blocks=8, fwd_warps_per_block=1, fwd_min_blocks=8, keep_fg=False,
-            fast_rcp=True, early_solve=True, fwd_pack=3, fwd_chunk=10, bwd_pack=2)
+BASE = dict(chunk=8, warps_per_block=1, min_blocks=8, fwd_warps_per_block=1, fwd_min_blocks=8, keep_fg=True,
+            fast_rcp=True, early_solve=True, fwd_pack=3, fwd_chunk=10, bwd_pack=2, fwd_vec=-1, prefetch=2, prefetch_dist=2, inline_eval=-1)
 V1 = dict(bwd_pack=1, chunk=17, warps_per_block=4, min_blocks=3, keep_fg=True)     # one trajectory per warp
 VARIANTS = [
     V1,
     {},                                                                    # shipped: two trajectories per warp
-    dict(chunk=5), dict(chunk=6), dict(chunk=7), dict(chunk=9),
-    dict(keep_fg=True), dict(chunk=7, keep_fg=True),
-    dict(warps_per_block=2, min_blocks=4), dict(chunk=7, early_solve=False),
+    dict(inline_eval=0), dict(chunk=16, min_blocks=6), dict(chunk=10), dict(chunk=12, min_blocks=7),
+    dict(chunk=6), dict(chunk=7), dict(chunk=9),
 ]
 
 

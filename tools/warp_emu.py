@@ -128,6 +128,7 @@ def translate(cuda_source: str) -> str:
     body = cuda_source[:cut]
     body = body.replace("#include <cuda_runtime.h>", "")
     body = _RCP.sub(lambda mo: "%s = 1.0 / %s;" % (mo.group(1), mo.group(2)), body)
+    body = re.sub(r'asm volatile\("prefetch\.global\.L[12] \[%0\];" :: "l"\(p\)\);', "(void)p;", body)
     if "asm(" in body:
         raise ValueError("untranslated inline asm in the generated source")
     return body
