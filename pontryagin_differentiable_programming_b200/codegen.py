@@ -907,7 +907,7 @@ class OCModuleSource:
 
     def _kernel_text(self):
         bwd = _K_AUX_LQR_BWD2 if getattr(self, "bwd_pack", 1) == 2 else _K_AUX_LQR_BWD
-        return _K_ROLLOUT_AUXEVAL + _K_AUX_LQR_HEAD + bwd + _K_AUX_LQR_FWD + _K_LAUNCH_COMMON + _K_LAUNCH_LQR
+        return _K_PRELUDE + _K_ROLLOUT_AUXEVAL + _K_AUX_LQR_HEAD + bwd + _K_AUX_LQR_FWD + _K_LAUNCH_COMMON + _K_LAUNCH_LQR
 
     def _eval_macros(self):
         el = "tl" if getattr(self, "bwd_pack", 1) == 2 else "lane"       # evaluation lane = time step of the chunk
@@ -1102,7 +1102,7 @@ class LQRModuleSource(OCModuleSource):
 
     def _kernel_text(self):
         info = _K_LAUNCH_COMMON[:_K_LAUNCH_COMMON.index('extern "C" int pdpmod_rollout_costate')]
-        return _K_AUX_LQR + info + _K_LAUNCH_LQR
+        return _K_PRELUDE + _K_AUX_LQR + info + _K_LAUNCH_LQR
 
     def _eval_macros(self):
         gather = """    {
@@ -1133,4 +1133,4 @@ class LQRModuleSource(OCModuleSource):
 from .kernel_templates import (  # noqa: E402
     K_AUX_LQR_BWD as _K_AUX_LQR_BWD, K_AUX_LQR_BWD2 as _K_AUX_LQR_BWD2, K_AUX_LQR_FWD as _K_AUX_LQR_FWD,
     K_AUX_LQR_HEAD as _K_AUX_LQR_HEAD, K_AUX_LQR as _K_AUX_LQR, K_LAUNCH_COMMON as _K_LAUNCH_COMMON, K_LAUNCH_LQR as _K_LAUNCH_LQR,
-    K_ROLLOUT_AUXEVAL as _K_ROLLOUT_AUXEVAL)
+    K_PRELUDE as _K_PRELUDE, K_ROLLOUT_AUXEVAL as _K_ROLLOUT_AUXEVAL)

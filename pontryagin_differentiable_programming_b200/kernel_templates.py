@@ -3,6 +3,20 @@
 ``codegen.py`` fills the ``@@...@@`` holes with generated straight-line code (structural non-zeros of the
 system at hand) and prepends the ``PDP_*`` constants.  See DESIGN.md for the kernel designs."""
 
+K_PRELUDE = r'''
+// Software prefetch of rows that a later chunk / step will read (PDP_PF: 0 off, 1 into L1, 2 into L2): used by the forward
+// Riccati kernel for its gain records and chunk rows (measured: -6 %; in the rollout kernel the same instructions cost
+// 10 % and in the backward kernel they change nothing, so those kernels do not prefetch).
+__device__ __forceinline__ void pdp_prefetch(const void* p) {
+#if PDP_PF == 1
+  asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+#elif PDP_PF == 2
+  asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+#endif
+}
+
+'''
+
 K_ROLLOUT_AUXEVAL = r'''
 // =====================================================================================================
 // Kernel 1: forward rollout + cost + costate recursion (+ optional dH/du), one thread per trajectory.
@@ -40,6 +54,42 @@ __device__ __forceinline__ void pdp_row_load(double* x, const double* g) {
   }
 }
 
+// Two-stage form of pdp_row_load for PREFETCHED rows: `issue` puts the row into a raw buffer with the same loads for
+// both address parities (16-byte pairs starting at element `par`, the one or two left-over elements as scalars), and
+// `unpack` sorts the buffer into x[] with selects when the row is consumed one step later.  (With pdp_row_load the
+// two parity paths fill different registers and nvcc merges them with MOVs right behind the loads -- which wait
+// for the data at once: 60 % of the rollout kernel's stall samples in the ncu source view.)
+template <int LEN>
+struct pdp_row_raw { double2 p[(LEN - 1) / 2 > 0 ? (LEN - 1) / 2 : 1]; double s0, s1; int par; };
+
+template <int LEN>
+__device__ __forceinline__ void pdp_row_issue(pdp_row_raw<LEN>& r, const double* g) {
+  constexpr int NP = (LEN - 1) / 2;
+  const int par = (int)((reinterpret_cast<uintptr_t>(g) >> 3) & 1);
+  r.par = par;
+  #pragma unroll
+  for (int k = 0; k < NP; ++k) r.p[k] = *reinterpret_cast<const double2*>(g + par + 2 * k);
+  if (LEN & 1) { r.s0 = g[par ? 0 : LEN - 1]; r.s1 = 0.0; }
+  else { r.s0 = g[par ? 0 : LEN - 2]; r.s1 = g[LEN - 1]; }
+}
+
+template <int LEN>
+__device__ __forceinline__ void pdp_row_unpack(double* x, const pdp_row_raw<LEN>& r) {
+  constexpr int NP = (LEN - 1) / 2;
+  const bool odd = r.par != 0;
+  #pragma unroll
+  for (int i = 0; i < LEN; ++i) {
+    // candidate of the aligned layout / of the layout shifted by one element
+    double c0, c1;
+    if (i < 2 * NP) c0 = (i & 1) ? r.p[i / 2].y : r.p[i / 2].x;
+    else c0 = (i == LEN - 1 && !(LEN & 1)) ? r.s1 : r.s0;
+    if (i == 0) c1 = r.s0;
+    else if (i <= 2 * NP) c1 = ((i - 1) & 1) ? r.p[(i - 1) / 2].y : r.p[(i - 1) / 2].x;
+    else c1 = r.s1;
+    x[i] = odd ? c1 : c0;
+  }
+}
+
 extern "C" __global__ void __launch_bounds__(128)
 pdp_k_rollout_costate(int B, int H, const double* __restrict__ x0, const double* __restrict__ theta, int theta_stride,
                       const double* __restrict__ U, double* __restrict__ X, double* __restrict__ Lam,
@@ -64,15 +114,14 @@ pdp_k_rollout_costate(int B, int H, const double* __restrict__ x0, const double*
   double* Xb = X + (size_t)b * (H + 1) * PDP_N;
   const double* Ub = U + (size_t)bs * H * PDP_M;
   const double fb_a = fb_gains ? fb_alpha[b] : 0.0;
-  double un[PDP_M];                       // software prefetch: the next step's control is in flight during this step
-  pdp_row_load<PDP_M>(un, Ub);
-  #pragma unroll 1
-  for (int t = 0; t < H; ++t) {
-    #pragma unroll
-    for (int i = 0; i < PDP_M; ++i) u[i] = un[i];
-    if (t + 1 < H) {
-      pdp_row_load<PDP_M>(un, Ub + (t + 1) * PDP_M);
-    }
+  // software prefetch TWO steps ahead: two raw buffers used by alternate steps of a loop unrolled by two, so that no
+  // register move (which would wait for the load) sits between the issue of a row and its use two steps later
+  pdp_row_raw<PDP_M> una, unb;
+  pdp_row_issue<PDP_M>(una, Ub);
+  pdp_row_issue<PDP_M>(unb, Ub + (H > 1 ? 1 : 0) * PDP_M);
+  auto fstep = [&](const int t, pdp_row_raw<PDP_M>& un) {
+    pdp_row_unpack<PDP_M>(u, un);
+    pdp_row_issue<PDP_M>(un, Ub + (t + 2 < H ? t + 2 : H - 1) * PDP_M);    // unconditional, index clamped
     if (fb_gains != nullptr) {
       const double* g = fb_gains + ((size_t)bs * H + t) * ((PDP_N + 1) * PDP_M);
       const double* xo = fb_X + ((size_t)bs * (H + 1) + t) * PDP_N;
@@ -93,6 +142,11 @@ pdp_k_rollout_costate(int B, int H, const double* __restrict__ x0, const double*
     pdp_f_dyn(x, u, th, xn);
     #pragma unroll
     for (int i = 0; i < PDP_N; ++i) x[i] = xn[i];
+  };
+  #pragma unroll 1
+  for (int t = 0; t < H; t += 2) {
+    fstep(t, una);
+    if (t + 1 < H) fstep(t + 1, unb);
   }
   pdp_row_store<PDP_N>(Xb + H * PDP_N, x);
   pdp_f_final_cost(x, th, tmp);
@@ -104,19 +158,21 @@ pdp_k_rollout_costate(int B, int H, const double* __restrict__ x0, const double*
     double* Lb = Lam + (size_t)b * H * PDP_N;
     pdp_f_dhx(x, th, lam);
     const double* Ua = fb_gains ? Uout + (size_t)b * H * PDP_M : Ub;      // the controls actually applied
-    double xp[PDP_N], up[PDP_M];          // prefetch of (x_{t-1}, u_{t-1}) while step t is being processed
-    pdp_row_load<PDP_N>(xp, Xb + (H - 1) * PDP_N);
-    pdp_row_load<PDP_M>(up, Ua + (H - 1) * PDP_M);
-    #pragma unroll 1
-    for (int t = H - 1; t >= 0; --t) {
+    // (x_{t-2}, u_{t-2}) are fetched while step t is being processed: two buffer pairs, loop unrolled by two
+    pdp_row_raw<PDP_N> xpa, xpb;
+    pdp_row_raw<PDP_M> upa, upb;
+    pdp_row_issue<PDP_N>(xpa, Xb + (H - 1) * PDP_N);
+    pdp_row_issue<PDP_M>(upa, Ua + (H - 1) * PDP_M);
+    pdp_row_issue<PDP_N>(xpb, Xb + (H > 1 ? H - 2 : 0) * PDP_N);
+    pdp_row_issue<PDP_M>(upb, Ua + (H > 1 ? H - 2 : 0) * PDP_M);
+    auto bstep = [&](const int t, pdp_row_raw<PDP_N>& xp, pdp_row_raw<PDP_M>& up) {
       pdp_row_store<PDP_N>(Lb + t * PDP_N, lam);
-      #pragma unroll
-      for (int i = 0; i < PDP_N; ++i) x[i] = xp[i];
-      #pragma unroll
-      for (int i = 0; i < PDP_M; ++i) u[i] = up[i];
-      if (t > 0) {
-        pdp_row_load<PDP_N>(xp, Xb + (t - 1) * PDP_N);
-        pdp_row_load<PDP_M>(up, Ua + (t - 1) * PDP_M);
+      pdp_row_unpack<PDP_N>(x, xp);
+      pdp_row_unpack<PDP_M>(u, up);
+      {
+        const int tq = t > 1 ? t - 2 : 0;       // unconditional, index clamped
+        pdp_row_issue<PDP_N>(xp, Xb + tq * PDP_N);
+        pdp_row_issue<PDP_M>(up, Ua + tq * PDP_M);
       }
       if (dHu != nullptr) {
         pdp_f_dHu(x, u, lam, th, gu);
@@ -128,6 +184,11 @@ pdp_k_rollout_costate(int B, int H, const double* __restrict__ x0, const double*
         #pragma unroll
         for (int i = 0; i < PDP_N; ++i) lam[i] = ln[i];
       }
+    };
+    #pragma unroll 1
+    for (int t = H - 1; t >= 0; t -= 2) {
+      bstep(t, xpa, upa);
+      if (t > 0) bstep(t - 1, xpb, upb);
     }
   }
   if (status && bad) atomicOr(&status[b], 1);
@@ -172,17 +233,6 @@ K_AUX_LQR = r'''
 //   The auxiliary matrices are evaluated in chunks of PDP_CH steps with lanes = time steps; they never
 //   exist in HBM.  Two kernels (not one) so that each gets its own register allocation / occupancy.
 // =====================================================================================================
-// Software prefetch of rows that a later chunk / step will read (PDP_PF: 0 off, 1 into L1, 2 into L2): the per-chunk
-// evaluation and the per-step gain records are the only HBM reads of these kernels, and their latency is exposed at
-// 2 warps per scheduler.
-__device__ __forceinline__ void pdp_prefetch(const void* p) {
-#if PDP_PF == 1
-  asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
-#elif PDP_PF == 2
-  asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
-#endif
-}
-
 extern "C" __global__ void __launch_bounds__(PDP_WPB * 32, PDP_MINB)
 pdp_k_aux_lqr_bwd(int B, int H, const double* __restrict__ X, const double* __restrict__ U, const double* __restrict__ Lam,
                   const double* __restrict__ theta, int theta_stride, double* __restrict__ gains,

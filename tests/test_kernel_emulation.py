@@ -93,3 +93,33 @@ def test_emulated_two_trajectory_kernel_chunk_tails_and_per_trajectory_theta():
             loss, dp = pdp_oracle.irl_loss_grad(X[b], U[b], Xd[b], Ud[b], ref[b][3], ref[b][4])
             assert abs(ldp[b, 0] - loss) < 1e-12 * abs(loss)
             assert _rel(ldp[b, 1:], np.asarray(dp).ravel()) < 1e-10
+
+
+@pytest.mark.parametrize("env", ["quadrotor", "pendulum", "cartpole"])
+def test_emulated_rollout_costate_kernel_matches_oracle(env):
+    """pdp_k_rollout_costate (thread per trajectory; two-stage prefetched row loads with both address parities:
+    rows of n = 13 doubles alternate between 16-byte aligned and misaligned) vs the oracle's rollout / PMP costate
+    recursion (PDP.py:158-175, 203-209)."""
+    from pontryagin_differentiable_programming_b200 import systems
+    src = systems.OC_BUILDERS[env](0.1).src
+    builder, kw = ORACLE_ENVS[env]
+    oc = pdp_oracle.build_oc(builder(**kw), 0.1)
+    rng = np.random.default_rng(2)
+    B, H = 5, 9
+    x0 = 0.3 * rng.standard_normal((B, src.n))
+    if env == "quadrotor":
+        x0[:, 6] += 1.0
+    theta = 1.0 + 0.2 * rng.uniform(-1, 1, (B, src.r))
+    U = 0.5 * rng.standard_normal((B, H, src.m)) + (2.5 if env == "quadrotor" else 0.0)
+    emu = warp_emu.Emulator(src)
+    for shift in (0, 1):                      # both parities of the base address
+        buf = np.zeros(B * H * src.m + 1)
+        Ush = buf[shift:shift + B * H * src.m].reshape(B, H, src.m)
+        Ush[...] = U
+        X, L, cost, dHu = emu.rollout(x0, theta, U if shift == 0 else Ush, want_dHu=True)
+        for b in range(B):
+            Xr, c = oc.rollout(x0[b], U[b], theta[b])
+            Lr = oc.costate(Xr, U[b], theta[b])
+            assert np.max(np.abs(X[b] - Xr)) < 1e-12
+            assert _rel(L[b], Lr) < 1e-12
+            assert abs(cost[b] - float(c)) < 1e-11 * max(1.0, abs(float(c)))

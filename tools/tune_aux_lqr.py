@@ -19,8 +19,7 @@ V1 = dict(bwd_pack=1, chunk=17, warps_per_block=4, min_blocks=3, keep_fg=True)  
 VARIANTS = [
     V1,
     {},                                                                    # shipped: two trajectories per warp
-    dict(inline_eval=0), dict(chunk=16, min_blocks=6), dict(chunk=10), dict(chunk=12, min_blocks=7),
-    dict(chunk=6), dict(chunk=7), dict(chunk=9),
+    dict(prefetch=0),
 ]
 
 
@@ -63,6 +62,16 @@ def main():
                    "dU": torch.empty((B, H, 4, 9), dtype=torch.float64, device=dev),
                    "loss_dp": torch.empty((B, 10), dtype=torch.float64, device=dev)}
             ms = {}
+            for _ in range(3):
+                s.rollout_costate(x0, theta, U, out=ro)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                s.rollout_costate(x0, theta, U, out=ro)
+            e1.record()
+            torch.cuda.synchronize()
+            ms["rollout"] = e0.elapsed_time(e1) / 10
             for phase in ("backward", "forward"):
                 for _ in range(3):
                     s.aux_lqr(ro["X"], U, ro["Lam"], theta, Xref=Xr, Uref=Ur, out=out, phase=phase)
@@ -80,8 +89,8 @@ def main():
             err = float((dx - ref_dx).abs().max() / ref_dx.abs().max())       # parity against the first variant
             row = dict(BASE)
             row.update(v)
-            row.update({"bwd_ms": ms["backward"], "fwd_ms": ms["forward"], "rel_diff_vs_first": err,
-                        "sweeps_per_s": B / (ms["backward"] + ms["forward"]) * 1e3})
+            row.update({"rollout_ms": ms["rollout"], "bwd_ms": ms["backward"], "fwd_ms": ms["forward"], "rel_diff_vs_first": err,
+                        "sweeps_per_s": B / (ms["rollout"] + ms["backward"] + ms["forward"]) * 1e3})
             rows.append(row)
             print(json.dumps(rows[-1]), flush=True)
             del out

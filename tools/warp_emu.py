@@ -114,6 +114,16 @@ extern "C" void emu_forward(int B, int H, const double* X, const double* U, cons
   emu_run((B + per_block - 1) / per_block, PDP_WPBF);
 }
 extern "C" int emu_grec() { return PDP_GREC; }
+#ifdef EMU_HAS_ROLLOUT
+// thread-per-trajectory kernel without warp-level primitives: the threads run one after the other
+extern "C" void emu_rollout(int B, int H, const double* x0, const double* theta, int theta_stride, const double* U,
+                            double* X, double* Lam, double* cost, double* dHu, int* status) {
+  for (int b = 0; b < B; ++b) {
+    threadIdx.x = b % 128; blockIdx.x = b / 128; blockDim.x = 128;
+    pdp_k_rollout_costate(B, H, x0, theta, theta_stride, U, X, Lam, cost, dHu, status, nullptr, nullptr, nullptr, nullptr, 1);
+  }
+}
+#endif
 '''
 
 _RCP = re.compile(r'asm\("rcp\.approx\.ftz\.f64 %0, %1;" : "=d"\((\w+)\) : "d"\((\w+)\)\);')
@@ -139,7 +149,8 @@ class Emulator:
                  keep=False):
         self.n, self.m, self.r = src.n, src.m, src.r
         text = src.source() if hasattr(src, "source") else str(src)
-        cpp = (PREAMBLE + translate(text) + "\n#define EMU_BWD_KERNEL %s\n#define EMU_BWD_TRAJ_PER_BLOCK (%s)\n"
+        has_ro = "pdp_k_rollout_costate" in text
+        cpp = (PREAMBLE + translate(text) + ("\n#define EMU_HAS_ROLLOUT 1" if has_ro else "") + "\n#define EMU_BWD_KERNEL %s\n#define EMU_BWD_TRAJ_PER_BLOCK (%s)\n"
                "#define EMU_BWD_WPB (%s)\n" % (bwd_kernel, bwd_traj_per_block, bwd_wpb) + DRIVER)
         key = hashlib.sha256(cpp.encode()).hexdigest()[:16]
         d = os.path.join(tempfile.gettempdir(), "pdp_warp_emu")
@@ -160,6 +171,21 @@ class Emulator:
     @staticmethod
     def _p(a):
         return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+    def rollout(self, x0, theta, U, want_dHu=False):
+        """pdp_k_rollout_costate -> X, Lam, cost[, dHu]."""
+        B, H = U.shape[0], U.shape[1]
+        x0, U = (np.ascontiguousarray(a, dtype=np.float64) for a in (x0, U))
+        theta = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
+        ts = 0 if theta.shape[0] == 1 else theta.shape[1]
+        X = np.full((B, H + 1, self.n), np.nan)
+        Lam = np.full((B, H, self.n), np.nan)
+        cost = np.full(B, np.nan)
+        dHu = np.full((B, H, self.m), np.nan) if want_dHu else None
+        status = np.zeros(B, dtype=np.int32)
+        self.lib.emu_rollout(B, H, self._p(x0), self._p(theta), ts, self._p(U), self._p(X), self._p(Lam), self._p(cost),
+                             self._p(dHu), self._p(status))
+        return X, Lam, cost, dHu
 
     def backward(self, X, U, Lam, theta):
         B, H = U.shape[0], U.shape[1]
