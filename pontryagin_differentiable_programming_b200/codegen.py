@@ -195,8 +195,9 @@ class OCModuleSource:
                  chunk: int = 8, warps_per_block: int = 4, min_blocks: int = 1, fwd_warps_per_block: int = 4,
                  fwd_min_blocks: int = 1, keep_fg: bool = True, fast_rcp: bool = False, early_solve: bool = False,
                  fwd_pack: int = 0, fwd_chunk: int = 0, bwd_pack: int = 1, fwd_vec: int = -1, prefetch: int = 2,
-                 prefetch_dist: int = 2, inline_eval: int = -1):
+                 prefetch_dist: int = 2, inline_eval: int = -1, h_group: int = 1):
         self.keep_fg = bool(keep_fg)
+        self.h_group = int(h_group)
         self.inline_eval = int(inline_eval)
         self.prefetch, self.prefetch_dist = int(prefetch), int(prefetch_dist)
         self.fwd_vec = int(fwd_vec)
@@ -279,6 +280,7 @@ class OCModuleSource:
                     node = self.ddHue.at(l - n, j - nm)
                 self.H_idx[j][l] = slots.exact(node)
         self.zero_slot = slots.exact(S.ZERO)
+        self.h_groups = self._h_column_groups() if getattr(self, "bwd_pack", 1) == 2 else None
         self._place_h_slots(slots)
         self.slots = slots
         self.nvar = len(slots)
@@ -286,13 +288,62 @@ class OCModuleSource:
         self.ldz = _odd(n)
         self.ldk = _even(n)
 
+    def _h_slot_rows(self):
+        """Stack rows served by slot 0 / slot 1 of the two-trajectory kernel."""
+        return [list(range(self.n)), list(range(self.n, self.ns))]
+
+    def _h_column_groups(self):
+        if not getattr(self, "h_group", 1):       # A/B switch: one load per column, as in the one-trajectory kernel
+            return [[[l] for l in range(self.n + self.m)] for _ in self._h_slot_rows()]
+        return self._h_column_groups_coloured()
+
+    def _h_column_groups_coloured(self):
+        """Two-trajectory kernel: the Hamiltonian stack is mostly structural zeros (quadrotor: 127 of 442 entries), and
+        every per-lane indexed load costs two shared-memory wavefronts however many lanes fetch a zero.  Columns of a
+        slot in which no row has more than one non-zero share ONE load (each lane fetches its own entry, then selects
+        the column it belongs to): greedy column colouring as for sparse Jacobians.  -> per slot a list of column
+        groups; columns without any non-zero in the slot are in no group."""
+        nm = self.n + self.m
+        out = []
+        for rows in self._h_slot_rows():
+            nzr = {l: {j for j in rows if self.H_idx[j][l] != self.zero_slot} for l in range(nm)}
+            groups: List[List[int]] = []
+            for l in sorted(range(nm), key=lambda c: (-len(nzr[c]), c)):
+                if not nzr[l]:
+                    continue
+                for g in groups:
+                    if len(g) < 15 and all(not (nzr[l] & nzr[o]) for o in g):
+                        g.append(l)
+                        break
+                else:
+                    groups.append([l])
+            out.append([sorted(g) for g in groups])
+        return out
+
+    def _h_group_entry(self, row, group):
+        """(slot index, member position) of ``row``'s entry within a column group; (zero slot, 15) if it has none."""
+        for pos, l in enumerate(group):
+            if self.H_idx[row][l] != self.zero_slot:
+                return self.H_idx[row][l], pos
+        return self.zero_slot, 15
+
     def _h_conflict_cost(self, phys):
         """Extra shared-memory wavefronts of the per-lane indexed Hamiltonian loads: a 64-bit warp load is served
         per half-warp, one wavefront per distinct word that shares a 16-way bank-pair with another distinct word."""
         ns, nm = self.ns, self.n + self.m
+        if getattr(self, "h_groups", None) is not None:
+            # two-trajectory kernel: one load per (slot, column group) serves the slot's rows of a half-warp; idle team
+            # lanes repeat the slot's first row
+            cost = 0
+            for rows, cgroups in zip(self._h_slot_rows(), self.h_groups):
+                for g in cgroups:
+                    banks: Dict[int, set] = {}
+                    for j in rows:
+                        a = phys[self._h_group_entry(j, g)[0]]
+                        banks.setdefault(a % 16, set()).add(a)
+                    cost += max(len(v) for v in banks.values()) - 1
+            return cost
         if getattr(self, "bwd_pack", 1) == 2:
-            # two-trajectory kernel: one load serves rows 0..n-1 (slot 0) or rows n..ns-1 (slot 1) of a half-warp;
-            # idle team lanes repeat the group's first row
             groups = [list(range(self.n)), list(range(self.n, ns))]
         else:
             groups = [list(range(16)), list(range(16, 32))]
@@ -556,6 +607,15 @@ class OCModuleSource:
         """Columns j of Z = P [F|G|E] that are structurally zero (no entry of column j of [F|G|E]); ns <= 32."""
         return {j for j in range(self.ns) if all(self.S_ent[k][j][0] == "z" for k in range(self.n))}
 
+    def _h_loads(self):
+        """[(slot, column group)] in load order (two-trajectory kernel)."""
+        return [(sl, g) for sl, cg in enumerate(self.h_groups) for g in cg]
+
+    def _h_multi_index(self, sl, g):
+        """Running index of a multi-column group among all multi-column groups (its 4-bit member code lives there)."""
+        multi = [(a, b) for a, b in self._h_loads() if len(b) > 1]
+        return multi.index((sl, g))
+
     def _hidx8(self) -> bool:
         """Two-trajectory kernel: pack four 8-bit Hamiltonian slot indices per register (needs < 256 slots)."""
         return self.nvar <= 255
@@ -599,11 +659,26 @@ class OCModuleSource:
         L.append(ind + "}")
         L.append(ind + "// C: Q(j,:) = Hstack(j,:) + Z(:,j)^T [F|G] for both rows (one operand load, two FMAs)")
         L.append(ind + "double " + ", ".join("q0_%d, q1_%d" % (l, l) for l in range(nm)) + ";")
-        for l in range(nm):
-            if self._hidx8():
-                w, sh = l // 2, 16 * (l % 2)
-                L.append(ind + "q0_%d = ar[(ho%d >> %d) & 0xffu]; q1_%d = ar[(ho%d >> %d) & 0xffu];" % (l, w, sh, l, w, sh + 8))
-            else:
+        if self._hidx8() and self.h_groups is not None:
+            # one load per (slot, column group); a lane whose row has no entry in the group reads the zero slot
+            assigned = set()
+            for k, (sl, g) in enumerate(self._h_loads()):
+                idx = "(ho%d >> %d) & 0xffu" % (k // 4, 8 * (k % 4))
+                if len(g) == 1:
+                    L.append(ind + "q%d_%d = ar[%s];" % (sl, g[0], idx))
+                else:
+                    c = self._h_multi_index(sl, g)
+                    L.append(ind + "{ const double hv = ar[%s]; const unsigned cd = (hc%d >> %d) & 0xfu;" % (idx, c // 8, 4 * (c % 8)))
+                    for pos, l in enumerate(g):
+                        L.append(ind + "  q%d_%d = (cd == %du) ? hv : 0.0;" % (sl, l, pos))
+                    L.append(ind + "}")
+                assigned |= {(sl, l) for l in g}
+            for sl in (0, 1):
+                for l in range(nm):
+                    if (sl, l) not in assigned:
+                        L.append(ind + "q%d_%d = 0.0;" % (sl, l))
+        else:
+            for l in range(nm):
                 L.append(ind + "q0_%d = ar[ho%d & 0xffffu]; q1_%d = ar[ho%d >> 16];" % (l, l, l, l))
         if not getattr(self, "keep_fg", True):
             needed = {self.S_ent[k][l][1] for k in range(n) for l in range(nm) if self.S_ent[k][l][0] == "v"}
@@ -838,13 +913,27 @@ class OCModuleSource:
                 tl = lane & 15
                 ra, rb = (tl if tl < n else 0), n + (tl if tl < m + r else 0)
                 return self.H_idx[ra][l], self.H_idx[rb][l]
+            hcode = []
             if self._hidx8():
-                nw = (nm + 1) // 2
+                loads = self._h_loads()
+                multi = [lg for lg in loads if len(lg[1]) > 1]
+
+                def lane_row(sl, lane):
+                    tl = lane & 15
+                    return (tl if tl < n else 0) if sl == 0 else n + (tl if tl < m + r else 0)
+                nw = (len(loads) + 3) // 4
                 for w in range(nw):
                     for lane in range(WARP):
-                        a0, a1 = pair(2 * w, lane)
-                        b0, b1 = pair(2 * w + 1, lane) if 2 * w + 1 < nm else (0, 0)
-                        hid.append(a0 | (a1 << 8) | (b0 << 16) | (b1 << 24))
+                        word = 0
+                        for q, (sl, g) in enumerate(loads[4 * w:4 * w + 4]):
+                            word |= self._h_group_entry(lane_row(sl, lane), g)[0] << (8 * q)
+                        hid.append(word)
+                for w in range((len(multi) + 7) // 8):
+                    for lane in range(WARP):
+                        word = 0
+                        for q, (sl, g) in enumerate(multi[8 * w:8 * w + 8]):
+                            word |= self._h_group_entry(lane_row(sl, lane), g)[1] << (4 * q)
+                        hcode.append(word)
             else:
                 nw = nm
                 for l in range(nm):
@@ -853,6 +942,10 @@ class OCModuleSource:
                         hid.append(a0 | (a1 << 16))
             tables.append("__device__ const unsigned int pdp_hidx[%d] = {%s};" % (len(hid), ", ".join(map(str, hid))))
             tabload = "\n".join("  const unsigned int ho%d = pdp_hidx[%d + lane];" % (w, w * WARP) for w in range(nw))
+            if hcode:
+                tables.append("__device__ const unsigned int pdp_hcode[%d] = {%s};" % (len(hcode), ", ".join(map(str, hcode))))
+                tabload += "\n" + "\n".join("  const unsigned int hc%d = pdp_hcode[%d + lane];" % (w, w * WARP)
+                                              for w in range(len(hcode) // WARP))
             ydecl = "double " + ", ".join("y0_%d = 0.0, y1_%d = 0.0" % (k, k) for k in range(n)) + ";"
             term_init = []
             for k in range(n):

@@ -1,3 +1,5 @@
+// SUPERSEDED by smem_wavefronts.cu (wavefronts read off ncu): this clock-based loop is bound by its own dependent DADD
+// chain, so it cannot tell one wavefront from two.  Kept for the record.
 // Micro-benchmark behind the multi-trajectory-per-warp kernels (run on the GPU box):
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/lds_groups tools/microbench/lds_groups.cu && /tmp/lds_groups
 // What does a shared-memory load cost when the warp's lanes form G groups and each group reads ITS OWN address
