@@ -195,8 +195,9 @@ class OCModuleSource:
                  chunk: int = 8, warps_per_block: int = 4, min_blocks: int = 1, fwd_warps_per_block: int = 4,
                  fwd_min_blocks: int = 1, keep_fg: bool = True, fast_rcp: bool = False, early_solve: bool = False,
                  fwd_pack: int = 0, fwd_chunk: int = 0, bwd_pack: int = 1, fwd_vec: int = -1, prefetch: int = 2,
-                 prefetch_dist: int = 2, inline_eval: int = -1, h_group: int = 1):
+                 prefetch_dist: int = 2, inline_eval: int = -1, h_group: int = 1, prefetch_l1_lead: int = 0):
         self.keep_fg = bool(keep_fg)
+        self.prefetch_l1_lead = int(prefetch_l1_lead)
         self.h_group = int(h_group)
         self.inline_eval = int(inline_eval)
         self.prefetch, self.prefetch_dist = int(prefetch), int(prefetch_dist)
@@ -901,6 +902,7 @@ class OCModuleSource:
             "BP": bp, "HS": half_stride,
             "ZMASK": sum(1 << j for j in self._zero_z_columns()) if (bp == 2 and hasattr(self, "S_ent")) else 0,
             "PF": getattr(self, "prefetch", 0), "PFD": max(1, getattr(self, "prefetch_dist", 3)),
+            "PFL": max(0, getattr(self, "prefetch_l1_lead", 0)),
         }
         header = ["// GENERATED by pontryagin_differentiable_programming_b200/codegen.py -- do not edit",
                   "#include <cuda_runtime.h>", "#include <math.h>", "#include <stdint.h>"]
@@ -1029,6 +1031,19 @@ class OCModuleSource:
       }
     }
 #endif""",
+            "@@PREFETCH_DYN_CHUNK_L1@@": """    {
+      const int tp = tc + PDP_CHF + se;
+      if (evl && tp < H) {
+        const double* xp = X + ((size_t)be * (H + 1) + tp) * PDP_N;
+        const double* up = U + ((size_t)be * H + tp) * PDP_M;
+        pdp_prefetch_l1(xp); pdp_prefetch_l1(xp + (PDP_N - 1)); pdp_prefetch_l1(up); pdp_prefetch_l1(up + (PDP_M - 1));
+        if (fused) {
+          const double* xr = Xref + ((size_t)be * (H + 1) + tp) * PDP_N;
+          pdp_prefetch_l1(xr); pdp_prefetch_l1(xr + (PDP_N - 1));
+          if (Uref) { pdp_prefetch_l1(Uref + ((size_t)be * H + tp) * PDP_M); pdp_prefetch_l1(Uref + ((size_t)be * H + tp) * PDP_M + (PDP_M - 1)); }
+        }
+      }
+    }""",
         }
 
     def key(self) -> str:
@@ -1211,6 +1226,7 @@ class LQRModuleSource(OCModuleSource):
             "@@EVAL_DYN@@": "",
             "@@PREFETCH_AUX_CHUNK@@": "",
             "@@PREFETCH_DYN_CHUNK@@": "",
+            "@@PREFETCH_DYN_CHUNK_L1@@": "",
             "@@EVAL_DYN_COOP@@": """    {
       const int nst = (tc + PDP_CHF < H ? PDP_CHF : H - tc);
       for (int idx = lane; idx < PDP_FG * nst * PDP_NVAR_S; idx += 32) {

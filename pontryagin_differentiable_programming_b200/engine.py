@@ -42,7 +42,7 @@ class OCSystem:
 
     def __init__(self, state, control, auxvar, dyn, path_cost, final_cost, chunk=None, warps_per_block=None,
                  min_blocks=None, fwd_warps_per_block=1, fwd_min_blocks=8, keep_fg=None, fast_rcp=True, early_solve=True,
-                 verbose=False, fwd_pack=0, fwd_chunk=0, bwd_pack=2, fwd_vec=-1, prefetch=2, prefetch_dist=2, inline_eval=-1, h_group=1):
+                 verbose=False, fwd_pack=0, fwd_chunk=0, bwd_pack=2, fwd_vec=-1, prefetch=2, prefetch_dist=2, inline_eval=-1, h_group=1, prefetch_l1_lead=0):
         fits = state.numel() <= 16 and control.numel() + auxvar.numel() <= 16
         bwd_pack = 2 if (int(bwd_pack) == 2 and fits) else 1
         d = self.BWD_DEFAULTS[bwd_pack]
@@ -52,7 +52,7 @@ class OCSystem:
         keep_fg = d["keep_fg"] if keep_fg is None else keep_fg
         self.src = codegen.OCModuleSource(state, control, auxvar, dyn, path_cost, final_cost, chunk, warps_per_block,
                                           min_blocks, fwd_warps_per_block, fwd_min_blocks, keep_fg, fast_rcp, early_solve,
-                                          fwd_pack, fwd_chunk, bwd_pack, fwd_vec, prefetch, prefetch_dist, inline_eval, h_group)
+                                          fwd_pack, fwd_chunk, bwd_pack, fwd_vec, prefetch, prefetch_dist, inline_eval, h_group, prefetch_l1_lead)
         self.n, self.m, self.r = self.src.n, self.src.m, self.src.r
         self.module_path = build.compile_module(self.src.source(), self.src.key(), verbose=verbose)
         self._handle = None

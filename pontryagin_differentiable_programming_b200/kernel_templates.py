@@ -14,6 +14,11 @@ __device__ __forceinline__ void pdp_prefetch(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
 #endif
 }
+__device__ __forceinline__ void pdp_prefetch_l1(const void* p) {
+#if PDP_PF
+  asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+#endif
+}
 
 '''
 
@@ -384,6 +389,11 @@ pdp_k_aux_lqr_fwd(int B, int H, const double* __restrict__ X, const double* __re
     #pragma unroll 1
     for (int t = tc; t < tend; ++t) {
       const double* ar = reg + (t - tc) * PDP_FLD;
+#if PDP_PF && PDP_PFL
+      if (t == tend - PDP_PFL) {      // the next chunk's rows were brought into L2 a chunk ago; now pull them into L1
+@@PREFETCH_DYN_CHUNK_L1@@
+      }
+#endif
 #if PDP_PF
       // gain record of step t + PDP_PFD of this lane's trajectory: lane c of the group touches 128-byte line c
       if (col >= 0 && col * 16 < PDP_GREC + 15 && t + PDP_PFD < H)

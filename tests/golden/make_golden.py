@@ -8,6 +8,7 @@ Sources (all under /root/reference, read-only, never copied as source):
   K5  Examples/OC/{cartpole,robotarm}/data/PDP_Neural_trial_0.mat -> k5_neural.npz
   K6  the reference's own LQR.lqrSolver / integrateAuxSys (imported unmodified under a casadi
       stub, oracle/ref_loader.py) run on auxiliary systems evaluated by the oracle -> k6_reference_lqr.npz
+  schema of the shipped result / demo / iodata .mat files -> schema_mat.json  (--schema: only this one)
 
 Usage:  python tests/golden/make_golden.py
 """
@@ -153,8 +154,47 @@ def k6():
     np.savez_compressed(os.path.join(HERE, "k6_reference_lqr.npz"), **out)
 
 
+
+
+def schema():
+    """Field names / dtypes / shapes of the `.mat` files the reference ships (first K entries only where a dimension
+    is the iteration count) -> schema_mat.json; pins pontryagin_differentiable_programming_b200/results_io.py."""
+    import json
+
+    def describe(path):
+        d = sio.loadmat(path)
+        out = {}
+        for k, v in d.items():
+            if k.startswith("__"):
+                continue
+            ent = {"dtype": str(v.dtype) if not v.dtype.names else "struct", "shape": list(v.shape)}
+            if v.dtype.names:
+                s = v[0, 0]
+                ent["fields"] = {n: {"dtype": str(s[n].dtype) if not s[n].dtype.names else "struct", "ndim": int(np.asarray(s[n]).ndim)}
+                                 for n in v.dtype.names}
+            elif v.dtype == object:
+                s = v[0, 0]
+                s = s[0, 0] if s.dtype.names and s.shape == (1, 1) else s
+                ent["fields"] = {n: {"dtype": str(np.asarray(s[n]).dtype), "ndim": int(np.asarray(s[n]).ndim)} for n in s.dtype.names}
+            out[k] = ent
+        return out
+    files = {"irl_results": "IRL/pendulum/data/PDP_results_trial_0.mat", "irl_demos": "IRL/pendulum/data/pendulum_demos.mat",
+             "sysid_results": "SysID/quadrotor/data/PDP_SysID_results_trial_0.mat", "sysid_iodata": "SysID/quadrotor/data/uav_iodata.mat",
+             "oc_results": "OC/rocket/data/PDP_OC_results_trial_0.mat"}
+    out = {}
+    for name, rel in files.items():
+        p = os.path.join(EX, rel)
+        if os.path.isfile(p):
+            out[name] = describe(p)
+    with open(os.path.join(HERE, "schema_mat.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
-    k1(); k2(); k3(); k4(); k5(); k6()
+    if "--schema" in sys.argv:          # only the .mat schema fixture
+        schema()
+    else:
+        k1(); k2(); k3(); k4(); k5(); k6(); schema()
     for f in sorted(os.listdir(HERE)):
-        if f.endswith(".npz"):
+        if f.endswith(".npz") or f.endswith(".json"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

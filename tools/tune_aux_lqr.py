@@ -14,12 +14,12 @@ sys.path.insert(0, ROOT)
 
 # every variant: keyword overrides of BASE (= the shipped configuration of engine.OCSystem)
 BASE = dict(chunk=8, warps_per_block=1, min_blocks=8, fwd_warps_per_block=1, fwd_min_blocks=8, keep_fg=True,
-            fast_rcp=True, early_solve=True, fwd_pack=3, fwd_chunk=10, bwd_pack=2, fwd_vec=-1, prefetch=2, prefetch_dist=2, inline_eval=-1, h_group=1)
+            fast_rcp=True, early_solve=True, fwd_pack=3, fwd_chunk=10, bwd_pack=2, fwd_vec=-1, prefetch=2, prefetch_dist=2, inline_eval=-1, h_group=1, prefetch_l1_lead=0)
 V1 = dict(bwd_pack=1, chunk=17, warps_per_block=4, min_blocks=3, keep_fg=True)     # one trajectory per warp
 VARIANTS = [
     V1,
     {},                                                                    # shipped: two trajectories per warp
-    dict(h_group=0), dict(early_solve=False), dict(h_group=0, early_solve=False), dict(chunk=10),
+    dict(prefetch_l1_lead=0), dict(prefetch_l1_lead=1), dict(prefetch_l1_lead=3), dict(prefetch_l1_lead=5),
 ]
 
 
