@@ -103,11 +103,19 @@ int pdp_lqr_dense(pdp_system_t* sys, int B, int H, const double* aux, const doub
 int pdp_eval_function(pdp_system_t* sys, int B, const double* const* inputs, const int* input_strides,
                       double* const* outputs, pdp_stream_t stream);
 
-/* One full PDP sweep = pdp_rollout_costate + pdp_aux_lqr on device buffers (the BASELINE metric's unit). */
+/* One full PDP sweep = pdp_rollout_costate + pdp_aux_lqr on device buffers (the BASELINE metric's unit).
+ * For large batches the aux-LQR phase is cut into sub-batches that alternate between two internal streams of the
+ * system (forked from / joined back into `stream` with events, so the call keeps its stream-ordered semantics and can
+ * be captured into a CUDA graph once the internal streams exist): the shared-memory-bound backward kernel of one
+ * sub-batch overlaps the HBM-bound forward kernel of the other.  Results are identical to the unsplit call. */
 int pdp_sweep(pdp_system_t* sys, int B, int H, const double* x0, const double* theta, int theta_stride,
               const double* U, double* X, double* Lam, double* cost, double* dXdtheta, double* dUdtheta,
               const double* Xref, const double* Uref, double* loss_dp, void* workspace, size_t ws_bytes,
               int* status, pdp_stream_t stream);
+
+/* Number of sub-batches pdp_sweep cuts its aux-LQR phase into: 0 = automatic (4 from 16384 trajectories, 2 from 8192,
+ * else 1), 1 = never split.  Concurrent pdp_sweep calls on one system serialise their (short) enqueue sequence. */
+int pdp_set_sweep_parts(pdp_system_t* sys, int parts);
 
 /* Dense auxiliary matrices for the legacy OCSys.getAuxSys return value (PDP/PDP.py:303-313).
  *   aux[B,H,NDENSE] with per-step layout [F n*n|G n*m|E n*r|Hxx|Hxu|Hxe|Hux m*n|Huu|Hue] row-major,

@@ -25,7 +25,7 @@ KIND_OC, KIND_SYSID, KIND_CP, KIND_LQR = 1, 2, 3, 4
 EXPORTS = ["pdp_load_system", "pdp_free_system", "pdp_system_dims", "pdp_last_error", "pdp_version",
            "pdp_workspace_bytes", "pdp_rollout_costate", "pdp_aux_lqr", "pdp_sweep", "pdp_aux_eval",
            "pdp_sens_fwd", "pdp_sweep_host", "pdp_lqr_dense", "pdp_eval_function", "pdp_aux_lqr_backward",
-           "pdp_aux_lqr_forward", "pdp_rollout_feedback"]
+           "pdp_aux_lqr_forward", "pdp_rollout_feedback", "pdp_set_sweep_parts"]
 
 
 def library_path():
@@ -71,6 +71,8 @@ def load_library(build_if_missing=True):
         lib.pdp_aux_lqr_forward.restype = i
         lib.pdp_sweep.argtypes = [vp, i, i, dp, dp, i, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp, sz, dp, vp]
         lib.pdp_sweep.restype = i
+        lib.pdp_set_sweep_parts.argtypes = [vp, i]
+        lib.pdp_set_sweep_parts.restype = i
         lib.pdp_aux_eval.argtypes = [vp, i, i, dp, dp, dp, dp, i, dp, dp, vp]
         lib.pdp_aux_eval.restype = i
         lib.pdp_sens_fwd.argtypes = [vp, i, i, dp, dp, i, dp, dp, dp, dp, dp, dp, dp, dp, vp]

@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 
 namespace {
@@ -49,6 +50,13 @@ struct pdp_system {
   fn_aux_lqr aux_lqr = nullptr;
   fn_sens sens = nullptr;
   fn_eval fneval = nullptr;
+  // pdp_sweep pipelining: sub-batches of the aux-LQR phase alternate between two internal streams so that the
+  // shared-memory-bound backward kernel of one sub-batch overlaps the HBM-bound forward kernel of the other
+  std::mutex mu;                                  // serialises the fork / join enqueue sequence
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  int side_dev = -1;
+  int sweep_parts = 0;                            // 0 = auto (by batch size), 1 = off, k = k sub-batches
   int kind() const { return info[0]; }
   int n() const { return info[1]; }
   int m() const { return info[2]; }
@@ -86,10 +94,45 @@ int pdp_load_system(const char* module_path, pdp_system_t** out) {
   return PDP_OK;
 }
 
+static void destroy_side(pdp_system* s) {
+  for (int k = 0; k < 2; ++k) {
+    if (s->side[k]) cudaStreamDestroy(s->side[k]);
+    if (s->ev_join[k]) cudaEventDestroy(s->ev_join[k]);
+    s->side[k] = nullptr;
+    s->ev_join[k] = nullptr;
+  }
+  if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+  s->ev_fork = nullptr;
+  s->side_dev = -1;
+}
+
+// internal streams / events of the current device, created on first use (never during a stream capture)
+static bool ensure_side(pdp_system* s, bool may_create) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  if (s->side_dev == dev) return true;
+  if (!may_create) return false;
+  destroy_side(s);
+  bool ok = cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  for (int k = 0; k < 2 && ok; ++k)
+    ok = cudaStreamCreateWithFlags(&s->side[k], cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&s->ev_join[k], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) { destroy_side(s); cudaGetLastError(); return false; }
+  s->side_dev = dev;
+  return true;
+}
+
 void pdp_free_system(pdp_system_t* sys) {
   if (!sys) return;
+  destroy_side(sys);
   if (sys->handle) dlclose(sys->handle);
   delete sys;
+}
+
+int pdp_set_sweep_parts(pdp_system_t* sys, int parts) {
+  if (!sys || parts < 0) return fail(PDP_ERR_ARG, "pdp_set_sweep_parts: bad argument");
+  sys->sweep_parts = parts;
+  return PDP_OK;
 }
 
 int pdp_system_dims(const pdp_system_t* sys, int* dims) {
@@ -219,6 +262,46 @@ int pdp_sweep(pdp_system_t* sys, int B, int H, const double* x0, const double* t
   if (!Lam) return fail(PDP_ERR_ARG, "pdp_sweep: Lam buffer required");
   int e = pdp_rollout_costate(sys, B, H, x0, theta, theta_stride, U, X, Lam, cost, nullptr, status, stream);
   if (e) return e;
+  int parts = sys->sweep_parts > 0 ? sys->sweep_parts : (B >= 16384 ? 4 : (B >= 8192 ? 2 : 1));
+  if (parts > B) parts = B;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (parts > 1) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); parts = 1; }
+    std::lock_guard<std::mutex> lock(sys->mu);
+    if (parts > 1 && !ensure_side(sys, cap == cudaStreamCaptureStatusNone)) parts = 1;
+    if (parts > 1) {
+      // same checks as pdp_aux_lqr, once for the whole batch; the sub-batches use disjoint slices of every buffer
+      if (!sys->aux_lqr || sys->kind() != PDP_KIND_OC)
+        return fail(PDP_ERR_UNSUPPORTED, "pdp_sweep: module has no fused aux-LQR kernel");
+      if (loss_dp && !Xref) return fail(PDP_ERR_ARG, "pdp_sweep: loss_dp needs Xref");
+      if (!workspace || ws_bytes < pdp_workspace_bytes(sys, PDP_OP_SWEEP, B, H))
+        return fail(PDP_ERR_WORKSPACE, "pdp_sweep: workspace too small");
+      const size_t n = sys->n(), m = sys->m(), r = sys->r(), g = sys->grec();
+      double* gains = reinterpret_cast<double*>(workspace);
+      cudaError_t ce = cudaEventRecord(sys->ev_fork, st);
+      for (int k = 0; k < 2 && ce == cudaSuccess; ++k) ce = cudaStreamWaitEvent(sys->side[k], sys->ev_fork, 0);
+      if (ce != cudaSuccess) return fail(PDP_ERR_CUDA, "pdp_sweep: %s", cudaGetErrorString(ce));
+      int err = 0;
+      for (int i = 0; i < parts && !err; ++i) {
+        const size_t lo = (size_t(B) * i) / parts, hi = (size_t(B) * (i + 1)) / parts;
+        err = sys->aux_lqr(int(hi - lo), H, X + lo * (H + 1) * n, U + lo * H * m, Lam + lo * H * n,
+                           theta + (theta_stride ? lo * size_t(theta_stride) : 0), theta_stride, nullptr, 0,
+                           dXdtheta ? dXdtheta + lo * (H + 1) * n * r : nullptr, dUdtheta ? dUdtheta + lo * H * m * r : nullptr,
+                           gains + lo * H * g, Xref ? Xref + lo * (H + 1) * n : nullptr, Uref ? Uref + lo * H * m : nullptr,
+                           loss_dp ? loss_dp + lo * (r + 1) : nullptr, nullptr, nullptr, 3, status ? status + lo : nullptr,
+                           sys->side[i & 1]);
+      }
+      // always join, also after a failed launch, so that the caller's stream stays ordered behind the side streams
+      for (int k = 0; k < 2; ++k) {
+        ce = cudaEventRecord(sys->ev_join[k], sys->side[k]);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(st, sys->ev_join[k], 0);
+        if (ce != cudaSuccess && !err) err = (int)ce;
+      }
+      if (err) return fail(PDP_ERR_CUDA, "pdp_sweep: CUDA error %d (%s)", err, cudaGetErrorString((cudaError_t)err));
+      return PDP_OK;
+    }
+  }
   return pdp_aux_lqr(sys, B, H, X, U, Lam, theta, theta_stride, nullptr, 0, dXdtheta, dUdtheta, Xref, Uref, loss_dp,
                      workspace, ws_bytes, status, stream);
 }

@@ -191,8 +191,13 @@ class OCSystem:
                                               _ptr(ws), ws.numel(), _ptr(status), st), "pdp_aux_lqr")
         return res
 
+    def set_sweep_parts(self, parts: int):
+        """Sub-batches ``pdp_sweep`` cuts its aux-LQR phase into (two internal streams): 0 = automatic, 1 = never."""
+        backend.check(self.handle.lib.pdp_set_sweep_parts(self.handle.ptr, int(parts)), "pdp_set_sweep_parts")
+
     def sweep(self, x0, theta, U, Xref=None, Uref=None, want_traj=True, status=None, out=None):
-        """One PDP sweep (the BASELINE metric's unit): rollout + costate + fused aux-LQR."""
+        """One PDP sweep (the BASELINE metric's unit): rollout + costate + fused aux-LQR.  Large batches are pipelined
+        inside the C ABI (sub-batches on two internal streams; identical results, see include/pdp_b200.h)."""
         require_cuda()
         dev = x0.device
         B, H = U.shape[0], U.shape[1]

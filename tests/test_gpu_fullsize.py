@@ -124,3 +124,29 @@ def test_empty_batch_and_status_flags():
     st = status.cpu().numpy()
     assert st[2] & 1 and not (st[[0, 1, 3, 4, 5]] & 1).any()
     assert torch.isfinite(res["dX"][[0, 1, 3, 4, 5]]).all() or (st[[0, 1, 3, 4, 5]] & 2).any()
+
+
+def test_pipelined_sweep_equals_the_unsplit_sweep_bit_for_bit():
+    """pdp_sweep cuts the aux-LQR phase of large batches into sub-batches on two internal streams; every output must
+    equal the unsplit call exactly (odd batch: uneven sub-batches), and the call must stay ordered in its stream."""
+    import bench
+    from pontryagin_differentiable_programming_b200 import systems
+    dev = _dev()
+    sys_ = systems.quadrotor_irl(0.1)
+    B, H = 16384 + 3, 20
+    x0, th, U, Xr, Ur = [torch.as_tensor(np.ascontiguousarray(a), device=dev) for a in bench.synth_quadrotor(B, H, seed=5)]
+    res = {}
+    try:
+        for parts in (1, 0, 3, 7):
+            sys_.set_sweep_parts(parts)
+            status = torch.zeros(B, dtype=torch.int32, device=dev)
+            out = sys_.sweep(x0, th, U, Xref=Xr, Uref=Ur, status=status)
+            # no synchronisation: the host copy below is ordered behind the sweep in the current stream
+            res[parts] = {k: v.clone() for k, v in out.items()}
+            res[parts]["status"] = status.clone()
+    finally:
+        sys_.set_sweep_parts(0)
+    torch.cuda.synchronize()
+    for parts in (0, 3, 7):
+        for k, v in res[1].items():
+            assert torch.equal(v, res[parts][k]), (parts, k)
