@@ -215,3 +215,64 @@ def test_sharded_gradient_allreduce_gloo_world2():
     for _, _, _, loss, dp, loss_ref, dp_ref in res:
         assert abs(loss - loss_ref) < 1e-14
         assert np.allclose(dp, dp_ref, atol=1e-14)
+
+
+def test_symbolic_warp_and_recovery_matrix_builders():
+    """ControlPlanning.warp_dynCost / warp_getAuxSys / recmat_recoveryMatrix (reference PDP.py:882-915, 940-957,
+    1039-1079): the composed interval dynamics / costs, their Jacobians and the recovery matrix dJ/d(stacked controls),
+    checked against the oracle's rollout cost at the expanded controls and against central differences."""
+    import numpy as np
+    from oracle import envs, pdp_oracle
+    from PDP import PDP
+    from JinEnv import JinEnv
+    env = JinEnv.CartPole()
+    env.initDyn(mc=0.1, mp=0.1, l=1)
+    env.initCost(wx=0.1, wq=0.6, wdx=0.1, wdq=0.1, wu=0.3)
+    cp = PDP.ControlPlanning()
+    cp.setStateVariable(env.X)
+    cp.setControlVariable(env.U)
+    dt, H = 0.05, 12
+    cp.setDyn(env.X + dt * env.f)
+    cp.setPathCost(env.path_cost)
+    cp.setFinalCost(env.final_cost)
+    cp.warp_init_step(H, time_grid=[0, 0.25, 0.6, 1.0])
+    assert list(cp.time_grid) == [0, 3, 7, 12] and cp.whorizon == 3
+    cp.warp_dynCost(cp.time_grid)
+    assert len(cp.wdyn_fns) == len(cp.wdfx_fns) == len(cp.wdcu_fns) == 3
+    rng = np.random.default_rng(0)
+    x0, Uw = 0.1 * rng.standard_normal(4), rng.standard_normal(3)
+    theta = rng.standard_normal(cp.n_auxvar)                     # polynomial policy parameters, (whorizon + 1) * m
+
+    def warped(Uw_):
+        x, c, xs = x0.copy(), 0.0, [x0.copy()]
+        for wt in range(3):
+            c += cp.wpath_cost_fns[wt](x, Uw_[wt:wt + 1]).full().item()
+            x = cp.wdyn_fns[wt](x, Uw_[wt:wt + 1]).full().ravel()
+            xs.append(x)
+        return c + cp.wfinal_cost_fn(x).full().item(), np.array(xs)
+
+    # the warped problem is the original rollout with piecewise-constant controls (oracle restatement of the rollout)
+    e = envs.cartpole(mc=0.1, mp=0.1, l=1, wx=0.1, wq=0.6, wdx=0.1, wdq=0.1, wu=0.3)
+    oc = pdp_oracle.build_oc(e, dt)
+    U_full = np.repeat(Uw, np.diff(cp.time_grid))[:, None]
+    X_ref, J_ref = oc.rollout(x0, U_full, np.ones(oc.r))
+    J, Xw = warped(Uw)
+    assert abs(J - float(J_ref)) < 1e-12 * abs(float(J_ref))
+    assert np.max(np.abs(Xw - np.asarray(X_ref)[cp.time_grid])) < 1e-13
+    # warped auxiliary system vs central differences of the composed dynamics
+    aux = cp.warp_getAuxSys(Xw, Uw[:, None], theta)
+    assert set(aux) == {"wdynF", "wdynG", "wdUx", "wdUe"} and len(aux["wdynF"]) == 3
+    h = 1e-6
+    for wt in range(3):
+        f = lambda x, u: cp.wdyn_fns[wt](x, u).full().ravel()
+        Ffd = np.stack([(f(Xw[wt] + h * np.eye(4)[i], Uw[wt:wt + 1]) - f(Xw[wt] - h * np.eye(4)[i], Uw[wt:wt + 1])) / (2 * h)
+                        for i in range(4)], axis=1)
+        Gfd = ((f(Xw[wt], Uw[wt:wt + 1] + h) - f(Xw[wt], Uw[wt:wt + 1] - h)) / (2 * h))[:, None]
+        assert np.max(np.abs(aux["wdynF"][wt] - Ffd)) < 1e-7 and np.max(np.abs(aux["wdynG"][wt] - Gfd)) < 1e-7
+        assert aux["wdUx"][wt].shape == (1, 4) and aux["wdUe"][wt].shape == (1, cp.n_auxvar)
+    # recovery matrix = dJ/d(stacked controls)
+    cp.recmat_recoveryMatrix(cp.whorizon)
+    assert cp.n_auxvar == 3
+    g = cp.recovery_matrix_fn(x0, Uw).full().ravel()
+    fd = np.array([(warped(Uw + h * np.eye(3)[i])[0] - warped(Uw - h * np.eye(3)[i])[0]) / (2 * h) for i in range(3)])
+    assert np.max(np.abs(g - fd)) < 1e-6 * np.max(np.abs(fd))
