@@ -40,19 +40,17 @@ class OCSystem:
     BWD_DEFAULTS = {2: dict(chunk=8, warps_per_block=1, min_blocks=8, keep_fg=True),
                     1: dict(chunk=17, warps_per_block=4, min_blocks=3, keep_fg=True)}
 
-    def __init__(self, state, control, auxvar, dyn, path_cost, final_cost, chunk=None, warps_per_block=None,
-                 min_blocks=None, fwd_warps_per_block=1, fwd_min_blocks=8, keep_fg=None, fast_rcp=True, early_solve=True,
-                 verbose=False, fwd_pack=0, fwd_chunk=0, bwd_pack=2, fwd_vec=-1, prefetch=2, prefetch_dist=2, inline_eval=-1, h_group=1, prefetch_l1_lead=0):
+    def __init__(self, state, control, auxvar, dyn, path_cost, final_cost, verbose=False, **kernel_options):
+        """``kernel_options``: keyword options of :class:`codegen.OCModuleSource` (``chunk``, ``warps_per_block``,
+        ``min_blocks``, ``keep_fg``, ``bwd_pack``, ``fwd_pack``, ``prefetch``, ... -- the A/B switches of
+        ``tools/tune_aux_lqr.py``); anything not given takes the measured default."""
         fits = state.numel() <= 16 and control.numel() + auxvar.numel() <= 16
-        bwd_pack = 2 if (int(bwd_pack) == 2 and fits) else 1
-        d = self.BWD_DEFAULTS[bwd_pack]
-        chunk = d["chunk"] if chunk is None else chunk
-        warps_per_block = d["warps_per_block"] if warps_per_block is None else warps_per_block
-        min_blocks = d["min_blocks"] if min_blocks is None else min_blocks
-        keep_fg = d["keep_fg"] if keep_fg is None else keep_fg
-        self.src = codegen.OCModuleSource(state, control, auxvar, dyn, path_cost, final_cost, chunk, warps_per_block,
-                                          min_blocks, fwd_warps_per_block, fwd_min_blocks, keep_fg, fast_rcp, early_solve,
-                                          fwd_pack, fwd_chunk, bwd_pack, fwd_vec, prefetch, prefetch_dist, inline_eval, h_group, prefetch_l1_lead)
+        opts = dict(fwd_warps_per_block=1, fwd_min_blocks=8, fast_rcp=True, early_solve=True)
+        opts.update({k: v for k, v in kernel_options.items() if v is not None})
+        opts["bwd_pack"] = 2 if (int(opts.get("bwd_pack", 2)) == 2 and fits) else 1
+        for k, v in self.BWD_DEFAULTS[opts["bwd_pack"]].items():
+            opts.setdefault(k, v)
+        self.src = codegen.OCModuleSource(state, control, auxvar, dyn, path_cost, final_cost, **opts)
         self.n, self.m, self.r = self.src.n, self.src.m, self.src.r
         self.module_path = build.compile_module(self.src.source(), self.src.key(), verbose=verbose)
         self._handle = None
