@@ -150,3 +150,23 @@ def test_pipelined_sweep_equals_the_unsplit_sweep_bit_for_bit():
     for parts in (0, 3, 7):
         for k, v in res[1].items():
             assert torch.equal(v, res[parts][k]), (parts, k)
+
+
+def test_both_backward_kernel_layouts_agree_on_the_gpu():
+    """The one-trajectory-per-warp backward kernel (fallback for systems whose stack does not fit two rows per team
+    lane, and the kernel of the generic dense LQR module) stays covered: same gains-driven outputs as the shipped
+    two-trajectory kernel on a mid-size batch with an odd count."""
+    import bench
+    from tools.tune_aux_lqr import make, V1
+    dev = _dev()
+    B, H = 1027, 50
+    x0, th, U, Xr, Ur = [torch.as_tensor(np.ascontiguousarray(a), device=dev) for a in bench.synth_quadrotor(B, H, seed=9)]
+    outs = []
+    for kw in ({}, V1):
+        s = make(**kw)
+        assert s.src.bwd_pack == (1 if kw else 2)
+        outs.append(s.sweep(x0, th, U, Xref=Xr, Uref=Ur))
+    torch.cuda.synchronize()
+    for k in ("dX", "dU", "loss_dp", "X", "Lam"):
+        a, b = outs[0][k], outs[1][k]
+        assert float((a - b).abs().max()) <= 1e-11 * float(b.abs().max()), k

@@ -85,3 +85,7 @@ cpl._cp_system()
 for nm in ("dfx_fn", "dfu_fn", "dpolicy_dx_fn", "dpolicy_de_fn"):
     engine.GpuFunction(getattr(cpl, nm))
 print("legacy-chain modules built")
+
+# the one-trajectory-per-warp build of the quadrotor module (tests/test_gpu_fullsize.py compares the two layouts)
+from tools.tune_aux_lqr import make, V1  # noqa: E402
+print("quadrotor, one trajectory per warp", make(**V1).module_path)
