@@ -16,6 +16,9 @@ import bench  # noqa: E402
 from tools.tune_aux_lqr import make  # noqa: E402
 
 
+PARTS = ((1, 1), (2, 2), (3, 2), (4, 2), (5, 2), (6, 2), (7, 2), (3, 3), (6, 3), (8, 2))     # (sub-batches, streams)
+
+
 def main():
     dev = torch.device("cuda:0")
     B, H = 16384, 50
@@ -26,7 +29,7 @@ def main():
            "dU": torch.empty((B, H, m, r), dtype=torch.float64, device=dev), "loss_dp": torch.empty((B, r + 1), dtype=torch.float64, device=dev)}
     rows = []
     ref = None
-    for parts, nslots in ((1, 1), (2, 2), (4, 2), (8, 2), (8, 3), (16, 2), (16, 3), (16, 4), (32, 2), (32, 4)):
+    for parts, nslots in PARTS:
         systems_ = [make() for _ in range(nslots)]
         for s_ in systems_:
             s_._handle = None                                  # separate handles -> separate workspaces
