@@ -32,9 +32,8 @@ class SensModuleSource:
     def __init__(self, kind: int, state: SX, control: SX, auxvar: SX, dyn: SX,
                  policy: Optional[SX] = None, tvar: Optional[SX] = None,
                  path_cost: Optional[SX] = None, final_cost: Optional[SX] = None,
-                 max_group_cols: int = 12, block: int = 64, prefetch_dist: int = 0):
+                 max_group_cols: int = 12, block: int = 64):
         self.kind = kind
-        self.prefetch_dist = int(prefetch_dist)       # > 0: prefetch.global.L2 of the input / observation rows t + d
         self.x, self.u, self.th = state, control, auxvar
         self.n, self.m, self.r = state.numel(), control.numel(), auxvar.numel()
         n, m, r = self.n, self.m, self.r
@@ -242,8 +241,7 @@ class SensModuleSource:
         hdr = ["// GENERATED by pontryagin_differentiable_programming_b200/codegen_sens.py -- do not edit",
                "#include <cuda_runtime.h>", "#include <math.h>", "#include <stdint.h>",
                "#define PDP_N %d" % n, "#define PDP_M %d" % m, "#define PDP_R %d" % r, "#define PDP_KIND %d" % self.kind,
-               "#define PDP_NG %d" % len(self.groups), "#define PDP_GMAX %d" % self.gmax, "#define PDP_BLOCK %d" % self.block,
-               "#define PDP_SPF %d" % max(0, getattr(self, "prefetch_dist", 0))]
+               "#define PDP_NG %d" % len(self.groups), "#define PDP_GMAX %d" % self.gmax, "#define PDP_BLOCK %d" % self.block]
         body = []
         body.append(r'''
 // One thread per (trajectory, column group); the group's columns of X_t (n x r) live in shared memory.
@@ -269,13 +267,6 @@ pdp_k_sens_fwd(int B, int H, const double* __restrict__ x0, const double* __rest
             body.append("    #pragma unroll 1")
             body.append("    for (int t = 0; t < H; ++t) {")
             body.append("      const double tt = (double)t; (void)tt;")
-            body.append("#if PDP_SPF")
-            body.append("      if (t + PDP_SPF < H) {     // rows a later step reads (thread-private, latency-exposed)")
-            if not cp:
-                body.append("        { const double* p = inputs + ((size_t)b * H + t + PDP_SPF) * %d; asm volatile(\"prefetch.global.L2 [%%0];\" :: \"l\"(p)); asm volatile(\"prefetch.global.L2 [%%0];\" :: \"l\"(p + %d)); }" % (m, m - 1))
-            body.append("        if (Xobs) { const double* p = Xobs + ((size_t)b * (H + 1) + t + PDP_SPF) * %d; asm volatile(\"prefetch.global.L2 [%%0];\" :: \"l\"(p)); asm volatile(\"prefetch.global.L2 [%%0];\" :: \"l\"(p + %d)); }" % (n, n - 1))
-            body.append("      }")
-            body.append("#endif")
             if not cp:
                 body.append("      " + " ".join("const double u%d = inputs[((size_t)b * H + t) * %d + %d];" % (a, m, a) for a in range(m)))
             body.append(self._group_step(g, cols))

@@ -79,11 +79,6 @@ def main():
         ms = timeit(lambda: sv.step(inputs, Xobs, th))
         rows.append({"config": "C5 variant group_cols=%d block=%d" % (gc, blk), "ms": ms, "sweeps_per_s": B / ms * 1e3,
                      "alg_GBps": alg * B / ms / 1e6})
-    for pd in (2, 4, 8):        # software prefetch distance of the input / observation rows
-        sv = engine.SysIDSystem(env.X, env.U, env.dyn_auxvar, env.X + 0.1 * env.f, prefetch_dist=pd)
-        ms = timeit(lambda: sv.step(inputs, Xobs, th))
-        rows.append({"config": "C5 variant prefetch_dist=%d" % pd, "ms": ms, "sweeps_per_s": B / ms * 1e3,
-                     "alg_GBps": alg * B / ms / 1e6})
     for r_ in rows:
         print(json.dumps(r_))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
