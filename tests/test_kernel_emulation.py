@@ -123,3 +123,33 @@ def test_emulated_rollout_costate_kernel_matches_oracle(env):
             assert np.max(np.abs(X[b] - Xr)) < 1e-12
             assert _rel(L[b], Lr) < 1e-12
             assert abs(cost[b] - float(c)) < 1e-11 * max(1.0, abs(float(c)))
+
+
+@pytest.mark.parametrize("env", ["quadrotor", "pendulum"])
+def test_emulated_newton_module_layouts_agree(env):
+    """The one-column "Newton module" of the batched ocSolver (Hue := dH/du, E = Hxe = 0, theta extended by the
+    Hessian switch s and the Levenberg shift mu) through both backward-kernel layouts: same gains, same (dx, du)."""
+    from pontryagin_differentiable_programming_b200 import codegen, systems
+    s = systems.OC_BUILDERS[env](0.1).src
+    rng = np.random.default_rng(1)
+    B, H = 3, 13
+    res = {}
+    for pack, kw in ((2, dict(chunk=8, warps_per_block=1, min_blocks=8, keep_fg=True)),
+                     (1, dict(chunk=5, warps_per_block=2, min_blocks=1, keep_fg=True))):
+        src = codegen.NewtonModuleSource(s.x, s.u, s.th, s.dyn, s.c, s.h, fast_rcp=True, early_solve=True, bwd_pack=pack, **kw)
+        assert src.bwd_pack == pack and src.r == 1 and src.nth == s.r + 2
+        if pack == 2:
+            X = rng.standard_normal((B, H + 1, src.n)) * 0.3
+            if env == "quadrotor":
+                X[:, :, 6] += 1.0
+            U = rng.standard_normal((B, H, src.m)) * 0.3 + (2.5 if env == "quadrotor" else 0.0)
+            L = rng.standard_normal((B, H, src.n)) * 0.1
+            th = np.concatenate([np.tile(np.abs(rng.standard_normal(src.nth - 2)) + 0.5, (B, 1)), np.zeros((B, 1)),
+                                 np.full((B, 1), 0.5)], axis=1)         # Gauss-Newton Hessians, mu = 0.5
+        emu = warp_emu.Emulator(src)
+        g, st = emu.backward(X, U, L, th)
+        dX, dU, _, _ = emu.forward(X, U, th, g)
+        assert int(st.max()) == 0 and not np.isnan(g).any() and np.isfinite(dU).all()
+        res[pack] = (g, dX, dU)
+    for a, b in zip(res[1], res[2]):
+        assert _rel(a, b) < 1e-11
