@@ -621,30 +621,40 @@ class OCModuleSource:
         """Two-trajectory kernel: pack four 8-bit Hamiltonian slot indices per register (needs < 256 slots)."""
         return self.nvar <= 255
 
-    def _backward_step2(self) -> str:
-        """Riccati step of the two-trajectories-per-warp kernel: team lane tl owns stack rows tl (slot 0: P) and
-        n + tl (slot 1: control rows, then the columns of W).  Same phases A-E as :meth:`_backward_step`."""
+    def _h_init_lines(self, L, ind, slots):
+        """q<slot>_<l> = Hstack entry of the lane's row (column-coloured loads, see _h_column_groups)."""
+        nm = self.n + self.m
+        if self._hidx8() and self.h_groups is not None:
+            assigned = set()
+            for k, (sl, g) in enumerate(self._h_loads()):
+                if sl not in slots:
+                    continue
+                idx = "(ho%d >> %d) & 0xffu" % (k // 4, 8 * (k % 4))
+                if len(g) == 1:
+                    L.append(ind + "q%d_%d = ar[%s];" % (sl, g[0], idx))
+                else:
+                    c = self._h_multi_index(sl, g)
+                    L.append(ind + "{ const double hv = ar[%s]; const unsigned cd = (hc%d >> %d) & 0xfu;" % (idx, c // 8, 4 * (c % 8)))
+                    for pos, l in enumerate(g):
+                        L.append(ind + "  q%d_%d = (cd == %du) ? hv : 0.0;" % (sl, l, pos))
+                    L.append(ind + "}")
+                assigned |= {(sl, l) for l in g}
+            for sl in slots:
+                for l in range(nm):
+                    if (sl, l) not in assigned:
+                        L.append(ind + "q%d_%d = 0.0;" % (sl, l))
+        else:
+            for l in range(nm):
+                if 0 in slots:
+                    L.append(ind + "q0_%d = ar[ho%d & 0xffffu];" % (l, l))
+                if 1 in slots:
+                    L.append(ind + "q1_%d = ar[ho%d >> 16];" % (l, l))
+
+    def _phase_c_joint(self, L, ind):
+        """Phases B(pick-up) / C / first half of D for both slots together: one operand load feeds two FMAs."""
         n, m, r, ns = self.n, self.m, self.r, self.ns
         nm = n + m
-        L: List[str] = []
-        ind = "      "
-        L.append(ind + "// A: Z(i,:) = P(i,:) * [F|G|E]  -- structural non-zeros only; each half-warp reads its own trajectory's slots")
-        L.append(ind + "double " + ", ".join("z%d" % j for j in range(ns)) + ";")
-        needed = {e[1] for row in self.S_ent for e in row if e[0] == "v"}
-        load = _SlotLoader(L, "ar", needed, ind, "sa")
-        acc = _Acc("z", ns, L, ind)
-        for k in range(n):
-            for j in range(ns):
-                acc.add(j, "y0_%d" % k, self.S_ent[k][j], load)
-        acc.finish()
-        L.append(ind + "// B: transpose through shared memory: slot 0 picks up column tl of Z, slot 1 column n + tl (+ its W column)")
-        zero_cols = self._zero_z_columns()
-        L.append(ind + "if (tl < %d) {" % n)
-        for j in range(ns):
-            if j not in zero_cols:
-                L.append(ind + "  ZT[%d + tl] = z%d;" % (j * self.ldz, j))
-        L.append(ind + "}")
-        L.append(ind + "__syncwarp();")
+        load = self._a_loader
         L.append(ind + "double " + ", ".join("c0_%d, c1_%d" % (k, k) for k in range(n)) + ";")
         L.append(ind + "{ const double* zr = ZT + zr0 * %d;" % self.ldz)
         for k in range(n):
@@ -660,27 +670,7 @@ class OCModuleSource:
         L.append(ind + "}")
         L.append(ind + "// C: Q(j,:) = Hstack(j,:) + Z(:,j)^T [F|G] for both rows (one operand load, two FMAs)")
         L.append(ind + "double " + ", ".join("q0_%d, q1_%d" % (l, l) for l in range(nm)) + ";")
-        if self._hidx8() and self.h_groups is not None:
-            # one load per (slot, column group); a lane whose row has no entry in the group reads the zero slot
-            assigned = set()
-            for k, (sl, g) in enumerate(self._h_loads()):
-                idx = "(ho%d >> %d) & 0xffu" % (k // 4, 8 * (k % 4))
-                if len(g) == 1:
-                    L.append(ind + "q%d_%d = ar[%s];" % (sl, g[0], idx))
-                else:
-                    c = self._h_multi_index(sl, g)
-                    L.append(ind + "{ const double hv = ar[%s]; const unsigned cd = (hc%d >> %d) & 0xfu;" % (idx, c // 8, 4 * (c % 8)))
-                    for pos, l in enumerate(g):
-                        L.append(ind + "  q%d_%d = (cd == %du) ? hv : 0.0;" % (sl, l, pos))
-                    L.append(ind + "}")
-                assigned |= {(sl, l) for l in g}
-            for sl in (0, 1):
-                for l in range(nm):
-                    if (sl, l) not in assigned:
-                        L.append(ind + "q%d_%d = 0.0;" % (sl, l))
-        else:
-            for l in range(nm):
-                L.append(ind + "q0_%d = ar[ho%d & 0xffffu]; q1_%d = ar[ho%d >> 16];" % (l, l, l, l))
+        self._h_init_lines(L, ind, (0, 1))
         if not getattr(self, "keep_fg", True):
             needed = {self.S_ent[k][l][1] for k in range(n) for l in range(nm) if self.S_ent[k][l][0] == "v"}
             load = _SlotLoader(L, "ar", needed, ind, "sc")
@@ -709,6 +699,34 @@ class OCModuleSource:
             L.append(ind + "  QUU[tl * %d + %d] = q1_%d;" % (m, a, n + a))
         L.append(ind + "}")
         L.append(ind + "__syncwarp();")
+        return late_lines
+
+    def _backward_step2(self) -> str:
+        """Riccati step of the two-trajectories-per-warp kernel: team lane tl owns stack rows tl (slot 0: P) and
+        n + tl (slot 1: control rows, then the columns of W).  Same phases A-E as :meth:`_backward_step`."""
+        n, m, r, ns = self.n, self.m, self.r, self.ns
+        nm = n + m
+        L: List[str] = []
+        ind = "      "
+        L.append(ind + "// A: Z(i,:) = P(i,:) * [F|G|E]  -- structural non-zeros only; each half-warp reads its own trajectory's slots")
+        L.append(ind + "double " + ", ".join("z%d" % j for j in range(ns)) + ";")
+        needed = {e[1] for row in self.S_ent for e in row if e[0] == "v"}
+        load = _SlotLoader(L, "ar", needed, ind, "sa")
+        self._a_loader = load
+        acc = _Acc("z", ns, L, ind)
+        for k in range(n):
+            for j in range(ns):
+                acc.add(j, "y0_%d" % k, self.S_ent[k][j], load)
+        acc.finish()
+        L.append(ind + "// B: transpose through shared memory: slot 0 picks up column tl of Z, slot 1 column n + tl (+ its W column)")
+        zero_cols = self._zero_z_columns()
+        L.append(ind + "if (tl < %d) {" % n)
+        for j in range(ns):
+            if j not in zero_cols:
+                L.append(ind + "  ZT[%d + tl] = z%d;" % (j * self.ldz, j))
+        L.append(ind + "}")
+        L.append(ind + "__syncwarp();")
+        late_lines = self._phase_c_joint(L, ind)
         self._ldlt_lines(L, ind, late_lines)
         self._solve_lines(L, ind, ["q0_%d" % (n + i) for i in range(m)], "0")
         self._solve_lines(L, ind, ["q1_%d" % (n + i) for i in range(m)], "1")
