@@ -153,3 +153,24 @@ def test_emulated_newton_module_layouts_agree(env):
         res[pack] = (g, dX, dU)
     for a, b in zip(res[1], res[2]):
         assert _rel(a, b) < 1e-11
+
+
+@pytest.mark.parametrize("env,dims", [("quadrotor", (13, 4, 9)), ("pendulum", (2, 1, 5))])
+def test_emulated_dense_lqr_kernels_reproduce_the_reference_lqrsolver(env, dims):
+    """K6 on the CPU: the generic dense LQR module (the kernels behind the drop-in ``LQR.lqrSolver``) fed with the
+    auxiliary matrices of the golden file must reproduce the output of the reference's OWN ``LQR.lqrSolver``
+    (PDP.py:446-615, run unmodified by tests/golden/make_golden.py) -- literal inv(I+PR) form there, stacked standard
+    form with LDL^T here."""
+    from pontryagin_differentiable_programming_b200 import codegen
+    n, m, r = dims
+    g = np.load(os.path.join(G, "k6_reference_lqr.npz"))
+    H = g[env + "_dynF"].shape[0]
+    aux = np.concatenate([g[env + "_" + k].reshape(H, -1)
+                          for k in ("dynF", "dynG", "dynE", "Hxx", "Hxu", "Hxe", "Hux", "Huu", "Hue")], axis=1)[None]
+    term = np.concatenate([g[env + "_hxx"].reshape(-1), g[env + "_hxe"].reshape(-1)])[None]
+    emu = warp_emu.Emulator(codegen.LQRModuleSource(n, m, r))
+    gains, st = emu.backward_dense(aux, term)
+    dX, dU, st2 = emu.forward_dense(aux, gains)
+    assert int(st.max()) == 0 and int(st2.max()) == 0
+    assert _rel(dX[0], g[env + "_dX"]) < 1e-11
+    assert _rel(dU[0], g[env + "_dU"]) < 1e-11

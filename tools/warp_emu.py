@@ -66,7 +66,7 @@ static inline int atomicOr(int* p, int v) { return __sync_fetch_and_or(p, v); }
 DRIVER = r'''
 struct emu_args {
   int kernel, B, H, theta_stride, x0a_stride;
-  const double *X, *U, *Lam, *theta, *X0a, *Xref, *Uref;
+  const double *X, *U, *Lam, *theta, *X0a, *Xref, *Uref, *auxrec, *termrec;
   double *gains, *dX, *dU, *loss_dp;
   int* status;
   unsigned bx, tx0, bdim;
@@ -78,10 +78,10 @@ static void* emu_lane(void* p) {
   blockIdx.x = EA.bx; blockIdx.y = blockIdx.z = 0;
   blockDim.x = EA.bdim; blockDim.y = blockDim.z = 1;
   if (EA.kernel == 0)
-    EMU_BWD_KERNEL(EA.B, EA.H, EA.X, EA.U, EA.Lam, EA.theta, EA.theta_stride, EA.gains, nullptr, nullptr, EA.status);
+    EMU_BWD_KERNEL(EA.B, EA.H, EA.X, EA.U, EA.Lam, EA.theta, EA.theta_stride, EA.gains, EA.auxrec, EA.termrec, EA.status);
   else
     pdp_k_aux_lqr_fwd(EA.B, EA.H, EA.X, EA.U, EA.theta, EA.theta_stride, EA.X0a, EA.x0a_stride, EA.dX, EA.dU, EA.gains,
-                      EA.Xref, EA.Uref, EA.loss_dp, nullptr, EA.status);
+                      EA.Xref, EA.Uref, EA.loss_dp, EA.auxrec, EA.status);
   return nullptr;
 }
 static void emu_run(unsigned nblocks, unsigned warps_per_block) {
@@ -96,8 +96,9 @@ static void emu_run(unsigned nblocks, unsigned warps_per_block) {
   pthread_barrier_destroy(&emu_bar);
 }
 extern "C" void emu_backward(int B, int H, const double* X, const double* U, const double* Lam, const double* theta,
-                             int theta_stride, double* gains, int* status) {
+                             int theta_stride, double* gains, int* status, const double* auxrec, const double* termrec) {
   memset(&EA, 0, sizeof(EA));
+  EA.auxrec = auxrec; EA.termrec = termrec;
   EA.kernel = 0; EA.B = B; EA.H = H; EA.X = X; EA.U = U; EA.Lam = Lam; EA.theta = theta; EA.theta_stride = theta_stride;
   EA.gains = gains; EA.status = status;
   const unsigned per_block = EMU_BWD_TRAJ_PER_BLOCK;
@@ -105,8 +106,9 @@ extern "C" void emu_backward(int B, int H, const double* X, const double* U, con
 }
 extern "C" void emu_forward(int B, int H, const double* X, const double* U, const double* theta, int theta_stride,
                             const double* X0a, int x0a_stride, double* dX, double* dU, const double* gains,
-                            const double* Xref, const double* Uref, double* loss_dp, int* status) {
+                            const double* Xref, const double* Uref, double* loss_dp, int* status, const double* auxrec) {
   memset(&EA, 0, sizeof(EA));
+  EA.auxrec = auxrec;
   EA.kernel = 1; EA.B = B; EA.H = H; EA.X = X; EA.U = U; EA.theta = theta; EA.theta_stride = theta_stride;
   EA.X0a = X0a; EA.x0a_stride = x0a_stride; EA.dX = dX; EA.dU = dU; EA.gains = (double*)gains;
   EA.Xref = Xref; EA.Uref = Uref; EA.loss_dp = loss_dp; EA.status = status;
@@ -187,6 +189,26 @@ class Emulator:
                              self._p(dHu), self._p(status))
         return X, Lam, cost, dHu
 
+    def backward_dense(self, aux, term):
+        """Generic dense LQR module: aux[B,H,NDENSE] (per step [F|G|E|Hxx|Hxu|Hxe|Hux|Huu|Hue] row-major), term[B,n*n+n*r]."""
+        aux, term = np.ascontiguousarray(aux, dtype=np.float64), np.ascontiguousarray(term, dtype=np.float64)
+        B, H = aux.shape[0], aux.shape[1]
+        gains = np.full((B, H, self.grec), np.nan)
+        status = np.zeros(B, dtype=np.int32)
+        self.lib.emu_backward(B, H, None, None, None, None, 0, self._p(gains), self._p(status), self._p(aux), self._p(term))
+        return gains, status
+
+    def forward_dense(self, aux, gains, X0=None):
+        aux, gains = np.ascontiguousarray(aux, dtype=np.float64), np.ascontiguousarray(gains, dtype=np.float64)
+        B, H = aux.shape[0], aux.shape[1]
+        dX = np.full((B, H + 1, self.n, self.r), np.nan)
+        dU = np.full((B, H, self.m, self.r), np.nan)
+        status = np.zeros(B, dtype=np.int32)
+        X0 = None if X0 is None else np.ascontiguousarray(X0, dtype=np.float64)
+        self.lib.emu_forward(B, H, None, None, None, 0, self._p(X0), 0 if X0 is None or X0.ndim == 2 else 1, self._p(dX),
+                             self._p(dU), self._p(gains), None, None, None, self._p(status), self._p(aux))
+        return dX, dU, status
+
     def backward(self, X, U, Lam, theta):
         B, H = U.shape[0], U.shape[1]
         X, U, Lam = (np.ascontiguousarray(a, dtype=np.float64) for a in (X, U, Lam))
@@ -195,7 +217,7 @@ class Emulator:
         gains = np.full((B, H, self.grec), np.nan)
         status = np.zeros(B, dtype=np.int32)
         self.lib.emu_backward(B, H, self._p(X), self._p(U), self._p(Lam), self._p(theta), ts, self._p(gains),
-                              self._p(status))
+                              self._p(status), None, None)
         return gains, status
 
     def forward(self, X, U, theta, gains, Xref=None, Uref=None):
@@ -213,5 +235,5 @@ class Emulator:
             Uref = None if Uref is None else np.ascontiguousarray(Uref, dtype=np.float64)
             ldp = np.full((B, r + 1), np.nan)
         self.lib.emu_forward(B, H, self._p(X), self._p(U), self._p(theta), ts, None, 0, self._p(dX), self._p(dU),
-                             self._p(gains), self._p(Xref), self._p(Uref), self._p(ldp), self._p(status))
+                             self._p(gains), self._p(Xref), self._p(Uref), self._p(ldp), self._p(status), None)
         return dX, dU, ldp, status
