@@ -174,3 +174,56 @@ def test_emulated_dense_lqr_kernels_reproduce_the_reference_lqrsolver(env, dims)
     assert int(st.max()) == 0 and int(st2.max()) == 0
     assert _rel(dX[0], g[env + "_dX"]) < 1e-11
     assert _rel(dU[0], g[env + "_dU"]) < 1e-11
+
+
+def test_emulated_sysid_kernel_matches_k1_golden_and_oracle():
+    """pdp_k_sens_fwd (SysID kind) on the CPU: the rollout at the true parameter reproduces the shipped
+    uav_iodata.mat states (K1), and off the optimum loss / half-gradient / sensitivities equal the oracle's
+    restatement of SysID.step (PDP.py:1261-1296)."""
+    from pontryagin_differentiable_programming_b200 import systems
+    g = np.load(os.path.join(G, "k1_iodata.npz"))
+    sys_ = systems.quadrotor_sysid(0.1)
+    inputs, states = g["quadrotor_inputs"][:3], g["quadrotor_states"][:3]
+    theta_true = g["quadrotor_true_parameter"]
+    emu = warp_emu.SensEmulator(sys_.src)
+    H = inputs.shape[1]
+    out = emu.run(states[:, 0], theta_true, H, inputs=inputs, Xobs=states)
+    assert np.max(np.abs(out["X"] - states)) < 1e-12 and np.max(np.abs(out["loss_dp"][:, 0])) < 1e-20
+    theta = theta_true + np.array([0.1, -0.2, 0.15, 0.2, -0.05])
+    e = envs.quadrotor(c=0.01)
+    sid = pdp_oracle.OracleSysID(e["X"], e["U"], e["dyn_params"], e["X"] + 0.1 * e["f"])
+    out = emu.run(states[:, 0], theta, H, inputs=inputs, Xobs=states)
+    loss_ref, dp_ref = sid.step(list(inputs), list(states), theta)
+    assert abs(out["loss_dp"][:, 0].mean() - loss_ref) < 1e-12 * loss_ref
+    assert _rel(out["loss_dp"][:, 1:].mean(axis=0), dp_ref) < 1e-11
+    for b in range(inputs.shape[0]):
+        X = sid.integrateDyn(states[b, 0], inputs[b], theta)
+        assert _rel(out["X"][b], X) < 1e-13
+        assert _rel(out["dX"][b], np.stack(sid.sens(X, inputs[b], theta))) < 1e-12
+
+
+@pytest.mark.parametrize("policy", ["poly", "neural"])
+def test_emulated_controlplanning_kernel_matches_oracle(policy):
+    """pdp_k_sens_fwd (ControlPlanning kind) on the CPU vs the oracle's ControlPlanning.step (PDP.py:850-878): policy
+    rollout, forward sensitivities of states and controls, cost and its gradient (r = 6 polynomial / r = 45 MLP)."""
+    from pontryagin_differentiable_programming_b200 import systems
+    H, dt = 20, 0.05
+    sys_ = systems.cartpole_cp(policy, H, dt)
+    e = envs.cartpole(mc=0.1, mp=0.1, l=1, wx=0.1, wq=0.6, wdx=0.1, wdq=0.1, wu=0.3)
+    cp = pdp_oracle.OracleCP(e["X"], e["U"], e["X"] + dt * e["f"], e["path_cost"], e["final_cost"])
+    if policy == "poly":
+        cp.set_poly(np.linspace(0, H, 6))
+    else:
+        cp.set_neural([4, 4])
+    assert cp.r == sys_.r
+    rng = np.random.default_rng(5)
+    B = 3
+    x0 = 0.1 * rng.standard_normal((B, 4))
+    theta = (1.0 if policy == "poly" else 0.5) * rng.standard_normal((B, cp.r))
+    out = warp_emu.SensEmulator(sys_.src).run(x0, theta, H, policy=True)
+    for b in range(B):
+        cost, gref, X, U, dX, dU = cp.step(x0[b], H, theta[b], return_traj=True)
+        assert _rel(out["X"][b], X) < 1e-11 and _rel(out["U"][b], U) < 1e-11
+        assert abs(out["loss_dp"][b, 0] - cost) < 1e-11 * abs(cost)
+        assert _rel(out["dX"][b], dX) < 1e-10 and _rel(out["dU"][b], dU) < 1e-10
+        assert _rel(out["loss_dp"][b, 1:], gref) < 1e-10

@@ -134,9 +134,12 @@ _RCP = re.compile(r'asm\("rcp\.approx\.ftz\.f64 %0, %1;" : "=d"\((\w+)\) : "d"\(
 def translate(cuda_source: str) -> str:
     """Generated CUDA translation unit -> C++ the emulator can compile (kernels + device functions only)."""
     cut = cuda_source.find("// Host-side launchers")
+    if cut >= 0:
+        cut = cuda_source.rfind("// ====", 0, cut)
+    else:
+        cut = cuda_source.find('extern "C" void pdpmod_info')      # sensitivity modules: launchers follow the kernel
     if cut < 0:
         raise ValueError("launcher marker not found in the generated source")
-    cut = cuda_source.rfind("// ====", 0, cut)
     body = cuda_source[:cut]
     body = body.replace("#include <cuda_runtime.h>", "")
     body = _RCP.sub(lambda mo: "%s = 1.0 / %s;" % (mo.group(1), mo.group(2)), body)
@@ -237,3 +240,57 @@ class Emulator:
         self.lib.emu_forward(B, H, self._p(X), self._p(U), self._p(theta), ts, None, 0, self._p(dX), self._p(dU),
                              self._p(gains), self._p(Xref), self._p(Uref), self._p(ldp), self._p(status), None)
         return dX, dU, ldp, status
+
+
+SENS_DRIVER = r'''
+// pdp_k_sens_fwd: one thread per (trajectory, column group), no warp-level primitives: threads run one after the other
+extern "C" void emu_sens(int B, int H, const double* x0, const double* theta, int theta_stride, const double* inputs,
+                         const double* Xobs, double* X, double* Uout, double* dX, double* dU, double* loss_dp, int* status) {
+  for (int g = 0; g < PDP_NG; ++g)
+    for (int b = 0; b < B; ++b) {
+      threadIdx.x = b % PDP_BLOCK; blockIdx.x = b / PDP_BLOCK; blockIdx.y = g; blockDim.x = PDP_BLOCK;
+      pdp_k_sens_fwd(B, H, x0, theta, theta_stride, inputs, Xobs, X, Uout, dX, dU, loss_dp, status);
+    }
+}
+'''
+
+
+class SensEmulator:
+    """SysID / ControlPlanning forward-sensitivity module (codegen_sens.SensModuleSource) on the CPU."""
+
+    def __init__(self, src):
+        self.n, self.m, self.r = src.n, src.m, src.r
+        cpp = PREAMBLE + "static inline double atomicAdd(double* p, double v) { double o = *p; *p += v; return o; }\n" + \
+            translate(src.source()) + SENS_DRIVER
+        key = hashlib.sha256(cpp.encode()).hexdigest()[:16]
+        d = os.path.join(tempfile.gettempdir(), "pdp_warp_emu")
+        os.makedirs(d, exist_ok=True)
+        so = os.path.join(d, "emu_%s.so" % key)
+        if not os.path.isfile(so):
+            cc = os.path.join(d, "emu_%s.cpp" % key)
+            with open(cc, "w") as f:
+                f.write(cpp)
+            p = subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-w", "-ffp-contract=off",
+                                "-o", so + ".tmp", cc], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            if p.returncode != 0:
+                raise RuntimeError("g++ failed on the emulated kernel source (%s):\n%s" % (cc, p.stdout[-6000:]))
+            os.replace(so + ".tmp", so)
+        self.lib = ctypes.CDLL(so)
+
+    def run(self, x0, theta, H, inputs=None, Xobs=None, policy=False):
+        """-> X[B,H+1,n], U[B,H,m] (policy modules), dX[B,H+1,n,r], dU[B,H,m,r] (policy), loss_dp[B,r+1]."""
+        p = Emulator._p
+        x0 = np.ascontiguousarray(np.atleast_2d(x0), dtype=np.float64)
+        B = x0.shape[0]
+        theta = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
+        ts = 0 if theta.shape[0] == 1 else theta.shape[1]
+        inputs = None if inputs is None else np.ascontiguousarray(inputs, dtype=np.float64)
+        Xobs = None if Xobs is None else np.ascontiguousarray(Xobs, dtype=np.float64)
+        X = np.full((B, H + 1, self.n), np.nan)
+        dX = np.full((B, H + 1, self.n, self.r), np.nan)
+        Uo = np.full((B, H, self.m), np.nan) if policy else None
+        dU = np.full((B, H, self.m, self.r), np.nan) if policy else None
+        ldp = np.zeros((B, self.r + 1))
+        status = np.zeros(B, dtype=np.int32)
+        self.lib.emu_sens(B, H, p(x0), p(theta), ts, p(inputs), p(Xobs), p(X), p(Uo), p(dX), p(dU), p(ldp), p(status))
+        return {"X": X, "U": Uo, "dX": dX, "dU": dU, "loss_dp": ldp, "status": status}
