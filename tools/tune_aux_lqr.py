@@ -19,7 +19,7 @@ V1 = dict(bwd_pack=1, chunk=17, warps_per_block=4, min_blocks=3, keep_fg=True)  
 VARIANTS = [
     V1,
     {},                                                                    # shipped: two trajectories per warp
-    dict(chunk=6, min_blocks=12), dict(chunk=8, min_blocks=10), dict(chunk=6, min_blocks=12, early_solve=False),   # 168 registers
+    dict(chunk=6, min_blocks=12), dict(chunk=8, min_blocks=10),            # 168 registers (profiles/r1m_tune_168reg.json)
 ]
 
 
