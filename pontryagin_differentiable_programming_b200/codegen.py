@@ -195,8 +195,9 @@ class OCModuleSource:
                  chunk: int = 8, warps_per_block: int = 4, min_blocks: int = 1, fwd_warps_per_block: int = 4,
                  fwd_min_blocks: int = 1, keep_fg: bool = True, fast_rcp: bool = False, early_solve: bool = False,
                  fwd_pack: int = 0, fwd_chunk: int = 0, bwd_pack: int = 1, fwd_vec: int = -1, prefetch: int = 2,
-                 prefetch_dist: int = 2, inline_eval: int = -1, h_group: int = 1, prefetch_l1_lead: int = 0):
+                 prefetch_dist: int = 2, inline_eval: int = -1, h_group: int = 1, prefetch_l1_lead: int = 0, fused: int = 0):
         self.keep_fg = bool(keep_fg)
+        self.fused = int(fused)
         self.prefetch_l1_lead = int(prefetch_l1_lead)
         self.h_group = int(h_group)
         self.inline_eval = int(inline_eval)
@@ -240,6 +241,10 @@ class OCModuleSource:
             self.bwd_pack = 1          # the two-rows-per-lane layout needs n <= 16 and m + r <= 16
         if self.bwd_pack == 2:
             self.chunk = min(self.chunk, 16)
+        if self.fused and self.bwd_pack != 2:
+            self.fused = 0
+        if self.fused:
+            self.fwd_pack = 2                 # the forward half works on the same two trajectories as the backward half
         self._layout()
 
     def _customise(self):
@@ -922,6 +927,8 @@ class OCModuleSource:
             "PF": getattr(self, "prefetch", 0), "PFD": max(1, getattr(self, "prefetch_dist", 3)),
             "PFL": max(0, getattr(self, "prefetch_l1_lead", 0)),
         }
+        if getattr(self, "fused", 0):
+            defs["FUSED_DOUBLES"] = max(warp_doubles, fwarp_doubles)
         header = ["// GENERATED by pontryagin_differentiable_programming_b200/codegen.py -- do not edit",
                   "#include <cuda_runtime.h>", "#include <math.h>", "#include <stdint.h>"]
         header += ["#define PDP_%s %d" % kv for kv in defs.items()]
@@ -1020,7 +1027,12 @@ class OCModuleSource:
 
     def _kernel_text(self):
         bwd = _K_AUX_LQR_BWD2 if getattr(self, "bwd_pack", 1) == 2 else _K_AUX_LQR_BWD
-        return _K_PRELUDE + _K_ROLLOUT_AUXEVAL + _K_AUX_LQR_HEAD + bwd + _K_AUX_LQR_FWD + _K_LAUNCH_COMMON + _K_LAUNCH_LQR
+        fused, launch = "", _K_LAUNCH_LQR
+        if getattr(self, "fused", 0):
+            from .kernel_templates import K_AUX_LQR_FUSED, as_device_functions, fused_launcher
+            fused = "\n".join(as_device_functions(_K_AUX_LQR_BWD2, _K_AUX_LQR_FWD)) + K_AUX_LQR_FUSED
+            launch = fused_launcher(_K_LAUNCH_LQR)
+        return _K_PRELUDE + _K_ROLLOUT_AUXEVAL + _K_AUX_LQR_HEAD + bwd + _K_AUX_LQR_FWD + fused + _K_LAUNCH_COMMON + launch
 
     def _eval_macros(self):
         el = "tl" if getattr(self, "bwd_pack", 1) == 2 else "lane"       # evaluation lane = time step of the chunk

@@ -591,3 +591,73 @@ extern "C" int pdpmod_aux_lqr(int B, int H, const double* X, const double* U, co
 _ib = K_AUX_LQR.index('extern "C" __global__ void __launch_bounds__(PDP_WPB * 32, PDP_MINB)')
 _if = K_AUX_LQR.index('extern "C" __global__ void __launch_bounds__(PDP_WPBF * 32, PDP_MINBF)')
 K_AUX_LQR_HEAD, K_AUX_LQR_BWD, K_AUX_LQR_FWD = K_AUX_LQR[:_ib], K_AUX_LQR[_ib:_if], K_AUX_LQR[_if:]
+
+
+# ---- fused backward + forward kernel (option `fused` of the OC module; two-trajectory layout only) -----------------
+K_AUX_LQR_FUSED = r"""
+// One warp: Riccati sweep of its two trajectories, then their forward pass at once -- the gain spill is re-read while
+// it is still in L2 (the latest records first).  The two halves are the bodies of pdp_k_aux_lqr_bwd / _fwd compiled as
+// device functions on the same per-warp shared-memory region.
+extern "C" __global__ void __launch_bounds__(PDP_WPB * 32, PDP_MINB)
+pdp_k_aux_lqr_fused(int B, int H, const double* __restrict__ X, const double* __restrict__ U, const double* __restrict__ Lam,
+                    const double* __restrict__ theta, int theta_stride, const double* __restrict__ X0a, int x0a_stride,
+                    double* __restrict__ dX, double* __restrict__ dU, double* gains,
+                    const double* __restrict__ Xref, const double* __restrict__ Uref, double* __restrict__ loss_dp,
+                    const double* __restrict__ auxrec, const double* __restrict__ termrec, int* __restrict__ status)
+{
+  extern __shared__ __align__(16) double pdp_smem[];
+  const int pdp_warp = blockIdx.x * PDP_WPB + (threadIdx.x >> 5);
+  if (pdp_warp * 2 >= B) return;
+  double* ws = pdp_smem + (size_t)(threadIdx.x >> 5) * PDP_FUSED_DOUBLES;
+  pdp_dev_aux_lqr_bwd(pdp_warp, ws, B, H, X, U, Lam, theta, theta_stride, gains, auxrec, termrec, status);
+  __syncwarp();            // the records were written by their owning lanes and are read by other lanes below
+  pdp_dev_aux_lqr_fwd(pdp_warp, ws, B, H, X, U, theta, theta_stride, X0a, x0a_stride, dX, dU, gains, Xref, Uref, loss_dp,
+                      auxrec, status);
+}
+"""
+
+
+K_LAUNCH_FUSED_BRANCH = r"""  if (phases == 3) {   // backward sweep and forward pass of a warp's two trajectories back to back in ONE kernel
+    static bool configured_fused[64] = {false};
+    const size_t smem_x = (size_t)PDP_WPB * PDP_FUSED_DOUBLES * sizeof(double);
+    if (!configured_fused[dev_ & 63]) {
+      cudaError_t e = cudaFuncSetAttribute(pdp_k_aux_lqr_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x);
+      if (e != cudaSuccess) return (int)e;
+      configured_fused[dev_ & 63] = true;
+    }
+    pdp_k_aux_lqr_fused<<<(B + PDP_WPB * 2 - 1) / (PDP_WPB * 2), PDP_WPB * 32, smem_x, st>>>(
+        B, H, X, U, Lam, theta, theta_stride, X0a, x0a_stride, dX, dU, gains, Xref, Uref, loss_dp, auxrec, termrec, status);
+    return (int)cudaGetLastError();
+  }
+"""
+
+
+def _replace_once(text, old, new):
+    assert text.count(old) == 1, (old, text.count(old))
+    return text.replace(old, new)
+
+
+def as_device_functions(bwd2_text, fwd_text):
+    """The (already macro-expanded or not) texts of the two-trajectory backward kernel and of the forward kernel turned
+    into ``__device__`` functions pdp_dev_aux_lqr_bwd / pdp_dev_aux_lqr_fwd(pdp_warp, pdp_wsmem, <kernel arguments>)."""
+    b = bwd2_text
+    b = _replace_once(b, 'extern "C" __global__ void __launch_bounds__(PDP_WPB * 32, PDP_MINB)\npdp_k_aux_lqr_bwd(int B,',
+                      '__device__ __forceinline__ void pdp_dev_aux_lqr_bwd(const int pdp_warp, double* pdp_wsmem, int B,')
+    b = _replace_once(b, "  extern __shared__ __align__(16) double pdp_smem[];\n", "")
+    b = _replace_once(b, "const int b0 = (blockIdx.x * PDP_WPB + (threadIdx.x >> 5)) * 2;", "const int b0 = pdp_warp * 2;")
+    b = _replace_once(b, "double* auxc = pdp_smem + (size_t)(threadIdx.x >> 5) * PDP_WARP_DOUBLES + half * PDP_HS;",
+                      "double* auxc = pdp_wsmem + half * PDP_HS;")
+    b = _replace_once(b, "double* __restrict__ gains,", "double* gains,")
+    f = fwd_text
+    f = _replace_once(f, 'extern "C" __global__ void __launch_bounds__(PDP_WPBF * 32, PDP_MINBF)\npdp_k_aux_lqr_fwd(int B,',
+                      '__device__ __forceinline__ void pdp_dev_aux_lqr_fwd(const int pdp_warp, double* pdp_wsmem, int B,')
+    f = _replace_once(f, "  extern __shared__ __align__(16) double pdp_smem[];\n", "")
+    f = _replace_once(f, "const int b0 = (blockIdx.x * PDP_WPBF + (threadIdx.x >> 5)) * PDP_FG;", "const int b0 = pdp_warp * PDP_FG;")
+    f = _replace_once(f, "double* wbase = pdp_smem + (size_t)(threadIdx.x >> 5) * PDP_FWARP_DOUBLES;", "double* wbase = pdp_wsmem;")
+    f = _replace_once(f, "const double* __restrict__ gains,", "const double* gains,")
+    return b, f
+
+
+def fused_launcher(launch_text):
+    """K_LAUNCH_LQR with the fused branch in front of the two-kernel launches (phases == 3 only)."""
+    return _replace_once(launch_text, "  if (phases & 1)\n    pdp_k_aux_lqr_bwd<<<", K_LAUNCH_FUSED_BRANCH + "  if (phases & 1)\n    pdp_k_aux_lqr_bwd<<<")

@@ -29,6 +29,7 @@ def _variant(base, **kw):
     cfg = dict(chunk=base.chunk, warps_per_block=base.wpb, min_blocks=base.min_blocks, fwd_warps_per_block=base.wpbf,
                fwd_min_blocks=base.min_blocks_f, keep_fg=base.keep_fg, fast_rcp=base.fast_rcp,
                early_solve=base.early_solve, fwd_pack=base.fwd_pack, fwd_chunk=base.fwd_chunk, bwd_pack=base.bwd_pack)
+    cfg.update(fwd_vec=base.fwd_vec, prefetch=base.prefetch, prefetch_dist=base.prefetch_dist, h_group=base.h_group)
     cfg.update(kw)
     return codegen.OCModuleSource(base.x, base.u, base.th, base.dyn, base.c, base.h, **cfg)
 
@@ -227,3 +228,31 @@ def test_emulated_controlplanning_kernel_matches_oracle(policy):
         assert abs(out["loss_dp"][b, 0] - cost) < 1e-11 * abs(cost)
         assert _rel(out["dX"][b], dX) < 1e-10 and _rel(out["dU"][b], dU) < 1e-10
         assert _rel(out["loss_dp"][b, 1:], gref) < 1e-10
+
+
+def test_emulated_fused_backward_forward_kernel_matches_oracle():
+    """pdp_k_aux_lqr_fused (option fused=1: a warp runs the Riccati sweep of its two trajectories and then their
+    forward pass in one kernel, so the gain spill is re-read while it is still in L2) -- same outputs as the
+    two-kernel path: dX/dtheta, dU/dtheta, fused loss / chain rule vs the oracle; odd batch, chunk tails."""
+    from pontryagin_differentiable_programming_b200 import systems
+    base = systems.quadrotor_irl(0.1).src
+    src = _variant(base, fused=1)
+    assert src.fused == 1 and src._fwd_shape()[0] == 2
+    assert "pdp_k_aux_lqr_fused" in src.source() and "pdp_k_aux_lqr_fused" not in base.source()
+    oc = pdp_oracle.build_oc(envs.quadrotor(c=0.01, wthrust=0.1), 0.1)
+    rng = np.random.default_rng(7)
+    B, H = 3, 19
+    x0 = np.tile(np.array([-8, -6, 9., 0, 0, 0, 1, 0, 0, 0, 0, 0, 0]), (B, 1)) + 0.05 * rng.standard_normal((B, 13))
+    theta = np.array([1, 1, 1, 1, 0.4, 1, 1, 5, 1.]) * (1 + 0.1 * rng.uniform(-1, 1, (B, 9)))
+    U = 2.5 + 0.5 * rng.standard_normal((B, H, 4))
+    ref = [pdp_oracle.pdp_sweep(oc, x0[b], U[b], theta[b]) for b in range(B)]
+    X = np.stack([r[0] for r in ref])
+    L = np.stack([r[1] for r in ref])
+    Xd = X + 0.1 * rng.standard_normal(X.shape)
+    Ud = U + 0.1 * rng.standard_normal(U.shape)
+    dX, dU, ldp, gains, st = warp_emu.Emulator(src).fused(X, U, L, theta, Xref=Xd, Uref=Ud)
+    assert not np.isnan(gains).any()
+    for b in range(B):
+        assert _rel(dX[b], np.asarray(ref[b][3])) < 1e-10 and _rel(dU[b], np.asarray(ref[b][4])) < 1e-10
+        loss, dp = pdp_oracle.irl_loss_grad(X[b], U[b], Xd[b], Ud[b], ref[b][3], ref[b][4])
+        assert abs(ldp[b, 0] - loss) < 1e-12 * abs(loss) and _rel(ldp[b, 1:], np.asarray(dp).ravel()) < 1e-10

@@ -14,12 +14,13 @@ sys.path.insert(0, ROOT)
 
 # every variant: keyword overrides of BASE (= the shipped configuration of engine.OCSystem)
 BASE = dict(chunk=8, warps_per_block=1, min_blocks=8, fwd_warps_per_block=1, fwd_min_blocks=8, keep_fg=True,
-            fast_rcp=True, early_solve=True, fwd_pack=3, fwd_chunk=10, bwd_pack=2, fwd_vec=-1, prefetch=2, prefetch_dist=2, inline_eval=-1, h_group=1, prefetch_l1_lead=0)
+            fast_rcp=True, early_solve=True, fwd_pack=3, fwd_chunk=10, bwd_pack=2, fwd_vec=-1, prefetch=2, prefetch_dist=2, inline_eval=-1, h_group=1, prefetch_l1_lead=0, fused=0)
 V1 = dict(bwd_pack=1, chunk=17, warps_per_block=4, min_blocks=3, keep_fg=True)     # one trajectory per warp
 VARIANTS = [
     V1,
     {},                                                                    # shipped: two trajectories per warp
-    dict(chunk=6, min_blocks=12), dict(chunk=8, min_blocks=10),            # 168 registers (profiles/r1m_tune_168reg.json)
+    dict(fused=1),      # NOT YET MEASURED: backward + forward of a warp's two trajectories in one kernel (time it with
+                        # OCSystem.sweep / phase="both": the "backward" / "forward" columns below still launch the two kernels)
 ]
 
 
@@ -72,7 +73,7 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             ms["rollout"] = e0.elapsed_time(e1) / 10
-            for phase in ("backward", "forward"):
+            for phase in ("backward", "forward", "both"):     # "both": one call (the fused kernel where the module has one)
                 for _ in range(3):
                     s.aux_lqr(ro["X"], U, ro["Lam"], theta, Xref=Xr, Uref=Ur, out=out, phase=phase)
                 torch.cuda.synchronize()
@@ -89,7 +90,8 @@ def main():
             err = float((dx - ref_dx).abs().max() / ref_dx.abs().max())       # parity against the first variant
             row = dict(BASE)
             row.update(v)
-            row.update({"rollout_ms": ms["rollout"], "bwd_ms": ms["backward"], "fwd_ms": ms["forward"], "rel_diff_vs_first": err,
+            row.update({"rollout_ms": ms["rollout"], "bwd_ms": ms["backward"], "fwd_ms": ms["forward"], "both_ms": ms["both"],
+                        "rel_diff_vs_first": err,
                         "sweeps_per_s": B / (ms["rollout"] + ms["backward"] + ms["forward"]) * 1e3})
             rows.append(row)
             print(json.dumps(rows[-1]), flush=True)

@@ -77,6 +77,13 @@ static void* emu_lane(void* p) {
   threadIdx.x = EA.tx0 + lane; threadIdx.y = threadIdx.z = 0;
   blockIdx.x = EA.bx; blockIdx.y = blockIdx.z = 0;
   blockDim.x = EA.bdim; blockDim.y = blockDim.z = 1;
+#ifdef PDP_FUSED_DOUBLES
+  if (EA.kernel == 2) {
+    pdp_k_aux_lqr_fused(EA.B, EA.H, EA.X, EA.U, EA.Lam, EA.theta, EA.theta_stride, EA.X0a, EA.x0a_stride, EA.dX, EA.dU,
+                        EA.gains, EA.Xref, EA.Uref, EA.loss_dp, EA.auxrec, EA.termrec, EA.status);
+    return nullptr;
+  }
+#endif
   if (EA.kernel == 0)
     EMU_BWD_KERNEL(EA.B, EA.H, EA.X, EA.U, EA.Lam, EA.theta, EA.theta_stride, EA.gains, EA.auxrec, EA.termrec, EA.status);
   else
@@ -116,6 +123,16 @@ extern "C" void emu_forward(int B, int H, const double* X, const double* U, cons
   emu_run((B + per_block - 1) / per_block, PDP_WPBF);
 }
 extern "C" int emu_grec() { return PDP_GREC; }
+#ifdef PDP_FUSED_DOUBLES
+extern "C" void emu_fused(int B, int H, const double* X, const double* U, const double* Lam, const double* theta,
+                          int theta_stride, double* dX, double* dU, double* gains, const double* Xref, const double* Uref,
+                          double* loss_dp, int* status) {
+  memset(&EA, 0, sizeof(EA));
+  EA.kernel = 2; EA.B = B; EA.H = H; EA.X = X; EA.U = U; EA.Lam = Lam; EA.theta = theta; EA.theta_stride = theta_stride;
+  EA.dX = dX; EA.dU = dU; EA.gains = gains; EA.Xref = Xref; EA.Uref = Uref; EA.loss_dp = loss_dp; EA.status = status;
+  emu_run((B + PDP_WPB * 2 - 1) / (PDP_WPB * 2), PDP_WPB);
+}
+#endif
 #ifdef EMU_HAS_ROLLOUT
 // thread-per-trajectory kernel without warp-level primitives: the threads run one after the other
 extern "C" void emu_rollout(int B, int H, const double* x0, const double* theta, int theta_stride, const double* U,
@@ -191,6 +208,25 @@ class Emulator:
         self.lib.emu_rollout(B, H, self._p(x0), self._p(theta), ts, self._p(U), self._p(X), self._p(Lam), self._p(cost),
                              self._p(dHu), self._p(status))
         return X, Lam, cost, dHu
+
+    def fused(self, X, U, Lam, theta, Xref=None, Uref=None):
+        """pdp_k_aux_lqr_fused (modules generated with fused=1) -> dX, dU, loss_dp, gains, status."""
+        B, H = U.shape[0], U.shape[1]
+        n, m, r = self.n, self.m, self.r
+        X, U, Lam = (np.ascontiguousarray(a, dtype=np.float64) for a in (X, U, Lam))
+        theta = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
+        ts = 0 if theta.shape[0] == 1 else theta.shape[1]
+        dX, dU = np.full((B, H + 1, n, r), np.nan), np.full((B, H, m, r), np.nan)
+        gains = np.full((B, H, self.grec), np.nan)
+        status = np.zeros(B, dtype=np.int32)
+        ldp = None
+        if Xref is not None:
+            Xref = np.ascontiguousarray(Xref, dtype=np.float64)
+            Uref = None if Uref is None else np.ascontiguousarray(Uref, dtype=np.float64)
+            ldp = np.full((B, r + 1), np.nan)
+        self.lib.emu_fused(B, H, self._p(X), self._p(U), self._p(Lam), self._p(theta), ts, self._p(dX), self._p(dU),
+                           self._p(gains), self._p(Xref), self._p(Uref), self._p(ldp), self._p(status))
+        return dX, dU, ldp, gains, status
 
     def backward_dense(self, aux, term):
         """Generic dense LQR module: aux[B,H,NDENSE] (per step [F|G|E|Hxx|Hxu|Hxe|Hux|Huu|Hue] row-major), term[B,n*n+n*r]."""
