@@ -195,9 +195,10 @@ class OCModuleSource:
                  chunk: int = 8, warps_per_block: int = 4, min_blocks: int = 1, fwd_warps_per_block: int = 4,
                  fwd_min_blocks: int = 1, keep_fg: bool = True, fast_rcp: bool = False, early_solve: bool = False,
                  fwd_pack: int = 0, fwd_chunk: int = 0, bwd_pack: int = 1, fwd_vec: int = -1, prefetch: int = 2,
-                 prefetch_dist: int = 2, inline_eval: int = -1, h_group: int = 1, prefetch_l1_lead: int = 0, fused: int = 0):
+                 prefetch_dist: int = 2, inline_eval: int = -1, h_group: int = 1, prefetch_l1_lead: int = 0, fused: int = 0, stream_out: int = 0):
         self.keep_fg = bool(keep_fg)
         self.fused = int(fused)
+        self.stream_out = int(stream_out)
         self.prefetch_l1_lead = int(prefetch_l1_lead)
         self.h_group = int(h_group)
         self.inline_eval = int(inline_eval)
@@ -995,8 +996,14 @@ class OCModuleSource:
         gndecl = "double " + ", ".join("gn%d = 0.0" % a for a in range(m)) + ";"
         gcur = "      const double " + ", ".join("g%d = gn%d" % (a, a) for a in range(m)) + ";"
         kq_setup, gnload, ks_store = self._fwd_gain_prefetch(fg)
-        xstore = "\n".join("          o[%d] = n%d;" % (i * r, i) for i in range(n))
-        ustore = "\n".join("          o[%d] = u%d;" % (a * r, a) for a in range(m))
+        if getattr(self, "stream_out", 0):
+            # streaming (evict-first) stores for dX / dU: they are never re-read by these kernels, while the gain spill
+            # should stay in L2 for the forward half of the fused kernel
+            xstore = "\n".join("          __stcs(o + %d, n%d);" % (i * r, i) for i in range(n))
+            ustore = "\n".join("          __stcs(o + %d, u%d);" % (a * r, a) for a in range(m))
+        else:
+            xstore = "\n".join("          o[%d] = n%d;" % (i * r, i) for i in range(n))
+            ustore = "\n".join("          o[%d] = u%d;" % (a * r, a) for a in range(m))
         xcopy = "\n".join("      x%d = n%d;" % (k, k) for k in range(n))
         x0store = "\n".join("    o[%d] = x%d;" % (i * r, i) for i in range(n))
 

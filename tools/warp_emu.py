@@ -61,6 +61,7 @@ static inline double __shfl_sync(unsigned, double v, int src) {
   return r;
 }
 static inline int atomicOr(int* p, int v) { return __sync_fetch_and_or(p, v); }
+static inline void __stcs(double* p, double v) { *p = v; }
 '''
 
 DRIVER = r'''
