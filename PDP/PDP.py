@@ -17,7 +17,7 @@ import numpy
 import numpy as np  # noqa: F401  (the reference leaks ``np`` through ``from casadi import *``)
 
 from pontryagin_differentiable_programming_b200.symbolic import (  # noqa: F401
-    SX, MX, DM, Function, dot, hcat, jacobian, mtimes, tanh, transpose, vcat, vertcat)
+    SX, MX, DM, Function, dot, jacobian, mtimes, tanh, transpose, vcat, vertcat)
 
 
 # ------------------------------------------------------------------------------------------------ helpers
@@ -591,86 +591,61 @@ class ControlPlanning:
     # The objects built here are ordinary ``Function``s of the symbolic front-end (numeric calls evaluate on the host
     # like every other user-visible ``*_fn`` attribute; symbolic calls substitute).
 
+    def _compose_interval(self, first_step, last_step):
+        """(state after steps first_step..last_step-1 under one constant control, path cost summed over them), symbolic."""
+        x, cost = self.state, SX(0.0)
+        for _ in range(int(first_step), int(last_step)):
+            cost = cost + self.path_cost_fn(x, self.control)
+            x = self.dyn_fn(x, self.control)
+        return x, cost
+
     def warp_dynCost(self, time_grid):
-        """Dynamics / path cost composed over every interval of ``time_grid`` and their Jacobians (reference
-        PDP.py:882-915): ``wdyn_fns, wdfx_fns, wdfu_fns, wpath_cost_fns, wdcx_fns, wdcu_fns`` (one per interval),
-        ``wfinal_cost_fn``, ``wdhx_fn``."""
+        """Per interval of ``time_grid``: the composed dynamics and summed path cost as functions of (state at the
+        interval start, the interval's control) and their Jacobians -- the attribute lists of reference PDP.py:882-915
+        (``wdyn_fns, wdfx_fns, wdfu_fns, wpath_cost_fns, wdcx_fns, wdcu_fns``, ``wfinal_cost_fn``, ``wdhx_fn``)."""
         assert hasattr(self, 'dyn_fn'), 'Please set the dynamics first!'
         assert hasattr(self, 'path_cost_fn'), 'Please set the path cost first!'
         assert hasattr(self, 'final_cost_fn'), 'Please set the final cost first!'
-        self.wdyn_fns, self.wdfx_fns, self.wdfu_fns = [], [], []
-        self.wpath_cost_fns, self.wdcx_fns, self.wdcu_fns = [], [], []
-        xu = [self.state, self.control]
-        for wt in range(len(time_grid) - 1):
-            X, U = self.state, self.control
-            path_cost = 0
-            for _t in range(int(time_grid[wt]), int(time_grid[wt + 1])):
-                path_cost = path_cost + self.path_cost_fn(X, U)
-                X = self.dyn_fn(X, U)
-            path_cost = path_cost if isinstance(path_cost, SX) else SX(path_cost)
-            self.wdyn_fns += [Function('wdyn_fn' + str(wt), xu, [X])]
-            self.wdfx_fns += [Function('wdfx_fn' + str(wt), xu, [jacobian(X, self.state)])]
-            self.wdfu_fns += [Function('wdfu_fn' + str(wt), xu, [jacobian(X, self.control)])]
-            self.wpath_cost_fns += [Function('wpath_cost_fn' + str(wt), xu, [path_cost])]
-            self.wdcx_fns += [Function('wdcx_fn' + str(wt), xu, [jacobian(path_cost, self.state)])]
-            self.wdcu_fns += [Function('wdcu_fn' + str(wt), xu, [jacobian(path_cost, self.control)])]
-        self.wfinal_cost_fn = self.final_cost_fn
-        self.wdhx_fn = self.dhx_fn
+        args = [self.state, self.control]
+        built = {name: [] for name in ("wdyn", "wdfx", "wdfu", "wpath_cost", "wdcx", "wdcu")}
+        for wt, (t0, t1) in enumerate(zip(time_grid[:-1], time_grid[1:])):
+            x_end, cost = self._compose_interval(t0, t1)
+            outputs = {"wdyn": x_end, "wdfx": jacobian(x_end, self.state), "wdfu": jacobian(x_end, self.control),
+                       "wpath_cost": cost, "wdcx": jacobian(cost, self.state), "wdcu": jacobian(cost, self.control)}
+            for name, expr in outputs.items():
+                built[name].append(Function("%s_fn%d" % (name, wt), args, [expr]))
+        for name, fns in built.items():
+            setattr(self, name + "_fns", fns)
+        self.wfinal_cost_fn, self.wdhx_fn = self.final_cost_fn, self.dhx_fn
 
     def warp_getAuxSys(self, wstate_traj, wcontrol_traj, auxvar_value):
-        """Warped auxiliary system along a warped trajectory (reference PDP.py:940-957) -> dict of lists
-        ``wdynF, wdynG, wdUx, wdUe``; needs :meth:`warp_dynCost` (``warp_dynCost(self.time_grid)``)."""
+        """Jacobians of the composed dynamics and of the policy along a warped trajectory (reference PDP.py:940-957)
+        -> dict of lists ``wdynF, wdynG, wdUx, wdUe``; needs ``warp_dynCost(self.time_grid)``."""
         assert hasattr(self, 'wdfx_fns'), "Warp the dynamics first by running warp_dynCost(self.time_grid)!"
-        wstate_traj, wcontrol_traj = numpy.asarray(wstate_traj), numpy.asarray(wcontrol_traj)
-        wdynF, wdynG, wdUx, wdUe = [], [], [], []
-        for wt in range(numpy.size(wcontrol_traj, 0)):
-            wcurr_x, wcurr_u = wstate_traj[wt, :], wcontrol_traj[wt, :]
-            wdynF += [self.wdfx_fns[wt](wcurr_x, wcurr_u).full()]
-            wdynG += [self.wdfu_fns[wt](wcurr_x, wcurr_u).full()]
-            wdUx += [self.dpolicy_dx_fn(wt, wcurr_x, auxvar_value).full()]
-            wdUe += [self.dpolicy_de_fn(wt, wcurr_x, auxvar_value).full()]
-        return {"wdynF": wdynF, "wdynG": wdynG, "wdUx": wdUx, "wdUe": wdUe}
+        xs, us = numpy.asarray(wstate_traj), numpy.asarray(wcontrol_traj)
+        steps = range(us.shape[0])
+        return {"wdynF": [self.wdfx_fns[k](xs[k], us[k]).full() for k in steps],
+                "wdynG": [self.wdfu_fns[k](xs[k], us[k]).full() for k in steps],
+                "wdUx": [self.dpolicy_dx_fn(k, xs[k], auxvar_value).full() for k in steps],
+                "wdUe": [self.dpolicy_de_fn(k, xs[k], auxvar_value).full() for k in steps]}
 
     def recmat_recoveryMatrix(self, whorizon):
-        """The symbolic "recovery matrix" dJ/d(stacked controls) of the warped problem (reference PDP.py:1039-1079):
-        defines ``recovery_matrix_fn(x0, auxvar)`` and, like the reference, re-declares ``auxvar`` as the stacked
-        controls.  Needs :meth:`warp_dynCost` and ``whorizon >= 2``."""
+        """``recovery_matrix_fn(x0, stacked controls)`` = gradient of the warped problem's cost with respect to the
+        stacked interval controls, as a column (the quantity reference PDP.py:1039-1079 assembles from products of the
+        interval Jacobians).  Here the warped cost is composed symbolically from ``wdyn_fns`` / ``wpath_cost_fns`` and
+        differentiated by the front-end's reverse mode.  Like the reference this re-declares ``auxvar`` as the stacked
+        controls.  Needs :meth:`warp_dynCost`."""
         assert hasattr(self, 'wdyn_fns'), 'Please warp the dynamics and cost function first by running warp_init_step!'
-        controls = []
-        ini_state = SX.sym('X0', self.n_state)
-        X_t = ini_state
-        U_t = SX.sym('U_' + str(0), self.n_control)
-        G_t = self.wdfu_fns[0](X_t, U_t)
-        Cu_t = self.wdcu_fns[0](X_t, U_t)
-        controls += [U_t]
-        X_next = self.wdyn_fns[0](X_t, U_t)
-        U_next = SX.sym('U_' + str(1), self.n_control)
-        F_next = self.wdfx_fns[1](X_next, U_next)
-        Cx_next = self.wdcx_fns[1](X_next, U_next)
-        H1 = [mtimes(Cx_next, G_t) + Cu_t]
-        H2 = [mtimes(F_next, G_t)]
-        U_t, X_t = U_next, X_next
-        for wt in range(1, whorizon - 1):
-            G_t = self.wdfu_fns[wt](X_t, U_t)
-            Cu_t = self.wdcu_fns[wt](X_t, U_t)
-            controls += [U_t]
-            X_next = self.wdyn_fns[wt](X_t, U_t)
-            U_next = SX.sym('U_' + str(wt + 1), self.n_control)
-            F_next = self.wdfx_fns[wt + 1](X_next, U_next)
-            Cx_next = self.wdcx_fns[wt + 1](X_next, U_next)
-            H1 = [hcat(H1) + mtimes(Cx_next, hcat(H2))] + [mtimes(Cx_next, G_t) + Cu_t]
-            H2 = [mtimes(F_next, hcat(H2))] + [mtimes(F_next, G_t)]
-            U_t, X_t = U_next, X_next
-        G_t = self.wdfu_fns[whorizon - 1](X_t, U_t)
-        Cu_t = self.wdcu_fns[whorizon - 1](X_t, U_t)
-        controls += [U_t]
-        X_next = self.wdyn_fns[whorizon - 1](X_t, U_t)
-        Cx_next = self.wdhx_fn(X_next)
-        H1 = [hcat(H1) + mtimes(Cx_next, hcat(H2))] + [mtimes(Cx_next, G_t) + Cu_t]
-        recovery_matrix = hcat(H1)
+        x0 = SX.sym('X0', self.n_state)
+        controls = [SX.sym('U_%d' % k, self.n_control) for k in range(whorizon)]
+        x, total = x0, SX(0.0)
+        for k, u_k in enumerate(controls):
+            total = total + self.wpath_cost_fns[k](x, u_k)
+            x = self.wdyn_fns[k](x, u_k)
+        total = total + self.wfinal_cost_fn(x)
         self.auxvar = vcat(controls)
         self.n_auxvar = self.auxvar.numel()
-        self.recovery_matrix_fn = Function('recovery_matrix_fn', [ini_state, self.auxvar], [transpose(recovery_matrix)])
+        self.recovery_matrix_fn = Function('recovery_matrix_fn', [x0, self.auxvar], [transpose(jacobian(total, self.auxvar))])
 
 
 def _forward_recursion(dynF, dynG, dUx, dUe, dynE, ini_condition):
