@@ -195,8 +195,9 @@ class OCModuleSource:
                  chunk: int = 8, warps_per_block: int = 4, min_blocks: int = 1, fwd_warps_per_block: int = 4,
                  fwd_min_blocks: int = 1, keep_fg: bool = True, fast_rcp: bool = False, early_solve: bool = False,
                  fwd_pack: int = 0, fwd_chunk: int = 0, bwd_pack: int = 1, fwd_vec: int = -1, prefetch: int = 2,
-                 prefetch_dist: int = 2, inline_eval: int = -1, h_group: int = 1, prefetch_l1_lead: int = 0, fused: int = 0, stream_out: int = 0):
+                 prefetch_dist: int = 2, inline_eval: int = -1, h_group: int = 1, prefetch_l1_lead: int = 0, fused: int = 0, stream_out: int = 0, rollout_parts: int = 1):
         self.keep_fg = bool(keep_fg)
+        self.rollout_parts = max(1, min(int(rollout_parts), 8))
         self.fused = int(fused)
         self.stream_out = int(stream_out)
         self.prefetch_l1_lead = int(prefetch_l1_lead)
@@ -440,6 +441,39 @@ class OCModuleSource:
             dense += [M.at(i, j) for i in range(M.shape[0]) for j in range(M.shape[1])]
         parts.append(_emit_function("pdp_f_aux_dense", [x, u, lam, th], dense, lambda i: "out[%d]" % i))
         return "\n\n".join(parts)
+
+    # ---- multi-warp rollout: the outputs of f / dH/dx split over the warps of a block -------------------------
+    @staticmethod
+    def _partition_outputs(nodes, parts):
+        """Greedy split of output expressions over ``parts`` groups, balancing the size of each group's expression cone
+        (shared sub-expressions are duplicated between groups).  -> list of index lists."""
+        cones = [{nd.uid for nd in S.topo_order([e]) if nd.op not in ("sym", "const")} for e in nodes]
+        groups = [[] for _ in range(parts)]
+        unions = [set() for _ in range(parts)]
+        for i in sorted(range(len(nodes)), key=lambda k: -len(cones[k])):
+            p = min(range(parts), key=lambda q: (len(unions[q] | cones[i]), len(groups[q])))
+            groups[p].append(i)
+            unions[p] |= cones[i]
+        return [sorted(g) for g in groups], [len(u_) for u_ in unions]
+
+    def _rollout_mw(self):
+        """(device functions, defines, kernel text) of the multi-warp rollout kernel."""
+        P = self.rollout_parts
+        x, u, th, lam = ("x", self.x), ("u", self.u), ("th", self.th), ("lam", self.lam)
+        dyn, dhx = self.dyn.elements(), self.dHx.elements()
+        gd, cd = self._partition_outputs(dyn, P)
+        gh, ch = self._partition_outputs(dhx, P)
+        fns, sw_d, sw_h = [], [], []
+        for p in range(P):
+            fns.append(_emit_function("pdp_f_dyn_part%d" % p, [x, u, th], [dyn[i] for i in gd[p]] or [S.ZERO], lambda i: "out[%d]" % i))
+            fns.append(_emit_function("pdp_f_dHx_part%d" % p, [x, u, lam, th], [dhx[i] for i in gh[p]] or [S.ZERO], lambda i: "out[%d]" % i))
+            sw_d.append("    if (part == %d) { pdp_f_dyn_part%d(x, u, th, tmp); %s }"
+                        % (p, p, " ".join("XS[buf][%d][lane] = tmp[%d];" % (i, k) for k, i in enumerate(gd[p]))))
+            sw_h.append("        if (part == %d) { pdp_f_dHx_part%d(x, u, lam, th, tmp); %s }"
+                        % (p, p, " ".join("XS[buf][%d][lane] = tmp[%d];" % (i, k) for k, i in enumerate(gh[p]))))
+        defs = {"RP": P, "RP_COST": min(range(P), key=lambda q: cd[q]), "RP_DHU": min(range(P), key=lambda q: ch[q])}
+        text = _K_ROLLOUT_MW.replace("@@MW_DYN_SWITCH@@", "\n".join(sw_d)).replace("@@MW_DHX_SWITCH@@", "\n".join(sw_h))
+        return "\n\n".join(fns), defs, text
 
     # ---- the Riccati step body ---------------------------------------------------------------------
     def _backward_step(self) -> str:
@@ -1034,12 +1068,18 @@ class OCModuleSource:
 
     def _kernel_text(self):
         bwd = _K_AUX_LQR_BWD2 if getattr(self, "bwd_pack", 1) == 2 else _K_AUX_LQR_BWD
+        mw, launch_common = "", _K_LAUNCH_COMMON
+        if getattr(self, "rollout_parts", 1) > 1:
+            from .kernel_templates import rollout_mw_launcher
+            fns, mwdefs, text = self._rollout_mw()
+            mw = "\n".join("#define PDP_%s %d" % kv for kv in mwdefs.items()) + "\n" + fns + "\n" + text
+            launch_common = rollout_mw_launcher(_K_LAUNCH_COMMON)
         fused, launch = "", _K_LAUNCH_LQR
         if getattr(self, "fused", 0):
             from .kernel_templates import K_AUX_LQR_FUSED, as_device_functions, fused_launcher
             fused = "\n".join(as_device_functions(_K_AUX_LQR_BWD2, _K_AUX_LQR_FWD)) + K_AUX_LQR_FUSED
             launch = fused_launcher(_K_LAUNCH_LQR)
-        return _K_PRELUDE + _K_ROLLOUT_AUXEVAL + _K_AUX_LQR_HEAD + bwd + _K_AUX_LQR_FWD + fused + _K_LAUNCH_COMMON + launch
+        return _K_PRELUDE + _K_ROLLOUT_AUXEVAL + mw + _K_AUX_LQR_HEAD + bwd + _K_AUX_LQR_FWD + fused + launch_common + launch
 
     def _eval_macros(self):
         el = "tl" if getattr(self, "bwd_pack", 1) == 2 else "lane"       # evaluation lane = time step of the chunk
@@ -1279,4 +1319,4 @@ class LQRModuleSource(OCModuleSource):
 from .kernel_templates import (  # noqa: E402
     K_AUX_LQR_BWD as _K_AUX_LQR_BWD, K_AUX_LQR_BWD2 as _K_AUX_LQR_BWD2, K_AUX_LQR_FWD as _K_AUX_LQR_FWD,
     K_AUX_LQR_HEAD as _K_AUX_LQR_HEAD, K_AUX_LQR as _K_AUX_LQR, K_LAUNCH_COMMON as _K_LAUNCH_COMMON, K_LAUNCH_LQR as _K_LAUNCH_LQR,
-    K_PRELUDE as _K_PRELUDE, K_ROLLOUT_AUXEVAL as _K_ROLLOUT_AUXEVAL)
+    K_PRELUDE as _K_PRELUDE, K_ROLLOUT_AUXEVAL as _K_ROLLOUT_AUXEVAL, K_ROLLOUT_MW as _K_ROLLOUT_MW)

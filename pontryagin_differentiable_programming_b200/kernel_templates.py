@@ -661,3 +661,114 @@ def as_device_functions(bwd2_text, fwd_text):
 def fused_launcher(launch_text):
     """K_LAUNCH_LQR with the fused branch in front of the two-kernel launches (phases == 3 only)."""
     return _replace_once(launch_text, "  if (phases & 1)\n    pdp_k_aux_lqr_bwd<<<", K_LAUNCH_FUSED_BRANCH + "  if (phases & 1)\n    pdp_k_aux_lqr_bwd<<<")
+
+
+# ---- rollout / costate kernel with the per-step derivative code split over the warps of a block (option rollout_parts)
+K_ROLLOUT_MW = r"""
+// =====================================================================================================
+// Kernel 1b: rollout + cost + costate recursion with PDP_RP WARPS PER 32 TRAJECTORIES.  The one-thread-per-trajectory
+// kernel is latency-bound (one warp per scheduler executing ~300 dependent instructions per step): here warp p of a block
+// evaluates only its share of the outputs of f / dH/dx for the block's 32 trajectories, the shares are exchanged through a
+// double-buffered shared-memory tile and ONE __syncthreads per step, and every warp keeps the full state / costate in
+// registers.  Same inputs, outputs and semantics as pdp_k_rollout_costate without the closed-loop mode.
+// =====================================================================================================
+extern "C" __global__ void __launch_bounds__(PDP_RP * 32)
+pdp_k_rollout_costate_mw(int B, int H, const double* __restrict__ x0, const double* __restrict__ theta, int theta_stride,
+                         const double* __restrict__ U, double* __restrict__ X, double* __restrict__ Lam,
+                         double* __restrict__ cost, double* __restrict__ dHu, int* __restrict__ status)
+{
+  __shared__ double XS[2][PDP_N][32];
+  const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+  const int bq = blockIdx.x * 32 + lane;
+  const bool live = bq < B;
+  const int b = live ? bq : B - 1;                     // idle lanes shadow a valid trajectory (they must reach the barriers)
+  double x[PDP_N], th[PDP_NTH], u[PDP_M], tmp[PDP_N > PDP_M ? PDP_N : PDP_M];
+  #pragma unroll
+  for (int i = 0; i < PDP_NTH; ++i) th[i] = theta[(size_t)b * theta_stride + i];
+  #pragma unroll
+  for (int i = 0; i < PDP_N; ++i) x[i] = x0[(size_t)b * PDP_N + i];
+  double J = 0.0;
+  double* Xb = X + (size_t)b * (H + 1) * PDP_N;
+  const double* Ub = U + (size_t)b * H * PDP_M;
+  pdp_row_raw<PDP_M> una, unb;
+  pdp_row_issue<PDP_M>(una, Ub);
+  pdp_row_issue<PDP_M>(unb, Ub + (H > 1 ? 1 : 0) * PDP_M);
+  int buf = 0;
+  auto fstep = [&](const int t, pdp_row_raw<PDP_M>& un) {
+    pdp_row_unpack<PDP_M>(u, un);
+    pdp_row_issue<PDP_M>(un, Ub + (t + 2 < H ? t + 2 : H - 1) * PDP_M);
+    if (live && part == t % PDP_RP) pdp_row_store<PDP_N>(Xb + t * PDP_N, x);       // the row stores rotate over the warps
+    if (part == PDP_RP_COST) { pdp_f_path_cost(x, u, th, tmp); J += tmp[0]; }
+@@MW_DYN_SWITCH@@
+    __syncthreads();
+    #pragma unroll
+    for (int i = 0; i < PDP_N; ++i) x[i] = XS[buf][i][lane];
+    buf ^= 1;
+  };
+  #pragma unroll 1
+  for (int t = 0; t < H; t += 2) {
+    fstep(t, una);
+    if (t + 1 < H) fstep(t + 1, unb);
+  }
+  if (live && part == H % PDP_RP) pdp_row_store<PDP_N>(Xb + H * PDP_N, x);
+  if (part == PDP_RP_COST) {
+    pdp_f_final_cost(x, th, tmp);
+    J += tmp[0];
+    if (live && cost) cost[b] = J;
+    if (live && status && !isfinite(J)) atomicOr(&status[b], 1);
+  }
+  if (Lam != nullptr) {
+    double lam[PDP_N], gu[PDP_M];
+    double* Lb = Lam + (size_t)b * H * PDP_N;
+    pdp_f_dhx(x, th, lam);
+    pdp_row_raw<PDP_N> xpa, xpb;
+    pdp_row_raw<PDP_M> upa, upb;
+    __syncthreads();                      // every warp has stored its X rows before any warp reads them back
+    pdp_row_issue<PDP_N>(xpa, Xb + (H - 1) * PDP_N);
+    pdp_row_issue<PDP_M>(upa, Ub + (H - 1) * PDP_M);
+    pdp_row_issue<PDP_N>(xpb, Xb + (H > 1 ? H - 2 : 0) * PDP_N);
+    pdp_row_issue<PDP_M>(upb, Ub + (H > 1 ? H - 2 : 0) * PDP_M);
+    auto bstep = [&](const int t, pdp_row_raw<PDP_N>& xp, pdp_row_raw<PDP_M>& up) {
+      if (live && part == t % PDP_RP) pdp_row_store<PDP_N>(Lb + t * PDP_N, lam);
+      pdp_row_unpack<PDP_N>(x, xp);
+      pdp_row_unpack<PDP_M>(u, up);
+      {
+        const int tq = t > 1 ? t - 2 : 0;
+        pdp_row_issue<PDP_N>(xp, Xb + tq * PDP_N);
+        pdp_row_issue<PDP_M>(up, Ub + tq * PDP_M);
+      }
+      if (dHu != nullptr && part == PDP_RP_DHU) {
+        pdp_f_dHu(x, u, lam, th, gu);
+        if (live) {
+          #pragma unroll
+          for (int i = 0; i < PDP_M; ++i) dHu[((size_t)b * H + t) * PDP_M + i] = gu[i];
+        }
+      }
+      if (t > 0) {
+@@MW_DHX_SWITCH@@
+        __syncthreads();
+        #pragma unroll
+        for (int i = 0; i < PDP_N; ++i) lam[i] = XS[buf][i][lane];
+        buf ^= 1;
+      }
+    };
+    #pragma unroll 1
+    for (int t = H - 1; t >= 0; t -= 2) {
+      bstep(t, xpa, upa);
+      if (t > 0) bstep(t - 1, xpb, upb);
+    }
+  }
+}
+"""
+
+K_LAUNCH_ROLLOUT_MW_BRANCH = r"""  if (fb_gains == nullptr) {   // open-loop rollout: the derivative code is split over PDP_RP warps per 32 trajectories
+    pdp_k_rollout_costate_mw<<<(B + 31) / 32, PDP_RP * 32, 0, st>>>(B, H, x0, theta, theta_stride, U, X, Lam, cost, dHu, status);
+    return (int)cudaGetLastError();
+  }
+"""
+
+
+def rollout_mw_launcher(launch_common_text):
+    """K_LAUNCH_COMMON with the multi-warp rollout in front of the one-thread-per-trajectory launch."""
+    return _replace_once(launch_common_text, "  pdp_k_rollout_costate<<<(B + 127) / 128, 128, 0, st>>>(",
+                         K_LAUNCH_ROLLOUT_MW_BRANCH + "  pdp_k_rollout_costate<<<(B + 127) / 128, 128, 0, st>>>(")

@@ -256,3 +256,31 @@ def test_emulated_fused_backward_forward_kernel_matches_oracle():
         assert _rel(dX[b], np.asarray(ref[b][3])) < 1e-10 and _rel(dU[b], np.asarray(ref[b][4])) < 1e-10
         loss, dp = pdp_oracle.irl_loss_grad(X[b], U[b], Xd[b], Ud[b], ref[b][3], ref[b][4])
         assert abs(ldp[b, 0] - loss) < 1e-12 * abs(loss) and _rel(ldp[b, 1:], np.asarray(dp).ravel()) < 1e-10
+
+
+@pytest.mark.parametrize("env,parts", [("quadrotor", 4), ("cartpole", 3)])
+def test_emulated_multi_warp_rollout_kernel_equals_the_single_thread_kernel(env, parts):
+    """pdp_k_rollout_costate_mw (option rollout_parts: the outputs of f / dH/dx split over the warps of a block, one
+    __syncthreads per step) -- bit-identical to the one-thread-per-trajectory kernel and equal to the oracle; 37
+    trajectories = two blocks, the second one mostly idle lanes."""
+    from pontryagin_differentiable_programming_b200 import systems
+    base = systems.OC_BUILDERS[env](0.1).src
+    src = _variant(base, rollout_parts=parts)
+    assert "pdp_k_rollout_costate_mw" in src.source() and "pdp_k_rollout_costate_mw" not in base.source()
+    builder, kw = ORACLE_ENVS[env]
+    oc = pdp_oracle.build_oc(builder(**kw), 0.1)
+    rng = np.random.default_rng(2)
+    B, H = 37, 9
+    x0 = 0.3 * rng.standard_normal((B, src.n))
+    if env == "quadrotor":
+        x0[:, 6] += 1.0
+    theta = 1.0 + 0.2 * rng.uniform(-1, 1, (B, src.r))
+    U = 0.5 * rng.standard_normal((B, H, src.m)) + (2.5 if env == "quadrotor" else 0.0)
+    emu = warp_emu.Emulator(src)
+    mw = emu.rollout(x0, theta, U, want_dHu=True, multi_warp=True)
+    one = emu.rollout(x0, theta, U, want_dHu=True)
+    for a, b_ in zip(mw, one):
+        assert np.array_equal(a, b_)
+    for b in (0, 36):
+        Xr, c = oc.rollout(x0[b], U[b], theta[b])
+        assert np.max(np.abs(mw[0][b] - Xr)) < 1e-12 and _rel(mw[1][b], oc.costate(Xr, U[b], theta[b])) < 1e-12

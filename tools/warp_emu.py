@@ -37,7 +37,7 @@ using std::isfinite;
 #define __forceinline__ inline
 #define __noinline__
 #define __restrict__
-#define __shared__
+#define __shared__ static          /* statically sized tiles: one block runs at a time */
 #define __align__(x)
 #define __launch_bounds__(...)
 struct emu_dim3 { unsigned x, y, z; };
@@ -47,7 +47,9 @@ static inline double2 make_double2(double a, double b) { double2 v; v.x = a; v.y
 extern "C" { alignas(16) double pdp_smem[1 << 18]; }
 static pthread_barrier_t emu_bar;
 static double emu_xch[32];
+static pthread_barrier_t emu_block_bar;
 static inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&emu_bar); }
+static inline void __syncthreads() { pthread_barrier_wait(&emu_block_bar); }
 static inline double __shfl_xor_sync(unsigned, double v, int o) {
   const int l = threadIdx.x & 31;
   emu_xch[l] = v; pthread_barrier_wait(&emu_bar);
@@ -134,6 +136,31 @@ extern "C" void emu_fused(int B, int H, const double* X, const double* U, const 
   emu_run((B + PDP_WPB * 2 - 1) / (PDP_WPB * 2), PDP_WPB);
 }
 #endif
+#ifdef PDP_RP
+// multi-warp rollout kernel: a whole block (PDP_RP warps) runs as PDP_RP * 32 host threads, __syncthreads = block barrier
+struct emu_mw_args { int B, H, theta_stride; const double *x0, *theta, *U; double *X, *Lam, *cost, *dHu; int* status; unsigned bx; };
+static emu_mw_args MW;
+static void* emu_mw_thread(void* p) {
+  threadIdx.x = (unsigned)(uintptr_t)p; threadIdx.y = threadIdx.z = 0;
+  blockIdx.x = MW.bx; blockIdx.y = blockIdx.z = 0; blockDim.x = PDP_RP * 32;
+  pdp_k_rollout_costate_mw(MW.B, MW.H, MW.x0, MW.theta, MW.theta_stride, MW.U, MW.X, MW.Lam, MW.cost, MW.dHu, MW.status);
+  return nullptr;
+}
+extern "C" void emu_rollout_mw(int B, int H, const double* x0, const double* theta, int theta_stride, const double* U,
+                               double* X, double* Lam, double* cost, double* dHu, int* status) {
+  MW.B = B; MW.H = H; MW.theta_stride = theta_stride; MW.x0 = x0; MW.theta = theta; MW.U = U; MW.X = X; MW.Lam = Lam;
+  MW.cost = cost; MW.dHu = dHu; MW.status = status;
+  const unsigned nt = PDP_RP * 32;
+  pthread_barrier_init(&emu_block_bar, nullptr, nt);
+  for (unsigned bx = 0; bx < (unsigned)(B + 31) / 32; ++bx) {
+    MW.bx = bx;
+    pthread_t th[256];
+    for (unsigned l = 0; l < nt; ++l) pthread_create(&th[l], nullptr, emu_mw_thread, (void*)(uintptr_t)l);
+    for (unsigned l = 0; l < nt; ++l) pthread_join(th[l], nullptr);
+  }
+  pthread_barrier_destroy(&emu_block_bar);
+}
+#endif
 #ifdef EMU_HAS_ROLLOUT
 // thread-per-trajectory kernel without warp-level primitives: the threads run one after the other
 extern "C" void emu_rollout(int B, int H, const double* x0, const double* theta, int theta_stride, const double* U,
@@ -160,6 +187,7 @@ def translate(cuda_source: str) -> str:
         raise ValueError("launcher marker not found in the generated source")
     body = cuda_source[:cut]
     body = body.replace("#include <cuda_runtime.h>", "")
+    body = body.replace("extern __shared__ __align__(16) double pdp_smem[];", "extern double pdp_smem[];")
     body = _RCP.sub(lambda mo: "%s = 1.0 / %s;" % (mo.group(1), mo.group(2)), body)
     body = re.sub(r'asm volatile\("prefetch\.global\.L[12] \[%0\];" :: "l"\(p\)\);', "(void)p;", body)
     if "asm(" in body:
@@ -195,8 +223,9 @@ class Emulator:
     def _p(a):
         return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
-    def rollout(self, x0, theta, U, want_dHu=False):
-        """pdp_k_rollout_costate -> X, Lam, cost[, dHu]."""
+    def rollout(self, x0, theta, U, want_dHu=False, multi_warp=False):
+        """pdp_k_rollout_costate (or, for modules generated with rollout_parts > 1, pdp_k_rollout_costate_mw) -> X, Lam,
+        cost[, dHu]."""
         B, H = U.shape[0], U.shape[1]
         x0, U = (np.ascontiguousarray(a, dtype=np.float64) for a in (x0, U))
         theta = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
@@ -206,8 +235,9 @@ class Emulator:
         cost = np.full(B, np.nan)
         dHu = np.full((B, H, self.m), np.nan) if want_dHu else None
         status = np.zeros(B, dtype=np.int32)
-        self.lib.emu_rollout(B, H, self._p(x0), self._p(theta), ts, self._p(U), self._p(X), self._p(Lam), self._p(cost),
-                             self._p(dHu), self._p(status))
+        fn = self.lib.emu_rollout_mw if multi_warp else self.lib.emu_rollout
+        fn(B, H, self._p(x0), self._p(theta), ts, self._p(U), self._p(X), self._p(Lam), self._p(cost), self._p(dHu),
+           self._p(status))
         return X, Lam, cost, dHu
 
     def fused(self, X, U, Lam, theta, Xref=None, Uref=None):
