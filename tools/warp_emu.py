@@ -9,9 +9,13 @@ show up here in seconds.  It says nothing about performance, and races that a ba
 to `tools/sanitize.sh` (compute-sanitizer racecheck on the GPU).
 
     from tools import warp_emu
-    emu = warp_emu.Emulator(src)            # src: an OCModuleSource
-    gains = emu.backward(X, U, Lam, theta)  # numpy float64 in / out
-    dX, dU = emu.forward(X, U, theta, gains)
+    emu = warp_emu.Emulator(src)                       # src: an OCModuleSource / NewtonModuleSource / LQRModuleSource
+    gains, status = emu.backward(X, U, Lam, theta)     # numpy float64 in / out
+    dX, dU, loss_dp, status = emu.forward(X, U, theta, gains)
+    X, Lam, cost, dHu = emu.rollout(x0, theta, U)      # thread-per-trajectory kernel; multi_warp=True: whole blocks of
+                                                       # the multi-warp kernel as host threads, __syncthreads = barrier
+    emu.fused(...), emu.backward_dense(aux, term), emu.forward_dense(aux, gains)
+    warp_emu.SensEmulator(sens_src).run(...)           # SysID / ControlPlanning sensitivity kernel
 """
 from __future__ import annotations
 
