@@ -284,3 +284,34 @@ def test_emulated_multi_warp_rollout_kernel_equals_the_single_thread_kernel(env,
     for b in (0, 36):
         Xr, c = oc.rollout(x0[b], U[b], theta[b])
         assert np.max(np.abs(mw[0][b] - Xr)) < 1e-12 and _rel(mw[1][b], oc.costate(Xr, U[b], theta[b])) < 1e-12
+
+
+def test_emulator_detects_a_missing_barrier():
+    """Negative control of the emulator itself: the lanes are real host threads, so a kernel whose Z^T staging
+    barrier is removed must give wrong gains (it does, by orders of magnitude and differently on every run) -- the
+    value comparisons of this file therefore also guard the shared-memory choreography, not only the arithmetic."""
+    from pontryagin_differentiable_programming_b200 import codegen, systems
+    base = systems.quadrotor_irl(0.1).src
+
+    class Broken(codegen.OCModuleSource):
+        def source(self):
+            t = super().source()
+            i = t.index("// B: transpose through shared memory")
+            j = t.index("__syncwarp();", i)
+            return t[:j] + "/* barrier removed */" + t[j + len("__syncwarp();"):]
+
+    broken = Broken(base.x, base.u, base.th, base.dyn, base.c, base.h, chunk=base.chunk, warps_per_block=base.wpb,
+                    min_blocks=base.min_blocks, keep_fg=base.keep_fg, fast_rcp=base.fast_rcp, early_solve=base.early_solve,
+                    bwd_pack=base.bwd_pack)
+    rng = np.random.default_rng(0)
+    B, H = 4, 12
+    X = 0.3 * rng.standard_normal((B, H + 1, 13))
+    X[:, :, 6] += 1.0
+    U = 2.5 + 0.3 * rng.standard_normal((B, H, 4))
+    L = 0.1 * rng.standard_normal((B, H, 13))
+    th = np.array([1, 1, 1, 1, 0.4, 1, 1, 5, 1.]) * np.ones((B, 9))
+    good, _ = warp_emu.Emulator(base).backward(X, U, L, th)
+    again, _ = warp_emu.Emulator(base).backward(X, U, L, th)
+    assert np.array_equal(good, again)                       # the intact kernel is deterministic
+    bad, _ = warp_emu.Emulator(broken).backward(X, U, L, th)
+    assert not np.allclose(np.nan_to_num(bad), good, rtol=1e-6, atol=0)

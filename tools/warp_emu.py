@@ -5,8 +5,10 @@ compiles the *generated CUDA source* of a module (`OCModuleSource.source()`, cut
 and runs one warp as 32 host threads: `__syncwarp()` is a pthread barrier, `__shfl_xor_sync` goes through a small
 exchange buffer, shared memory is a global array.  It executes exactly the statements the GPU executes (same
 generated text, same lane predicates, same shared-memory indices), so layout / indexing / synchronisation mistakes
-show up here in seconds.  It says nothing about performance, and races that a barrier would hide on the CPU are left
-to `tools/sanitize.sh` (compute-sanitizer racecheck on the GPU).
+show up here in seconds: the lanes are real concurrent threads, so a missing barrier gives wrong, run-to-run different
+results (negative control in tests/test_kernel_emulation.py).  It says nothing about performance, and hazards between
+accesses that a CPU barrier orders but a GPU warp does not are left to `tools/sanitize.sh` (compute-sanitizer racecheck
+on the GPU).
 
     from tools import warp_emu
     emu = warp_emu.Emulator(src)                       # src: an OCModuleSource / NewtonModuleSource / LQRModuleSource
