@@ -9,6 +9,29 @@ mkdir -p gpurun_out
 #    path: compare the both_ms column (one aux-LQR call) -- DESIGN.md section 9, item 1
 python tools/tune_aux_lqr.py --run 2>&1 | tail -6 > gpurun_out/pending_tune_fused.log
 cp gpurun_out/tune_aux_lqr.json gpurun_out/pending_tune_fused.json 2>/dev/null
+# 1b. the same unmeasured kernels under compute-sanitizer (racecheck + memcheck) and against the shipped path, BEFORE
+#     anything is adopted: small batch with a tail (odd count, last block mostly idle lanes)
+cat > /tmp/pdp_new_kernels_case.py <<'PY'
+import sys, numpy as np, torch
+sys.path.insert(0, '.')
+import bench
+from tools.tune_aux_lqr import make
+dev = torch.device('cuda:0')
+x0, th, U, Xr, Ur = [torch.as_tensor(np.ascontiguousarray(a), device=dev) for a in bench.synth_quadrotor(37, 19, seed=4)]
+ref = make().sweep(x0, th, U, Xref=Xr, Uref=Ur)
+new = make(fused=1, stream_out=1, rollout_parts=4).sweep(x0, th, U, Xref=Xr, Uref=Ur)
+torch.cuda.synchronize()
+for k in ("X", "Lam", "cost", "dX", "dU", "loss_dp"):
+    d = float((ref[k] - new[k]).abs().max() / ref[k].abs().max())
+    print(k, "max rel diff fused/multi-warp vs shipped:", d)
+    assert d < 1e-11, k
+print("new kernels ok")
+PY
+python /tmp/pdp_new_kernels_case.py > gpurun_out/pending_new_kernels_parity.log 2>&1
+for tool in racecheck memcheck; do
+  timeout 600 compute-sanitizer --tool $tool --print-limit 20 python /tmp/pdp_new_kernels_case.py > gpurun_out/pending_sanitizer_$tool.log 2>&1
+  tail -2 gpurun_out/pending_sanitizer_$tool.log
+done
 # 2. first ncu capture of the SysID / ControlPlanning sensitivity kernel (C5 at its per-GPU size) -- item 5
 cat > /tmp/pdp_c5_case.py <<'PY'
 import sys, torch
