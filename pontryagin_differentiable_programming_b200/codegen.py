@@ -195,8 +195,9 @@ class OCModuleSource:
                  chunk: int = 8, warps_per_block: int = 4, min_blocks: int = 1, fwd_warps_per_block: int = 4,
                  fwd_min_blocks: int = 1, keep_fg: bool = True, fast_rcp: bool = False, early_solve: bool = False,
                  fwd_pack: int = 0, fwd_chunk: int = 0, bwd_pack: int = 1, fwd_vec: int = -1, prefetch: int = 2,
-                 prefetch_dist: int = 2, inline_eval: int = -1, h_group: int = 1, prefetch_l1_lead: int = 0, fused: int = 0, stream_out: int = 0, rollout_parts: int = 1):
+                 prefetch_dist: int = 2, inline_eval: int = -1, h_group: int = 1, prefetch_l1_lead: int = 0, fused: int = 0, stream_out: int = 0, rollout_parts: int = 1, stage_inputs: int = 0):
         self.keep_fg = bool(keep_fg)
+        self.stage_inputs = int(stage_inputs)
         self.rollout_parts = max(1, min(int(rollout_parts), 8))
         self.fused = int(fused)
         self.stream_out = int(stream_out)
@@ -243,6 +244,8 @@ class OCModuleSource:
             self.bwd_pack = 1          # the two-rows-per-lane layout needs n <= 16 and m + r <= 16
         if self.bwd_pack == 2:
             self.chunk = min(self.chunk, 16)
+        if self.stage_inputs and (self.bwd_pack != 2 or type(self)._eval_macros is not OCModuleSource._eval_macros):
+            self.stage_inputs = 0             # only the two-trajectory kernel of modules that evaluate their own slots
         if self.fused and self.bwd_pack != 2:
             self.fused = 0
         if self.fused:
@@ -935,6 +938,9 @@ class OCModuleSource:
         off_quu = off_ks + ks_size
         off_th = off_quu + _even(m * m)
         warp_doubles = _even(off_th + max(self.nth, 1))
+        off_in = warp_doubles
+        if getattr(self, "stage_inputs", 0):
+            warp_doubles = _even(off_in + self.chunk * (2 * n + m))
         bp = getattr(self, "bwd_pack", 1)
         half_stride = _pad_ld(warp_doubles)       # two-trajectory kernel: per-trajectory regions = 2 (mod 16) doubles apart
         if bp == 2:
@@ -964,6 +970,8 @@ class OCModuleSource:
         }
         if getattr(self, "fused", 0):
             defs["FUSED_DOUBLES"] = max(warp_doubles, fwarp_doubles)
+        if getattr(self, "stage_inputs", 0):
+            defs["OFF_IN"], defs["NIN"] = off_in, 2 * n + m
         header = ["// GENERATED by pontryagin_differentiable_programming_b200/codegen.py -- do not edit",
                   "#include <cuda_runtime.h>", "#include <math.h>", "#include <stdint.h>"]
         header += ["#define PDP_%s %d" % kv for kv in defs.items()]
@@ -1067,7 +1075,11 @@ class OCModuleSource:
         return []
 
     def _kernel_text(self):
-        bwd = _K_AUX_LQR_BWD2 if getattr(self, "bwd_pack", 1) == 2 else _K_AUX_LQR_BWD
+        bwd2 = _K_AUX_LQR_BWD2
+        if getattr(self, "stage_inputs", 0):
+            from .kernel_templates import K_STAGE_HELPERS, staged_backward_kernel
+            bwd2 = K_STAGE_HELPERS + staged_backward_kernel(_K_AUX_LQR_BWD2)
+        bwd = bwd2 if getattr(self, "bwd_pack", 1) == 2 else _K_AUX_LQR_BWD
         mw, launch_common = "", _K_LAUNCH_COMMON
         if getattr(self, "rollout_parts", 1) > 1:
             from .kernel_templates import rollout_mw_launcher
@@ -1077,7 +1089,8 @@ class OCModuleSource:
         fused, launch = "", _K_LAUNCH_LQR
         if getattr(self, "fused", 0):
             from .kernel_templates import K_AUX_LQR_FUSED, as_device_functions, fused_launcher
-            fused = "\n".join(as_device_functions(_K_AUX_LQR_BWD2, _K_AUX_LQR_FWD)) + K_AUX_LQR_FUSED
+            stage = K_STAGE_HELPERS if getattr(self, "stage_inputs", 0) else ""
+            fused = "\n".join(as_device_functions(bwd2[len(stage):], _K_AUX_LQR_FWD)) + K_AUX_LQR_FUSED
             launch = fused_launcher(_K_LAUNCH_LQR)
         return _K_PRELUDE + _K_ROLLOUT_AUXEVAL + mw + _K_AUX_LQR_HEAD + bwd + _K_AUX_LQR_FWD + fused + launch_common + launch
 
@@ -1085,11 +1098,15 @@ class OCModuleSource:
         el = "tl" if getattr(self, "bwd_pack", 1) == 2 else "lane"       # evaluation lane = time step of the chunk
         return {
             "@@EVAL_TERM@@": "  if (%s == 0) pdp_f_terminal(Xb + (size_t)H * PDP_N, TH, TB);" % el,
-            "@@EVAL_AUX_CHUNK@@": """    {
+            "@@EVAL_AUX_CHUNK@@": ("""    {
+      const int te = tc + tl;
+      if (tl < PDP_CH && te < H)      // inputs from the rows staged in shared memory one chunk ago
+        pdp_f_aux_slots(IN + tl * PDP_NIN, IN + tl * PDP_NIN + PDP_N, IN + tl * PDP_NIN + PDP_N + PDP_M, TH, auxc + tl * PDP_AUXLD);
+    }""" if getattr(self, "stage_inputs", 0) else """    {
       const int te = tc + %(el)s;
       if (%(el)s < PDP_CH && te < H)
         pdp_f_aux_slots(Xb + (size_t)te * PDP_N, Ub + (size_t)te * PDP_M, Lb + (size_t)te * PDP_N, TH, auxc + %(el)s * PDP_AUXLD);
-    }""" % {"el": el},
+    }""" % {"el": el}),
             "@@EVAL_DYN@@": "        pdp_f_dyn_slots(X + ((size_t)be * (H + 1) + te) * PDP_N, U + ((size_t)be * H + te) * PDP_M, the, eo);",
             "@@EVAL_DYN_COOP@@": "",
             "@@PREFETCH_AUX_CHUNK@@": "",      # measured: no gain (two-trajectory kernel) / a loss (one-trajectory kernel)

@@ -772,3 +772,52 @@ def rollout_mw_launcher(launch_common_text):
     """K_LAUNCH_COMMON with the multi-warp rollout in front of the one-thread-per-trajectory launch."""
     return _replace_once(launch_common_text, "  pdp_k_rollout_costate<<<(B + 127) / 128, 128, 0, st>>>(",
                          K_LAUNCH_ROLLOUT_MW_BRANCH + "  pdp_k_rollout_costate<<<(B + 127) / 128, 128, 0, st>>>(")
+
+
+# ---- asynchronous staging of the per-chunk inputs of the two-trajectory backward kernel (option stage_inputs) ---------
+K_STAGE_HELPERS = r"""
+// The chunk evaluation (lanes = time steps) is the only place where the backward kernel waits for HBM: its rows of
+// X / U / Lam are therefore copied into shared memory with cp.async ONE CHUNK AHEAD (issued right after the current
+// chunk has been evaluated, so they overlap the chunk's Riccati steps) and the evaluator reads shared memory.
+__device__ __forceinline__ void pdp_cp_async8(double* dst_shared, const double* src_global) {
+#ifdef __CUDACC__
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(dst_shared)), "l"(src_global) : "memory");
+#else
+  *dst_shared = *src_global;      /* CPU emulation: immediate copy */
+#endif
+}
+__device__ __forceinline__ void pdp_cp_async_wait() {
+#ifdef __CUDACC__
+  asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+// rows of steps tc .. tc+CH-1 of one trajectory: IN[s] = [x_t (n) | u_t (m) | lambda_{t+1} (n)], 16 team lanes cooperate
+__device__ __forceinline__ void pdp_stage_chunk(double* IN, const double* Xb, const double* Ub, const double* Lb, int tc, int H, int tl) {
+  for (int idx = tl; idx < PDP_CH * PDP_NIN; idx += 16) {
+    const int s = idx / PDP_NIN, e = idx - s * PDP_NIN;
+    const int te = tc + s;
+    if (te < H) {
+      const double* src = e < PDP_N ? Xb + (size_t)te * PDP_N + e
+                        : (e < PDP_N + PDP_M ? Ub + (size_t)te * PDP_M + (e - PDP_N) : Lb + (size_t)te * PDP_N + (e - PDP_N - PDP_M));
+      pdp_cp_async8(IN + idx, src);
+    }
+  }
+}
+"""
+
+
+def staged_backward_kernel(bwd2_text):
+    """K_AUX_LQR_BWD2 with the chunk inputs staged through shared memory one chunk ahead (see K_STAGE_HELPERS)."""
+    t = bwd2_text
+    t = _replace_once(t, "  double* TB = auxc;                                                         // terminal buffer aliases the chunk buffer\n",
+                      "  double* TB = auxc;                                                         // terminal buffer aliases the chunk buffer\n"
+                      "  double* IN = auxc + PDP_OFF_IN;                                            // staged rows of the next chunk\n")
+    t = _replace_once(t, "  #pragma unroll 1\n  for (int tc = ((H - 1) / PDP_CH) * PDP_CH; tc >= 0; tc -= PDP_CH) {\n    __syncwarp();            // every lane is done reading the previous chunk's slots\n",
+                      "  pdp_stage_chunk(IN, Xb, Ub, Lb, ((H - 1) / PDP_CH) * PDP_CH, H, tl);\n"
+                      "  #pragma unroll 1\n  for (int tc = ((H - 1) / PDP_CH) * PDP_CH; tc >= 0; tc -= PDP_CH) {\n"
+                      "    pdp_cp_async_wait();     // this chunk's rows were requested one chunk ago\n"
+                      "    __syncwarp();            // ... and every lane is done reading the previous chunk's slots\n")
+    t = _replace_once(t, "@@PREFETCH_AUX_CHUNK@@\n    __syncwarp();\n",
+                      "@@PREFETCH_AUX_CHUNK@@\n    __syncwarp();\n"
+                      "    if (tc >= PDP_CH) pdp_stage_chunk(IN, Xb, Ub, Lb, tc - PDP_CH, H, tl);     // overlaps the steps below\n")
+    return t

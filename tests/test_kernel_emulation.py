@@ -315,3 +315,25 @@ def test_emulator_detects_a_missing_barrier():
     assert np.array_equal(good, again)                       # the intact kernel is deterministic
     bad, _ = warp_emu.Emulator(broken).backward(X, U, L, th)
     assert not np.allclose(np.nan_to_num(bad), good, rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("extra", [dict(stage_inputs=1), dict(stage_inputs=1, chunk=5), dict(stage_inputs=1, fused=1)])
+def test_emulated_staged_chunk_inputs_variant_is_identical(extra):
+    """Option stage_inputs: the rows of X / U / Lam that the chunk evaluation needs are copied into shared memory with
+    cp.async one chunk ahead (immediate copies in the emulator) and the evaluator reads shared memory -- same gains
+    bit for bit, also inside the fused kernel and with a chunk that does not divide the horizon."""
+    from pontryagin_differentiable_programming_b200 import systems
+    base = systems.quadrotor_irl(0.1).src
+    src = _variant(base, **extra)
+    assert src.stage_inputs == 1 and "pdp_stage_chunk" in src.source() and "pdp_stage_chunk" not in base.source()
+    rng = np.random.default_rng(0)
+    B, H = 5, 21
+    X = 0.3 * rng.standard_normal((B, H + 1, 13))
+    X[:, :, 6] += 1.0
+    U = 2.5 + 0.3 * rng.standard_normal((B, H, 4))
+    L = 0.1 * rng.standard_normal((B, H, 13))
+    th = np.array([1, 1, 1, 1, 0.4, 1, 1, 5, 1.]) * (1 + 0.1 * rng.uniform(-1, 1, (B, 9)))
+    g0, _ = warp_emu.Emulator(base).backward(X, U, L, th)
+    emu = warp_emu.Emulator(src)
+    g1 = emu.fused(X, U, L, th)[3] if extra.get("fused") else emu.backward(X, U, L, th)[0]
+    assert np.array_equal(g0, g1)
