@@ -195,9 +195,10 @@ class OCModuleSource:
                  chunk: int = 8, warps_per_block: int = 4, min_blocks: int = 1, fwd_warps_per_block: int = 4,
                  fwd_min_blocks: int = 1, keep_fg: bool = True, fast_rcp: bool = False, early_solve: bool = False,
                  fwd_pack: int = 0, fwd_chunk: int = 0, bwd_pack: int = 1, fwd_vec: int = -1, prefetch: int = 2,
-                 prefetch_dist: int = 2, inline_eval: int = -1, h_group: int = 1, prefetch_l1_lead: int = 0, fused: int = 0, stream_out: int = 0, rollout_parts: int = 1, stage_inputs: int = 0):
+                 prefetch_dist: int = 2, inline_eval: int = -1, h_group: int = 1, prefetch_l1_lead: int = 0, fused: int = 0, stream_out: int = 0, rollout_parts: int = 1, stage_inputs: int = 0, fwd_stage_inputs: int = 0):
         self.keep_fg = bool(keep_fg)
         self.stage_inputs = int(stage_inputs)
+        self.fwd_stage_inputs = int(fwd_stage_inputs)
         self.rollout_parts = max(1, min(int(rollout_parts), 8))
         self.fused = int(fused)
         self.stream_out = int(stream_out)
@@ -246,6 +247,8 @@ class OCModuleSource:
             self.chunk = min(self.chunk, 16)
         if self.stage_inputs and (self.bwd_pack != 2 or type(self)._eval_macros is not OCModuleSource._eval_macros):
             self.stage_inputs = 0             # only the two-trajectory kernel of modules that evaluate their own slots
+        if self.fwd_stage_inputs and type(self)._eval_macros is not OCModuleSource._eval_macros:
+            self.fwd_stage_inputs = 0
         if self.fused and self.bwd_pack != 2:
             self.fused = 0
         if self.fused:
@@ -833,7 +836,7 @@ class OCModuleSource:
         fg = max(1, min(fg, WARP // gs, WARP))
         ch = getattr(self, "fwd_chunk", 0)
         if not ch:
-            per_step = _pad_ld(self.nvar_s) + self.n + self.m
+            per_step = _pad_ld(self.nvar_s) + self.n + self.m + (2 * (self.n + self.m) if getattr(self, "fwd_stage_inputs", 0) else 0)
             fit = (self.fwd_smem_budget // (8 * fg) - self.n * self.m - max(self.nth, 1) - 16) // per_step
             ch = min(WARP // fg if fg > 1 else self.chunk, max(fit, 1))
         ch = max(1, min(ch, WARP // fg))
@@ -952,7 +955,9 @@ class OCModuleSource:
         foff_th = foff_ks + _even(n * m)
         foff_dl = foff_th + _even(max(self.nth, 1))               # residuals x - xref [CHF*n], u - uref [CHF*m]
         foff_du = foff_dl + chf * n
-        fts = _pad_ld(foff_du + chf * m)
+        foff_in = _even(foff_du + chf * m)
+        fnin = 2 * (n + m)
+        fts = _pad_ld(foff_in + chf * fnin) if getattr(self, "fwd_stage_inputs", 0) else _pad_ld(foff_du + chf * m)
         fwarp_doubles = max(fg * fts, WARP)
         defs = {
             "N": n, "M": m, "R": r, "NS": ns, "NM": nm, "NVAR": self.nvar, "NVAR_S": self.nvar_s,
@@ -972,6 +977,8 @@ class OCModuleSource:
             defs["FUSED_DOUBLES"] = max(warp_doubles, fwarp_doubles)
         if getattr(self, "stage_inputs", 0):
             defs["OFF_IN"], defs["NIN"] = off_in, 2 * n + m
+        if getattr(self, "fwd_stage_inputs", 0):
+            defs["FOFF_IN"], defs["FNIN"] = foff_in, fnin
         header = ["// GENERATED by pontryagin_differentiable_programming_b200/codegen.py -- do not edit",
                   "#include <cuda_runtime.h>", "#include <math.h>", "#include <stdint.h>"]
         header += ["#define PDP_%s %d" % kv for kv in defs.items()]
@@ -1075,10 +1082,17 @@ class OCModuleSource:
         return []
 
     def _kernel_text(self):
-        bwd2 = _K_AUX_LQR_BWD2
+        from .kernel_templates import K_CP_ASYNC, K_FSTAGE_HELPERS, K_STAGE_HELPERS, staged_backward_kernel, staged_forward_kernel
+        bwd2, fwdk, prims = _K_AUX_LQR_BWD2, _K_AUX_LQR_FWD, ""
+        stage = ""
         if getattr(self, "stage_inputs", 0):
-            from .kernel_templates import K_STAGE_HELPERS, staged_backward_kernel
-            bwd2 = K_STAGE_HELPERS + staged_backward_kernel(_K_AUX_LQR_BWD2)
+            stage = K_STAGE_HELPERS
+            bwd2 = staged_backward_kernel(_K_AUX_LQR_BWD2)
+        if getattr(self, "fwd_stage_inputs", 0):
+            stage += K_FSTAGE_HELPERS
+            fwdk = staged_forward_kernel(_K_AUX_LQR_FWD)
+        if stage:
+            prims = K_CP_ASYNC + stage
         bwd = bwd2 if getattr(self, "bwd_pack", 1) == 2 else _K_AUX_LQR_BWD
         mw, launch_common = "", _K_LAUNCH_COMMON
         if getattr(self, "rollout_parts", 1) > 1:
@@ -1089,10 +1103,9 @@ class OCModuleSource:
         fused, launch = "", _K_LAUNCH_LQR
         if getattr(self, "fused", 0):
             from .kernel_templates import K_AUX_LQR_FUSED, as_device_functions, fused_launcher
-            stage = K_STAGE_HELPERS if getattr(self, "stage_inputs", 0) else ""
-            fused = "\n".join(as_device_functions(bwd2[len(stage):], _K_AUX_LQR_FWD)) + K_AUX_LQR_FUSED
+            fused = "\n".join(as_device_functions(bwd2, fwdk)) + K_AUX_LQR_FUSED
             launch = fused_launcher(_K_LAUNCH_LQR)
-        return _K_PRELUDE + _K_ROLLOUT_AUXEVAL + mw + _K_AUX_LQR_HEAD + bwd + _K_AUX_LQR_FWD + fused + launch_common + launch
+        return _K_PRELUDE + _K_ROLLOUT_AUXEVAL + mw + _K_AUX_LQR_HEAD + prims + bwd + fwdk + fused + launch_common + launch
 
     def _eval_macros(self):
         el = "tl" if getattr(self, "bwd_pack", 1) == 2 else "lane"       # evaluation lane = time step of the chunk
@@ -1107,7 +1120,8 @@ class OCModuleSource:
       if (%(el)s < PDP_CH && te < H)
         pdp_f_aux_slots(Xb + (size_t)te * PDP_N, Ub + (size_t)te * PDP_M, Lb + (size_t)te * PDP_N, TH, auxc + %(el)s * PDP_AUXLD);
     }""" % {"el": el}),
-            "@@EVAL_DYN@@": "        pdp_f_dyn_slots(X + ((size_t)be * (H + 1) + te) * PDP_N, U + ((size_t)be * H + te) * PDP_M, the, eo);",
+            "@@EVAL_DYN@@": ("        pdp_f_dyn_slots(fin, fin + PDP_N, the, eo);" if getattr(self, "fwd_stage_inputs", 0) else
+                             "        pdp_f_dyn_slots(X + ((size_t)be * (H + 1) + te) * PDP_N, U + ((size_t)be * H + te) * PDP_M, the, eo);"),
             "@@EVAL_DYN_COOP@@": "",
             "@@PREFETCH_AUX_CHUNK@@": "",      # measured: no gain (two-trajectory kernel) / a loss (one-trajectory kernel)
             "@@PREFETCH_DYN_CHUNK@@": """#if PDP_PF

@@ -775,7 +775,7 @@ def rollout_mw_launcher(launch_common_text):
 
 
 # ---- asynchronous staging of the per-chunk inputs of the two-trajectory backward kernel (option stage_inputs) ---------
-K_STAGE_HELPERS = r"""
+K_CP_ASYNC = r"""
 // The chunk evaluation (lanes = time steps) is the only place where the backward kernel waits for HBM: its rows of
 // X / U / Lam are therefore copied into shared memory with cp.async ONE CHUNK AHEAD (issued right after the current
 // chunk has been evaluated, so they overlap the chunk's Riccati steps) and the evaluator reads shared memory.
@@ -791,6 +791,9 @@ __device__ __forceinline__ void pdp_cp_async_wait() {
   asm volatile("cp.async.wait_all;" ::: "memory");
 #endif
 }
+"""
+
+K_STAGE_HELPERS = r"""
 // rows of steps tc .. tc+CH-1 of one trajectory: IN[s] = [x_t (n) | u_t (m) | lambda_{t+1} (n)], 16 team lanes cooperate
 __device__ __forceinline__ void pdp_stage_chunk(double* IN, const double* Xb, const double* Ub, const double* Lb, int tc, int H, int tl) {
   for (int idx = tl; idx < PDP_CH * PDP_NIN; idx += 16) {
@@ -820,4 +823,46 @@ def staged_backward_kernel(bwd2_text):
     t = _replace_once(t, "@@PREFETCH_AUX_CHUNK@@\n    __syncwarp();\n",
                       "@@PREFETCH_AUX_CHUNK@@\n    __syncwarp();\n"
                       "    if (tc >= PDP_CH) pdp_stage_chunk(IN, Xb, Ub, Lb, tc - PDP_CH, H, tl);     // overlaps the steps below\n")
+    return t
+
+
+# ---- the same staging for the forward kernel's chunk rows (option fwd_stage_inputs) ------------------------------------
+K_FSTAGE_HELPERS = r"""
+// rows of steps tc .. tc+CHF-1 of the warp's PDP_FG trajectories: FIN[s] = [x_t (n) | u_t (m) | xref_t (n) | uref_t (m)]
+__device__ __forceinline__ void pdp_fstage_chunk(double* wbase, const double* X, const double* U, const double* Xref,
+                                                 const double* Uref, int b0, int B, int tc, int H, int lane) {
+  for (int idx = lane; idx < PDP_FG * PDP_CHF * PDP_FNIN; idx += 32) {
+    const int g = idx / (PDP_CHF * PDP_FNIN), rem = idx - g * (PDP_CHF * PDP_FNIN);
+    const int s = rem / PDP_FNIN, e = rem - s * PDP_FNIN;
+    const int te = tc + s;
+    const int bb = (b0 + g < B) ? b0 + g : B - 1;
+    if (te < H) {
+      const double* src = nullptr;
+      if (e < PDP_N) src = X + ((size_t)bb * (H + 1) + te) * PDP_N + e;
+      else if (e < PDP_N + PDP_M) src = U + ((size_t)bb * H + te) * PDP_M + (e - PDP_N);
+      else if (e < 2 * PDP_N + PDP_M) { if (Xref) src = Xref + ((size_t)bb * (H + 1) + te) * PDP_N + (e - PDP_N - PDP_M); }
+      else if (Uref) src = Uref + ((size_t)bb * H + te) * PDP_M + (e - 2 * PDP_N - PDP_M);
+      if (src) pdp_cp_async8(wbase + g * PDP_FTS + PDP_FOFF_IN + s * PDP_FNIN + e, src);
+    }
+  }
+}
+"""
+
+
+def staged_forward_kernel(fwd_text):
+    """K_AUX_LQR_FWD (macros not yet expanded) with its chunk rows staged through shared memory one chunk ahead."""
+    t = fwd_text
+    t = _replace_once(t, "  #pragma unroll 1\n  for (int tc = 0; tc < H; tc += PDP_CHF) {\n    const int nst = (tc + PDP_CHF < H ? PDP_CHF : H - tc);\n    (void)nst;\n",
+                      "  pdp_fstage_chunk(wbase, X, U, fused ? Xref : nullptr, fused ? Uref : nullptr, b0, B, 0, H, lane);\n"
+                      "  #pragma unroll 1\n  for (int tc = 0; tc < H; tc += PDP_CHF) {\n    const int nst = (tc + PDP_CHF < H ? PDP_CHF : H - tc);\n    (void)nst;\n"
+                      "    pdp_cp_async_wait();     // this chunk's rows were requested one chunk ago\n    __syncwarp();\n")
+    t = _replace_once(t, "        const double* the = ereg + PDP_FOFF_TH;\n",
+                      "        const double* the = ereg + PDP_FOFF_TH;\n        const double* fin = ereg + PDP_FOFF_IN + se * PDP_FNIN;     // staged [x | u | xref | uref]\n        (void)fin;\n")
+    t = _replace_once(t, "          const double* xe = X + ((size_t)be * (H + 1) + te) * PDP_N;\n          const double* xr = Xref + ((size_t)be * (H + 1) + te) * PDP_N;\n",
+                      "          const double* xe = fin;\n          const double* xr = fin + PDP_N + PDP_M;\n")
+    t = _replace_once(t, "const double d = Uref ? U[((size_t)be * H + te) * PDP_M + i] - Uref[((size_t)be * H + te) * PDP_M + i] : 0.0;",
+                      "const double d = Uref ? fin[PDP_N + i] - fin[2 * PDP_N + PDP_M + i] : 0.0;")
+    t = _replace_once(t, "@@PREFETCH_DYN_CHUNK@@\n    __syncwarp();\n",
+                      "    __syncwarp();\n    if (tc + PDP_CHF < H)      // overlaps the steps below\n"
+                      "      pdp_fstage_chunk(wbase, X, U, fused ? Xref : nullptr, fused ? Uref : nullptr, b0, B, tc + PDP_CHF, H, lane);\n")
     return t

@@ -337,3 +337,27 @@ def test_emulated_staged_chunk_inputs_variant_is_identical(extra):
     emu = warp_emu.Emulator(src)
     g1 = emu.fused(X, U, L, th)[3] if extra.get("fused") else emu.backward(X, U, L, th)[0]
     assert np.array_equal(g0, g1)
+
+
+def test_emulated_forward_kernel_with_staged_chunk_rows_is_identical():
+    """Option fwd_stage_inputs: the forward kernel's per-chunk rows (x, u, xref, uref) staged through shared memory with
+    cp.async one chunk ahead; same dX / dU bit for bit and the same fused loss / chain rule, with and without demos."""
+    from pontryagin_differentiable_programming_b200 import systems
+    base = systems.quadrotor_irl(0.1).src
+    src = _variant(base, fwd_stage_inputs=1, fwd_chunk=10)
+    assert src.fwd_stage_inputs == 1 and "pdp_fstage_chunk" in src.source() and "pdp_fstage_chunk" not in base.source()
+    rng = np.random.default_rng(0)
+    B, H = 7, 23
+    X = 0.3 * rng.standard_normal((B, H + 1, 13))
+    X[:, :, 6] += 1.0
+    U = 2.5 + 0.3 * rng.standard_normal((B, H, 4))
+    L = 0.1 * rng.standard_normal((B, H, 13))
+    th = np.array([1, 1, 1, 1, 0.4, 1, 1, 5, 1.]) * (1 + 0.1 * rng.uniform(-1, 1, (B, 9)))
+    Xd, Ud = X + 0.1 * rng.standard_normal(X.shape), U + 0.1 * rng.standard_normal(U.shape)
+    e0, e1 = warp_emu.Emulator(base), warp_emu.Emulator(src)
+    g, _ = e0.backward(X, U, L, th)
+    for kwargs in (dict(Xref=Xd, Uref=Ud), dict(Xref=Xd), dict()):
+        a, b = e0.forward(X, U, th, g, **kwargs), e1.forward(X, U, th, g, **kwargs)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        if kwargs:
+            assert _rel(b[2], a[2]) < 1e-14

@@ -19,7 +19,7 @@ from tools.tune_aux_lqr import make
 dev = torch.device('cuda:0')
 x0, th, U, Xr, Ur = [torch.as_tensor(np.ascontiguousarray(a), device=dev) for a in bench.synth_quadrotor(37, 19, seed=4)]
 ref = make().sweep(x0, th, U, Xref=Xr, Uref=Ur)
-new = make(fused=1, stream_out=1, rollout_parts=4, stage_inputs=1).sweep(x0, th, U, Xref=Xr, Uref=Ur)
+new = make(fused=1, stream_out=1, rollout_parts=4, stage_inputs=1, fwd_stage_inputs=1).sweep(x0, th, U, Xref=Xr, Uref=Ur)
 torch.cuda.synchronize()
 for k in ("X", "Lam", "cost", "dX", "dU", "loss_dp"):
     d = float((ref[k] - new[k]).abs().max() / ref[k].abs().max())
