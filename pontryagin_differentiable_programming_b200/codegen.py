@@ -195,13 +195,8 @@ class OCModuleSource:
                  chunk: int = 8, warps_per_block: int = 4, min_blocks: int = 1, fwd_warps_per_block: int = 4,
                  fwd_min_blocks: int = 1, keep_fg: bool = True, fast_rcp: bool = False, early_solve: bool = False,
                  fwd_pack: int = 0, fwd_chunk: int = 0, bwd_pack: int = 1, fwd_vec: int = -1, prefetch: int = 2,
-                 prefetch_dist: int = 2, inline_eval: int = -1, h_group: int = 1, prefetch_l1_lead: int = 0, fused: int = 0, stream_out: int = 0, rollout_parts: int = 1, stage_inputs: int = 0, fwd_stage_inputs: int = 0):
+                 prefetch_dist: int = 2, inline_eval: int = -1, h_group: int = 1, prefetch_l1_lead: int = 0):
         self.keep_fg = bool(keep_fg)
-        self.stage_inputs = int(stage_inputs)
-        self.fwd_stage_inputs = int(fwd_stage_inputs)
-        self.rollout_parts = max(1, min(int(rollout_parts), 8))
-        self.fused = int(fused)
-        self.stream_out = int(stream_out)
         self.prefetch_l1_lead = int(prefetch_l1_lead)
         self.h_group = int(h_group)
         self.inline_eval = int(inline_eval)
@@ -245,14 +240,6 @@ class OCModuleSource:
             self.bwd_pack = 1          # the two-rows-per-lane layout needs n <= 16 and m + r <= 16
         if self.bwd_pack == 2:
             self.chunk = min(self.chunk, 16)
-        if self.stage_inputs and (self.bwd_pack != 2 or type(self)._eval_macros is not OCModuleSource._eval_macros):
-            self.stage_inputs = 0             # only the two-trajectory kernel of modules that evaluate their own slots
-        if self.fwd_stage_inputs and type(self)._eval_macros is not OCModuleSource._eval_macros:
-            self.fwd_stage_inputs = 0
-        if self.fused and self.bwd_pack != 2:
-            self.fused = 0
-        if self.fused:
-            self.fwd_pack = 2                 # the forward half works on the same two trajectories as the backward half
         self._layout()
 
     def _customise(self):
@@ -447,39 +434,6 @@ class OCModuleSource:
             dense += [M.at(i, j) for i in range(M.shape[0]) for j in range(M.shape[1])]
         parts.append(_emit_function("pdp_f_aux_dense", [x, u, lam, th], dense, lambda i: "out[%d]" % i))
         return "\n\n".join(parts)
-
-    # ---- multi-warp rollout: the outputs of f / dH/dx split over the warps of a block -------------------------
-    @staticmethod
-    def _partition_outputs(nodes, parts):
-        """Greedy split of output expressions over ``parts`` groups, balancing the size of each group's expression cone
-        (shared sub-expressions are duplicated between groups).  -> list of index lists."""
-        cones = [{nd.uid for nd in S.topo_order([e]) if nd.op not in ("sym", "const")} for e in nodes]
-        groups = [[] for _ in range(parts)]
-        unions = [set() for _ in range(parts)]
-        for i in sorted(range(len(nodes)), key=lambda k: -len(cones[k])):
-            p = min(range(parts), key=lambda q: (len(unions[q] | cones[i]), len(groups[q])))
-            groups[p].append(i)
-            unions[p] |= cones[i]
-        return [sorted(g) for g in groups], [len(u_) for u_ in unions]
-
-    def _rollout_mw(self):
-        """(device functions, defines, kernel text) of the multi-warp rollout kernel."""
-        P = self.rollout_parts
-        x, u, th, lam = ("x", self.x), ("u", self.u), ("th", self.th), ("lam", self.lam)
-        dyn, dhx = self.dyn.elements(), self.dHx.elements()
-        gd, cd = self._partition_outputs(dyn, P)
-        gh, ch = self._partition_outputs(dhx, P)
-        fns, sw_d, sw_h = [], [], []
-        for p in range(P):
-            fns.append(_emit_function("pdp_f_dyn_part%d" % p, [x, u, th], [dyn[i] for i in gd[p]] or [S.ZERO], lambda i: "out[%d]" % i))
-            fns.append(_emit_function("pdp_f_dHx_part%d" % p, [x, u, lam, th], [dhx[i] for i in gh[p]] or [S.ZERO], lambda i: "out[%d]" % i))
-            sw_d.append("    if (part == %d) { pdp_f_dyn_part%d(x, u, th, tmp); %s }"
-                        % (p, p, " ".join("XS[buf][%d][lane] = tmp[%d];" % (i, k) for k, i in enumerate(gd[p]))))
-            sw_h.append("        if (part == %d) { pdp_f_dHx_part%d(x, u, lam, th, tmp); %s }"
-                        % (p, p, " ".join("XS[buf][%d][lane] = tmp[%d];" % (i, k) for k, i in enumerate(gh[p]))))
-        defs = {"RP": P, "RP_COST": min(range(P), key=lambda q: cd[q]), "RP_DHU": min(range(P), key=lambda q: ch[q])}
-        text = _K_ROLLOUT_MW.replace("@@MW_DYN_SWITCH@@", "\n".join(sw_d)).replace("@@MW_DHX_SWITCH@@", "\n".join(sw_h))
-        return "\n\n".join(fns), defs, text
 
     # ---- the Riccati step body ---------------------------------------------------------------------
     def _backward_step(self) -> str:
@@ -836,7 +790,7 @@ class OCModuleSource:
         fg = max(1, min(fg, WARP // gs, WARP))
         ch = getattr(self, "fwd_chunk", 0)
         if not ch:
-            per_step = _pad_ld(self.nvar_s) + self.n + self.m + (2 * (self.n + self.m) if getattr(self, "fwd_stage_inputs", 0) else 0)
+            per_step = _pad_ld(self.nvar_s) + self.n + self.m
             fit = (self.fwd_smem_budget // (8 * fg) - self.n * self.m - max(self.nth, 1) - 16) // per_step
             ch = min(WARP // fg if fg > 1 else self.chunk, max(fit, 1))
         ch = max(1, min(ch, WARP // fg))
@@ -941,9 +895,6 @@ class OCModuleSource:
         off_quu = off_ks + ks_size
         off_th = off_quu + _even(m * m)
         warp_doubles = _even(off_th + max(self.nth, 1))
-        off_in = warp_doubles
-        if getattr(self, "stage_inputs", 0):
-            warp_doubles = _even(off_in + self.chunk * (2 * n + m))
         bp = getattr(self, "bwd_pack", 1)
         half_stride = _pad_ld(warp_doubles)       # two-trajectory kernel: per-trajectory regions = 2 (mod 16) doubles apart
         if bp == 2:
@@ -955,9 +906,7 @@ class OCModuleSource:
         foff_th = foff_ks + _even(n * m)
         foff_dl = foff_th + _even(max(self.nth, 1))               # residuals x - xref [CHF*n], u - uref [CHF*m]
         foff_du = foff_dl + chf * n
-        foff_in = _even(foff_du + chf * m)
-        fnin = 2 * (n + m)
-        fts = _pad_ld(foff_in + chf * fnin) if getattr(self, "fwd_stage_inputs", 0) else _pad_ld(foff_du + chf * m)
+        fts = _pad_ld(foff_du + chf * m)
         fwarp_doubles = max(fg * fts, WARP)
         defs = {
             "N": n, "M": m, "R": r, "NS": ns, "NM": nm, "NVAR": self.nvar, "NVAR_S": self.nvar_s,
@@ -973,12 +922,6 @@ class OCModuleSource:
             "PF": getattr(self, "prefetch", 0), "PFD": max(1, getattr(self, "prefetch_dist", 3)),
             "PFL": max(0, getattr(self, "prefetch_l1_lead", 0)),
         }
-        if getattr(self, "fused", 0):
-            defs["FUSED_DOUBLES"] = max(warp_doubles, fwarp_doubles)
-        if getattr(self, "stage_inputs", 0):
-            defs["OFF_IN"], defs["NIN"] = off_in, 2 * n + m
-        if getattr(self, "fwd_stage_inputs", 0):
-            defs["FOFF_IN"], defs["FNIN"] = foff_in, fnin
         header = ["// GENERATED by pontryagin_differentiable_programming_b200/codegen.py -- do not edit",
                   "#include <cuda_runtime.h>", "#include <math.h>", "#include <stdint.h>"]
         header += ["#define PDP_%s %d" % kv for kv in defs.items()]
@@ -1045,14 +988,10 @@ class OCModuleSource:
         gndecl = "double " + ", ".join("gn%d = 0.0" % a for a in range(m)) + ";"
         gcur = "      const double " + ", ".join("g%d = gn%d" % (a, a) for a in range(m)) + ";"
         kq_setup, gnload, ks_store = self._fwd_gain_prefetch(fg)
-        if getattr(self, "stream_out", 0):
-            # streaming (evict-first) stores for dX / dU: they are never re-read by these kernels, while the gain spill
-            # should stay in L2 for the forward half of the fused kernel
-            xstore = "\n".join("          __stcs(o + %d, n%d);" % (i * r, i) for i in range(n))
-            ustore = "\n".join("          __stcs(o + %d, u%d);" % (a * r, a) for a in range(m))
-        else:
-            xstore = "\n".join("          o[%d] = n%d;" % (i * r, i) for i in range(n))
-            ustore = "\n".join("          o[%d] = u%d;" % (a * r, a) for a in range(m))
+        # streaming (evict-first) stores for dX / dU: nothing on the device re-reads them, so they should not displace
+        # the gain records / chunk rows in L2 (measured r2a: forward kernel 0.4033 -> 0.4002 ms)
+        xstore = "\n".join("          __stcs(o + %d, n%d);" % (i * r, i) for i in range(n))
+        ustore = "\n".join("          __stcs(o + %d, u%d);" % (a * r, a) for a in range(m))
         xcopy = "\n".join("      x%d = n%d;" % (k, k) for k in range(n))
         x0store = "\n".join("    o[%d] = x%d;" % (i * r, i) for i in range(n))
 
@@ -1082,46 +1021,19 @@ class OCModuleSource:
         return []
 
     def _kernel_text(self):
-        from .kernel_templates import K_CP_ASYNC, K_FSTAGE_HELPERS, K_STAGE_HELPERS, staged_backward_kernel, staged_forward_kernel
-        bwd2, fwdk, prims = _K_AUX_LQR_BWD2, _K_AUX_LQR_FWD, ""
-        stage = ""
-        if getattr(self, "stage_inputs", 0):
-            stage = K_STAGE_HELPERS
-            bwd2 = staged_backward_kernel(_K_AUX_LQR_BWD2)
-        if getattr(self, "fwd_stage_inputs", 0):
-            stage += K_FSTAGE_HELPERS
-            fwdk = staged_forward_kernel(_K_AUX_LQR_FWD)
-        if stage:
-            prims = K_CP_ASYNC + stage
-        bwd = bwd2 if getattr(self, "bwd_pack", 1) == 2 else _K_AUX_LQR_BWD
-        mw, launch_common = "", _K_LAUNCH_COMMON
-        if getattr(self, "rollout_parts", 1) > 1:
-            from .kernel_templates import rollout_mw_launcher
-            fns, mwdefs, text = self._rollout_mw()
-            mw = "\n".join("#define PDP_%s %d" % kv for kv in mwdefs.items()) + "\n" + fns + "\n" + text
-            launch_common = rollout_mw_launcher(_K_LAUNCH_COMMON)
-        fused, launch = "", _K_LAUNCH_LQR
-        if getattr(self, "fused", 0):
-            from .kernel_templates import K_AUX_LQR_FUSED, as_device_functions, fused_launcher
-            fused = "\n".join(as_device_functions(bwd2, fwdk)) + K_AUX_LQR_FUSED
-            launch = fused_launcher(_K_LAUNCH_LQR)
-        return _K_PRELUDE + _K_ROLLOUT_AUXEVAL + mw + _K_AUX_LQR_HEAD + prims + bwd + fwdk + fused + launch_common + launch
+        bwd = _K_AUX_LQR_BWD2 if getattr(self, "bwd_pack", 1) == 2 else _K_AUX_LQR_BWD
+        return _K_PRELUDE + _K_ROLLOUT_AUXEVAL + _K_AUX_LQR_HEAD + bwd + _K_AUX_LQR_FWD + _K_LAUNCH_COMMON + _K_LAUNCH_LQR
 
     def _eval_macros(self):
         el = "tl" if getattr(self, "bwd_pack", 1) == 2 else "lane"       # evaluation lane = time step of the chunk
         return {
             "@@EVAL_TERM@@": "  if (%s == 0) pdp_f_terminal(Xb + (size_t)H * PDP_N, TH, TB);" % el,
-            "@@EVAL_AUX_CHUNK@@": ("""    {
-      const int te = tc + tl;
-      if (tl < PDP_CH && te < H)      // inputs from the rows staged in shared memory one chunk ago
-        pdp_f_aux_slots(IN + tl * PDP_NIN, IN + tl * PDP_NIN + PDP_N, IN + tl * PDP_NIN + PDP_N + PDP_M, TH, auxc + tl * PDP_AUXLD);
-    }""" if getattr(self, "stage_inputs", 0) else """    {
+            "@@EVAL_AUX_CHUNK@@": """    {
       const int te = tc + %(el)s;
       if (%(el)s < PDP_CH && te < H)
         pdp_f_aux_slots(Xb + (size_t)te * PDP_N, Ub + (size_t)te * PDP_M, Lb + (size_t)te * PDP_N, TH, auxc + %(el)s * PDP_AUXLD);
-    }""" % {"el": el}),
-            "@@EVAL_DYN@@": ("        pdp_f_dyn_slots(fin, fin + PDP_N, the, eo);" if getattr(self, "fwd_stage_inputs", 0) else
-                             "        pdp_f_dyn_slots(X + ((size_t)be * (H + 1) + te) * PDP_N, U + ((size_t)be * H + te) * PDP_M, the, eo);"),
+    }""" % {"el": el},
+            "@@EVAL_DYN@@": "        pdp_f_dyn_slots(X + ((size_t)be * (H + 1) + te) * PDP_N, U + ((size_t)be * H + te) * PDP_M, the, eo);",
             "@@EVAL_DYN_COOP@@": "",
             "@@PREFETCH_AUX_CHUNK@@": "",      # measured: no gain (two-trajectory kernel) / a loss (one-trajectory kernel)
             "@@PREFETCH_DYN_CHUNK@@": """#if PDP_PF
@@ -1350,4 +1262,4 @@ class LQRModuleSource(OCModuleSource):
 from .kernel_templates import (  # noqa: E402
     K_AUX_LQR_BWD as _K_AUX_LQR_BWD, K_AUX_LQR_BWD2 as _K_AUX_LQR_BWD2, K_AUX_LQR_FWD as _K_AUX_LQR_FWD,
     K_AUX_LQR_HEAD as _K_AUX_LQR_HEAD, K_AUX_LQR as _K_AUX_LQR, K_LAUNCH_COMMON as _K_LAUNCH_COMMON, K_LAUNCH_LQR as _K_LAUNCH_LQR,
-    K_PRELUDE as _K_PRELUDE, K_ROLLOUT_AUXEVAL as _K_ROLLOUT_AUXEVAL, K_ROLLOUT_MW as _K_ROLLOUT_MW)
+    K_PRELUDE as _K_PRELUDE, K_ROLLOUT_AUXEVAL as _K_ROLLOUT_AUXEVAL)

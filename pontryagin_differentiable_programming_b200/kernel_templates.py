@@ -593,276 +593,3 @@ _if = K_AUX_LQR.index('extern "C" __global__ void __launch_bounds__(PDP_WPBF * 3
 K_AUX_LQR_HEAD, K_AUX_LQR_BWD, K_AUX_LQR_FWD = K_AUX_LQR[:_ib], K_AUX_LQR[_ib:_if], K_AUX_LQR[_if:]
 
 
-# ---- fused backward + forward kernel (option `fused` of the OC module; two-trajectory layout only) -----------------
-K_AUX_LQR_FUSED = r"""
-// One warp: Riccati sweep of its two trajectories, then their forward pass at once -- the gain spill is re-read while
-// it is still in L2 (the latest records first).  The two halves are the bodies of pdp_k_aux_lqr_bwd / _fwd compiled as
-// device functions on the same per-warp shared-memory region.
-extern "C" __global__ void __launch_bounds__(PDP_WPB * 32, PDP_MINB)
-pdp_k_aux_lqr_fused(int B, int H, const double* __restrict__ X, const double* __restrict__ U, const double* __restrict__ Lam,
-                    const double* __restrict__ theta, int theta_stride, const double* __restrict__ X0a, int x0a_stride,
-                    double* __restrict__ dX, double* __restrict__ dU, double* gains,
-                    const double* __restrict__ Xref, const double* __restrict__ Uref, double* __restrict__ loss_dp,
-                    const double* __restrict__ auxrec, const double* __restrict__ termrec, int* __restrict__ status)
-{
-  extern __shared__ __align__(16) double pdp_smem[];
-  const int pdp_warp = blockIdx.x * PDP_WPB + (threadIdx.x >> 5);
-  if (pdp_warp * 2 >= B) return;
-  double* ws = pdp_smem + (size_t)(threadIdx.x >> 5) * PDP_FUSED_DOUBLES;
-  pdp_dev_aux_lqr_bwd(pdp_warp, ws, B, H, X, U, Lam, theta, theta_stride, gains, auxrec, termrec, status);
-  __syncwarp();            // the records were written by their owning lanes and are read by other lanes below
-  pdp_dev_aux_lqr_fwd(pdp_warp, ws, B, H, X, U, theta, theta_stride, X0a, x0a_stride, dX, dU, gains, Xref, Uref, loss_dp,
-                      auxrec, status);
-}
-"""
-
-
-K_LAUNCH_FUSED_BRANCH = r"""  if (phases == 3) {   // backward sweep and forward pass of a warp's two trajectories back to back in ONE kernel
-    static bool configured_fused[64] = {false};
-    const size_t smem_x = (size_t)PDP_WPB * PDP_FUSED_DOUBLES * sizeof(double);
-    if (!configured_fused[dev_ & 63]) {
-      cudaError_t e = cudaFuncSetAttribute(pdp_k_aux_lqr_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x);
-      if (e != cudaSuccess) return (int)e;
-      configured_fused[dev_ & 63] = true;
-    }
-    pdp_k_aux_lqr_fused<<<(B + PDP_WPB * 2 - 1) / (PDP_WPB * 2), PDP_WPB * 32, smem_x, st>>>(
-        B, H, X, U, Lam, theta, theta_stride, X0a, x0a_stride, dX, dU, gains, Xref, Uref, loss_dp, auxrec, termrec, status);
-    return (int)cudaGetLastError();
-  }
-"""
-
-
-def _replace_once(text, old, new):
-    assert text.count(old) == 1, (old, text.count(old))
-    return text.replace(old, new)
-
-
-def as_device_functions(bwd2_text, fwd_text):
-    """The (already macro-expanded or not) texts of the two-trajectory backward kernel and of the forward kernel turned
-    into ``__device__`` functions pdp_dev_aux_lqr_bwd / pdp_dev_aux_lqr_fwd(pdp_warp, pdp_wsmem, <kernel arguments>)."""
-    b = bwd2_text
-    b = _replace_once(b, 'extern "C" __global__ void __launch_bounds__(PDP_WPB * 32, PDP_MINB)\npdp_k_aux_lqr_bwd(int B,',
-                      '__device__ __forceinline__ void pdp_dev_aux_lqr_bwd(const int pdp_warp, double* pdp_wsmem, int B,')
-    b = _replace_once(b, "  extern __shared__ __align__(16) double pdp_smem[];\n", "")
-    b = _replace_once(b, "const int b0 = (blockIdx.x * PDP_WPB + (threadIdx.x >> 5)) * 2;", "const int b0 = pdp_warp * 2;")
-    b = _replace_once(b, "double* auxc = pdp_smem + (size_t)(threadIdx.x >> 5) * PDP_WARP_DOUBLES + half * PDP_HS;",
-                      "double* auxc = pdp_wsmem + half * PDP_HS;")
-    b = _replace_once(b, "double* __restrict__ gains,", "double* gains,")
-    f = fwd_text
-    f = _replace_once(f, 'extern "C" __global__ void __launch_bounds__(PDP_WPBF * 32, PDP_MINBF)\npdp_k_aux_lqr_fwd(int B,',
-                      '__device__ __forceinline__ void pdp_dev_aux_lqr_fwd(const int pdp_warp, double* pdp_wsmem, int B,')
-    f = _replace_once(f, "  extern __shared__ __align__(16) double pdp_smem[];\n", "")
-    f = _replace_once(f, "const int b0 = (blockIdx.x * PDP_WPBF + (threadIdx.x >> 5)) * PDP_FG;", "const int b0 = pdp_warp * PDP_FG;")
-    f = _replace_once(f, "double* wbase = pdp_smem + (size_t)(threadIdx.x >> 5) * PDP_FWARP_DOUBLES;", "double* wbase = pdp_wsmem;")
-    f = _replace_once(f, "const double* __restrict__ gains,", "const double* gains,")
-    return b, f
-
-
-def fused_launcher(launch_text):
-    """K_LAUNCH_LQR with the fused branch in front of the two-kernel launches (phases == 3 only)."""
-    return _replace_once(launch_text, "  if (phases & 1)\n    pdp_k_aux_lqr_bwd<<<", K_LAUNCH_FUSED_BRANCH + "  if (phases & 1)\n    pdp_k_aux_lqr_bwd<<<")
-
-
-# ---- rollout / costate kernel with the per-step derivative code split over the warps of a block (option rollout_parts)
-K_ROLLOUT_MW = r"""
-// =====================================================================================================
-// Kernel 1b: rollout + cost + costate recursion with PDP_RP WARPS PER 32 TRAJECTORIES.  The one-thread-per-trajectory
-// kernel is latency-bound (one warp per scheduler executing ~300 dependent instructions per step): here warp p of a block
-// evaluates only its share of the outputs of f / dH/dx for the block's 32 trajectories, the shares are exchanged through a
-// double-buffered shared-memory tile and ONE __syncthreads per step, and every warp keeps the full state / costate in
-// registers.  Same inputs, outputs and semantics as pdp_k_rollout_costate without the closed-loop mode.
-// =====================================================================================================
-extern "C" __global__ void __launch_bounds__(PDP_RP * 32)
-pdp_k_rollout_costate_mw(int B, int H, const double* __restrict__ x0, const double* __restrict__ theta, int theta_stride,
-                         const double* __restrict__ U, double* __restrict__ X, double* __restrict__ Lam,
-                         double* __restrict__ cost, double* __restrict__ dHu, int* __restrict__ status)
-{
-  __shared__ double XS[2][PDP_N][32];
-  const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
-  const int bq = blockIdx.x * 32 + lane;
-  const bool live = bq < B;
-  const int b = live ? bq : B - 1;                     // idle lanes shadow a valid trajectory (they must reach the barriers)
-  double x[PDP_N], th[PDP_NTH], u[PDP_M], tmp[PDP_N > PDP_M ? PDP_N : PDP_M];
-  #pragma unroll
-  for (int i = 0; i < PDP_NTH; ++i) th[i] = theta[(size_t)b * theta_stride + i];
-  #pragma unroll
-  for (int i = 0; i < PDP_N; ++i) x[i] = x0[(size_t)b * PDP_N + i];
-  double J = 0.0;
-  double* Xb = X + (size_t)b * (H + 1) * PDP_N;
-  const double* Ub = U + (size_t)b * H * PDP_M;
-  pdp_row_raw<PDP_M> una, unb;
-  pdp_row_issue<PDP_M>(una, Ub);
-  pdp_row_issue<PDP_M>(unb, Ub + (H > 1 ? 1 : 0) * PDP_M);
-  int buf = 0;
-  auto fstep = [&](const int t, pdp_row_raw<PDP_M>& un) {
-    pdp_row_unpack<PDP_M>(u, un);
-    pdp_row_issue<PDP_M>(un, Ub + (t + 2 < H ? t + 2 : H - 1) * PDP_M);
-    if (live && part == t % PDP_RP) pdp_row_store<PDP_N>(Xb + t * PDP_N, x);       // the row stores rotate over the warps
-    if (part == PDP_RP_COST) { pdp_f_path_cost(x, u, th, tmp); J += tmp[0]; }
-@@MW_DYN_SWITCH@@
-    __syncthreads();
-    #pragma unroll
-    for (int i = 0; i < PDP_N; ++i) x[i] = XS[buf][i][lane];
-    buf ^= 1;
-  };
-  #pragma unroll 1
-  for (int t = 0; t < H; t += 2) {
-    fstep(t, una);
-    if (t + 1 < H) fstep(t + 1, unb);
-  }
-  if (live && part == H % PDP_RP) pdp_row_store<PDP_N>(Xb + H * PDP_N, x);
-  if (part == PDP_RP_COST) {
-    pdp_f_final_cost(x, th, tmp);
-    J += tmp[0];
-    if (live && cost) cost[b] = J;
-    if (live && status && !isfinite(J)) atomicOr(&status[b], 1);
-  }
-  if (Lam != nullptr) {
-    double lam[PDP_N], gu[PDP_M];
-    double* Lb = Lam + (size_t)b * H * PDP_N;
-    pdp_f_dhx(x, th, lam);
-    pdp_row_raw<PDP_N> xpa, xpb;
-    pdp_row_raw<PDP_M> upa, upb;
-    __syncthreads();                      // every warp has stored its X rows before any warp reads them back
-    pdp_row_issue<PDP_N>(xpa, Xb + (H - 1) * PDP_N);
-    pdp_row_issue<PDP_M>(upa, Ub + (H - 1) * PDP_M);
-    pdp_row_issue<PDP_N>(xpb, Xb + (H > 1 ? H - 2 : 0) * PDP_N);
-    pdp_row_issue<PDP_M>(upb, Ub + (H > 1 ? H - 2 : 0) * PDP_M);
-    auto bstep = [&](const int t, pdp_row_raw<PDP_N>& xp, pdp_row_raw<PDP_M>& up) {
-      if (live && part == t % PDP_RP) pdp_row_store<PDP_N>(Lb + t * PDP_N, lam);
-      pdp_row_unpack<PDP_N>(x, xp);
-      pdp_row_unpack<PDP_M>(u, up);
-      {
-        const int tq = t > 1 ? t - 2 : 0;
-        pdp_row_issue<PDP_N>(xp, Xb + tq * PDP_N);
-        pdp_row_issue<PDP_M>(up, Ub + tq * PDP_M);
-      }
-      if (dHu != nullptr && part == PDP_RP_DHU) {
-        pdp_f_dHu(x, u, lam, th, gu);
-        if (live) {
-          #pragma unroll
-          for (int i = 0; i < PDP_M; ++i) dHu[((size_t)b * H + t) * PDP_M + i] = gu[i];
-        }
-      }
-      if (t > 0) {
-@@MW_DHX_SWITCH@@
-        __syncthreads();
-        #pragma unroll
-        for (int i = 0; i < PDP_N; ++i) lam[i] = XS[buf][i][lane];
-        buf ^= 1;
-      }
-    };
-    #pragma unroll 1
-    for (int t = H - 1; t >= 0; t -= 2) {
-      bstep(t, xpa, upa);
-      if (t > 0) bstep(t - 1, xpb, upb);
-    }
-  }
-}
-"""
-
-K_LAUNCH_ROLLOUT_MW_BRANCH = r"""  if (fb_gains == nullptr) {   // open-loop rollout: the derivative code is split over PDP_RP warps per 32 trajectories
-    pdp_k_rollout_costate_mw<<<(B + 31) / 32, PDP_RP * 32, 0, st>>>(B, H, x0, theta, theta_stride, U, X, Lam, cost, dHu, status);
-    return (int)cudaGetLastError();
-  }
-"""
-
-
-def rollout_mw_launcher(launch_common_text):
-    """K_LAUNCH_COMMON with the multi-warp rollout in front of the one-thread-per-trajectory launch."""
-    return _replace_once(launch_common_text, "  pdp_k_rollout_costate<<<(B + 127) / 128, 128, 0, st>>>(",
-                         K_LAUNCH_ROLLOUT_MW_BRANCH + "  pdp_k_rollout_costate<<<(B + 127) / 128, 128, 0, st>>>(")
-
-
-# ---- asynchronous staging of the per-chunk inputs of the two-trajectory backward kernel (option stage_inputs) ---------
-K_CP_ASYNC = r"""
-// The chunk evaluation (lanes = time steps) is the only place where the backward kernel waits for HBM: its rows of
-// X / U / Lam are therefore copied into shared memory with cp.async ONE CHUNK AHEAD (issued right after the current
-// chunk has been evaluated, so they overlap the chunk's Riccati steps) and the evaluator reads shared memory.
-__device__ __forceinline__ void pdp_cp_async8(double* dst_shared, const double* src_global) {
-#ifdef __CUDACC__
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(dst_shared)), "l"(src_global) : "memory");
-#else
-  *dst_shared = *src_global;      /* CPU emulation: immediate copy */
-#endif
-}
-__device__ __forceinline__ void pdp_cp_async_wait() {
-#ifdef __CUDACC__
-  asm volatile("cp.async.wait_all;" ::: "memory");
-#endif
-}
-"""
-
-K_STAGE_HELPERS = r"""
-// rows of steps tc .. tc+CH-1 of one trajectory: IN[s] = [x_t (n) | u_t (m) | lambda_{t+1} (n)], 16 team lanes cooperate
-__device__ __forceinline__ void pdp_stage_chunk(double* IN, const double* Xb, const double* Ub, const double* Lb, int tc, int H, int tl) {
-  for (int idx = tl; idx < PDP_CH * PDP_NIN; idx += 16) {
-    const int s = idx / PDP_NIN, e = idx - s * PDP_NIN;
-    const int te = tc + s;
-    if (te < H) {
-      const double* src = e < PDP_N ? Xb + (size_t)te * PDP_N + e
-                        : (e < PDP_N + PDP_M ? Ub + (size_t)te * PDP_M + (e - PDP_N) : Lb + (size_t)te * PDP_N + (e - PDP_N - PDP_M));
-      pdp_cp_async8(IN + idx, src);
-    }
-  }
-}
-"""
-
-
-def staged_backward_kernel(bwd2_text):
-    """K_AUX_LQR_BWD2 with the chunk inputs staged through shared memory one chunk ahead (see K_STAGE_HELPERS)."""
-    t = bwd2_text
-    t = _replace_once(t, "  double* TB = auxc;                                                         // terminal buffer aliases the chunk buffer\n",
-                      "  double* TB = auxc;                                                         // terminal buffer aliases the chunk buffer\n"
-                      "  double* IN = auxc + PDP_OFF_IN;                                            // staged rows of the next chunk\n")
-    t = _replace_once(t, "  #pragma unroll 1\n  for (int tc = ((H - 1) / PDP_CH) * PDP_CH; tc >= 0; tc -= PDP_CH) {\n    __syncwarp();            // every lane is done reading the previous chunk's slots\n",
-                      "  pdp_stage_chunk(IN, Xb, Ub, Lb, ((H - 1) / PDP_CH) * PDP_CH, H, tl);\n"
-                      "  #pragma unroll 1\n  for (int tc = ((H - 1) / PDP_CH) * PDP_CH; tc >= 0; tc -= PDP_CH) {\n"
-                      "    pdp_cp_async_wait();     // this chunk's rows were requested one chunk ago\n"
-                      "    __syncwarp();            // ... and every lane is done reading the previous chunk's slots\n")
-    t = _replace_once(t, "@@PREFETCH_AUX_CHUNK@@\n    __syncwarp();\n",
-                      "@@PREFETCH_AUX_CHUNK@@\n    __syncwarp();\n"
-                      "    if (tc >= PDP_CH) pdp_stage_chunk(IN, Xb, Ub, Lb, tc - PDP_CH, H, tl);     // overlaps the steps below\n")
-    return t
-
-
-# ---- the same staging for the forward kernel's chunk rows (option fwd_stage_inputs) ------------------------------------
-K_FSTAGE_HELPERS = r"""
-// rows of steps tc .. tc+CHF-1 of the warp's PDP_FG trajectories: FIN[s] = [x_t (n) | u_t (m) | xref_t (n) | uref_t (m)]
-__device__ __forceinline__ void pdp_fstage_chunk(double* wbase, const double* X, const double* U, const double* Xref,
-                                                 const double* Uref, int b0, int B, int tc, int H, int lane) {
-  for (int idx = lane; idx < PDP_FG * PDP_CHF * PDP_FNIN; idx += 32) {
-    const int g = idx / (PDP_CHF * PDP_FNIN), rem = idx - g * (PDP_CHF * PDP_FNIN);
-    const int s = rem / PDP_FNIN, e = rem - s * PDP_FNIN;
-    const int te = tc + s;
-    const int bb = (b0 + g < B) ? b0 + g : B - 1;
-    if (te < H) {
-      const double* src = nullptr;
-      if (e < PDP_N) src = X + ((size_t)bb * (H + 1) + te) * PDP_N + e;
-      else if (e < PDP_N + PDP_M) src = U + ((size_t)bb * H + te) * PDP_M + (e - PDP_N);
-      else if (e < 2 * PDP_N + PDP_M) { if (Xref) src = Xref + ((size_t)bb * (H + 1) + te) * PDP_N + (e - PDP_N - PDP_M); }
-      else if (Uref) src = Uref + ((size_t)bb * H + te) * PDP_M + (e - 2 * PDP_N - PDP_M);
-      if (src) pdp_cp_async8(wbase + g * PDP_FTS + PDP_FOFF_IN + s * PDP_FNIN + e, src);
-    }
-  }
-}
-"""
-
-
-def staged_forward_kernel(fwd_text):
-    """K_AUX_LQR_FWD (macros not yet expanded) with its chunk rows staged through shared memory one chunk ahead."""
-    t = fwd_text
-    t = _replace_once(t, "  #pragma unroll 1\n  for (int tc = 0; tc < H; tc += PDP_CHF) {\n    const int nst = (tc + PDP_CHF < H ? PDP_CHF : H - tc);\n    (void)nst;\n",
-                      "  pdp_fstage_chunk(wbase, X, U, fused ? Xref : nullptr, fused ? Uref : nullptr, b0, B, 0, H, lane);\n"
-                      "  #pragma unroll 1\n  for (int tc = 0; tc < H; tc += PDP_CHF) {\n    const int nst = (tc + PDP_CHF < H ? PDP_CHF : H - tc);\n    (void)nst;\n"
-                      "    pdp_cp_async_wait();     // this chunk's rows were requested one chunk ago\n    __syncwarp();\n")
-    t = _replace_once(t, "        const double* the = ereg + PDP_FOFF_TH;\n",
-                      "        const double* the = ereg + PDP_FOFF_TH;\n        const double* fin = ereg + PDP_FOFF_IN + se * PDP_FNIN;     // staged [x | u | xref | uref]\n        (void)fin;\n")
-    t = _replace_once(t, "          const double* xe = X + ((size_t)be * (H + 1) + te) * PDP_N;\n          const double* xr = Xref + ((size_t)be * (H + 1) + te) * PDP_N;\n",
-                      "          const double* xe = fin;\n          const double* xr = fin + PDP_N + PDP_M;\n")
-    t = _replace_once(t, "const double d = Uref ? U[((size_t)be * H + te) * PDP_M + i] - Uref[((size_t)be * H + te) * PDP_M + i] : 0.0;",
-                      "const double d = Uref ? fin[PDP_N + i] - fin[2 * PDP_N + PDP_M + i] : 0.0;")
-    t = _replace_once(t, "@@PREFETCH_DYN_CHUNK@@\n    __syncwarp();\n",
-                      "    __syncwarp();\n    if (tc + PDP_CHF < H)      // overlaps the steps below\n"
-                      "      pdp_fstage_chunk(wbase, X, U, fused ? Xref : nullptr, fused ? Uref : nullptr, b0, B, tc + PDP_CHF, H, lane);\n")
-    return t

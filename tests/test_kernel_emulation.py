@@ -230,62 +230,6 @@ def test_emulated_controlplanning_kernel_matches_oracle(policy):
         assert _rel(out["loss_dp"][b, 1:], gref) < 1e-10
 
 
-def test_emulated_fused_backward_forward_kernel_matches_oracle():
-    """pdp_k_aux_lqr_fused (option fused=1: a warp runs the Riccati sweep of its two trajectories and then their
-    forward pass in one kernel, so the gain spill is re-read while it is still in L2) -- same outputs as the
-    two-kernel path: dX/dtheta, dU/dtheta, fused loss / chain rule vs the oracle; odd batch, chunk tails."""
-    from pontryagin_differentiable_programming_b200 import systems
-    base = systems.quadrotor_irl(0.1).src
-    src = _variant(base, fused=1)
-    assert src.fused == 1 and src._fwd_shape()[0] == 2
-    assert "pdp_k_aux_lqr_fused" in src.source() and "pdp_k_aux_lqr_fused" not in base.source()
-    oc = pdp_oracle.build_oc(envs.quadrotor(c=0.01, wthrust=0.1), 0.1)
-    rng = np.random.default_rng(7)
-    B, H = 3, 19
-    x0 = np.tile(np.array([-8, -6, 9., 0, 0, 0, 1, 0, 0, 0, 0, 0, 0]), (B, 1)) + 0.05 * rng.standard_normal((B, 13))
-    theta = np.array([1, 1, 1, 1, 0.4, 1, 1, 5, 1.]) * (1 + 0.1 * rng.uniform(-1, 1, (B, 9)))
-    U = 2.5 + 0.5 * rng.standard_normal((B, H, 4))
-    ref = [pdp_oracle.pdp_sweep(oc, x0[b], U[b], theta[b]) for b in range(B)]
-    X = np.stack([r[0] for r in ref])
-    L = np.stack([r[1] for r in ref])
-    Xd = X + 0.1 * rng.standard_normal(X.shape)
-    Ud = U + 0.1 * rng.standard_normal(U.shape)
-    dX, dU, ldp, gains, st = warp_emu.Emulator(src).fused(X, U, L, theta, Xref=Xd, Uref=Ud)
-    assert not np.isnan(gains).any()
-    for b in range(B):
-        assert _rel(dX[b], np.asarray(ref[b][3])) < 1e-10 and _rel(dU[b], np.asarray(ref[b][4])) < 1e-10
-        loss, dp = pdp_oracle.irl_loss_grad(X[b], U[b], Xd[b], Ud[b], ref[b][3], ref[b][4])
-        assert abs(ldp[b, 0] - loss) < 1e-12 * abs(loss) and _rel(ldp[b, 1:], np.asarray(dp).ravel()) < 1e-10
-
-
-@pytest.mark.parametrize("env,parts", [("quadrotor", 4), ("cartpole", 3)])
-def test_emulated_multi_warp_rollout_kernel_equals_the_single_thread_kernel(env, parts):
-    """pdp_k_rollout_costate_mw (option rollout_parts: the outputs of f / dH/dx split over the warps of a block, one
-    __syncthreads per step) -- bit-identical to the one-thread-per-trajectory kernel and equal to the oracle; 37
-    trajectories = two blocks, the second one mostly idle lanes."""
-    from pontryagin_differentiable_programming_b200 import systems
-    base = systems.OC_BUILDERS[env](0.1).src
-    src = _variant(base, rollout_parts=parts)
-    assert "pdp_k_rollout_costate_mw" in src.source() and "pdp_k_rollout_costate_mw" not in base.source()
-    builder, kw = ORACLE_ENVS[env]
-    oc = pdp_oracle.build_oc(builder(**kw), 0.1)
-    rng = np.random.default_rng(2)
-    B, H = 37, 9
-    x0 = 0.3 * rng.standard_normal((B, src.n))
-    if env == "quadrotor":
-        x0[:, 6] += 1.0
-    theta = 1.0 + 0.2 * rng.uniform(-1, 1, (B, src.r))
-    U = 0.5 * rng.standard_normal((B, H, src.m)) + (2.5 if env == "quadrotor" else 0.0)
-    emu = warp_emu.Emulator(src)
-    mw = emu.rollout(x0, theta, U, want_dHu=True, multi_warp=True)
-    one = emu.rollout(x0, theta, U, want_dHu=True)
-    for a, b_ in zip(mw, one):
-        assert np.array_equal(a, b_)
-    for b in (0, 36):
-        Xr, c = oc.rollout(x0[b], U[b], theta[b])
-        assert np.max(np.abs(mw[0][b] - Xr)) < 1e-12 and _rel(mw[1][b], oc.costate(Xr, U[b], theta[b])) < 1e-12
-
-
 def test_emulator_detects_a_missing_barrier():
     """Negative control of the emulator itself: the lanes are real host threads, so a kernel whose Z^T staging
     barrier is removed must give wrong gains (it does, by orders of magnitude and differently on every run) -- the
@@ -315,49 +259,3 @@ def test_emulator_detects_a_missing_barrier():
     assert np.array_equal(good, again)                       # the intact kernel is deterministic
     bad, _ = warp_emu.Emulator(broken).backward(X, U, L, th)
     assert not np.allclose(np.nan_to_num(bad), good, rtol=1e-6, atol=0)
-
-
-@pytest.mark.parametrize("extra", [dict(stage_inputs=1), dict(stage_inputs=1, chunk=5), dict(stage_inputs=1, fused=1)])
-def test_emulated_staged_chunk_inputs_variant_is_identical(extra):
-    """Option stage_inputs: the rows of X / U / Lam that the chunk evaluation needs are copied into shared memory with
-    cp.async one chunk ahead (immediate copies in the emulator) and the evaluator reads shared memory -- same gains
-    bit for bit, also inside the fused kernel and with a chunk that does not divide the horizon."""
-    from pontryagin_differentiable_programming_b200 import systems
-    base = systems.quadrotor_irl(0.1).src
-    src = _variant(base, **extra)
-    assert src.stage_inputs == 1 and "pdp_stage_chunk" in src.source() and "pdp_stage_chunk" not in base.source()
-    rng = np.random.default_rng(0)
-    B, H = 5, 21
-    X = 0.3 * rng.standard_normal((B, H + 1, 13))
-    X[:, :, 6] += 1.0
-    U = 2.5 + 0.3 * rng.standard_normal((B, H, 4))
-    L = 0.1 * rng.standard_normal((B, H, 13))
-    th = np.array([1, 1, 1, 1, 0.4, 1, 1, 5, 1.]) * (1 + 0.1 * rng.uniform(-1, 1, (B, 9)))
-    g0, _ = warp_emu.Emulator(base).backward(X, U, L, th)
-    emu = warp_emu.Emulator(src)
-    g1 = emu.fused(X, U, L, th)[3] if extra.get("fused") else emu.backward(X, U, L, th)[0]
-    assert np.array_equal(g0, g1)
-
-
-def test_emulated_forward_kernel_with_staged_chunk_rows_is_identical():
-    """Option fwd_stage_inputs: the forward kernel's per-chunk rows (x, u, xref, uref) staged through shared memory with
-    cp.async one chunk ahead; same dX / dU bit for bit and the same fused loss / chain rule, with and without demos."""
-    from pontryagin_differentiable_programming_b200 import systems
-    base = systems.quadrotor_irl(0.1).src
-    src = _variant(base, fwd_stage_inputs=1, fwd_chunk=10)
-    assert src.fwd_stage_inputs == 1 and "pdp_fstage_chunk" in src.source() and "pdp_fstage_chunk" not in base.source()
-    rng = np.random.default_rng(0)
-    B, H = 7, 23
-    X = 0.3 * rng.standard_normal((B, H + 1, 13))
-    X[:, :, 6] += 1.0
-    U = 2.5 + 0.3 * rng.standard_normal((B, H, 4))
-    L = 0.1 * rng.standard_normal((B, H, 13))
-    th = np.array([1, 1, 1, 1, 0.4, 1, 1, 5, 1.]) * (1 + 0.1 * rng.uniform(-1, 1, (B, 9)))
-    Xd, Ud = X + 0.1 * rng.standard_normal(X.shape), U + 0.1 * rng.standard_normal(U.shape)
-    e0, e1 = warp_emu.Emulator(base), warp_emu.Emulator(src)
-    g, _ = e0.backward(X, U, L, th)
-    for kwargs in (dict(Xref=Xd, Uref=Ud), dict(Xref=Xd), dict()):
-        a, b = e0.forward(X, U, th, g, **kwargs), e1.forward(X, U, th, g, **kwargs)
-        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
-        if kwargs:
-            assert _rel(b[2], a[2]) < 1e-14

@@ -14,18 +14,18 @@ sys.path.insert(0, ROOT)
 
 # every variant: keyword overrides of BASE (= the shipped configuration of engine.OCSystem)
 BASE = dict(chunk=8, warps_per_block=1, min_blocks=8, fwd_warps_per_block=1, fwd_min_blocks=8, keep_fg=True,
-            fast_rcp=True, early_solve=True, fwd_pack=3, fwd_chunk=10, bwd_pack=2, fwd_vec=-1, prefetch=2, prefetch_dist=2, inline_eval=-1, h_group=1, prefetch_l1_lead=0, fused=0, stream_out=0, rollout_parts=1, stage_inputs=0, fwd_stage_inputs=0)
+            fast_rcp=True, early_solve=True, fwd_pack=3, fwd_chunk=10, bwd_pack=2, fwd_vec=-1, prefetch=2, prefetch_dist=2,
+            inline_eval=-1, h_group=1, prefetch_l1_lead=0)
 V1 = dict(bwd_pack=1, chunk=17, warps_per_block=4, min_blocks=3, keep_fg=True)     # one trajectory per warp
 VARIANTS = [
     V1,
     {},                                                                    # shipped: two trajectories per warp
-    dict(stage_inputs=1), dict(stage_inputs=1, chunk=10), dict(fwd_stage_inputs=1), dict(stage_inputs=1, fwd_stage_inputs=1),
-                                                       # NOT YET MEASURED: chunk inputs staged with cp.async (bwd / fwd)
-    dict(rollout_parts=2), dict(rollout_parts=4),      # NOT YET MEASURED: multi-warp rollout kernel (rollout_ms column)
-    dict(stream_out=1), dict(fused=1, stream_out=1),
-    dict(fused=1),      # NOT YET MEASURED: backward + forward of a warp's two trajectories in one kernel (time it with
-                        # OCSystem.sweep / phase="both": the "backward" / "forward" columns below still launch the two kernels)
 ]
+# Measured and removed in round 2 (profiles/r2a_tune_pending_variants.json, B200, C3 at 16 384 trajectories; shipped path
+# rollout 0.101 / bwd 0.650 / fwd 0.403 ms): cp.async staging of the backward kernel's chunk rows (bwd 0.757), of the
+# forward kernel's chunk rows (fwd 0.605), multi-warp rollout with 2 / 4 warps per 32 trajectories (0.120 / 0.178),
+# backward + forward of a warp's trajectories fused in one kernel (1.096 vs 1.054 for the two launches).  Streaming
+# stores of dX / dU (fwd 0.400) were adopted unconditionally.
 
 
 def make(verbose=False, **kw):
