@@ -182,10 +182,23 @@ class OCSys:
     def aux_lqr_batched(self, state_traj, control_traj, costate_traj, auxvar_value, **kw):
         return self._system().aux_lqr(state_traj, control_traj, costate_traj, auxvar_value, **kw)
 
+    def _check_unbounded(self):
+        """The reference hands state / control bounds to IPOPT as lbw / ubw (PDP.py:147-168).  The batched Newton / DDP
+        solver that replaces IPOPT here is unconstrained: refuse loudly instead of returning an unconstrained optimum
+        for a constrained problem.  (None of the reference's Examples scripts passes a bound.)"""
+        for name in ("state_lb", "state_ub", "control_lb", "control_ub"):
+            b = numpy.asarray(getattr(self, name, []), dtype=numpy.float64).ravel()
+            if b.size and bool(numpy.any(numpy.abs(b) < 1e19)):
+                raise NotImplementedError(
+                    "OCSys.ocSolver: finite %s = %s was set, but the CUDA Newton/DDP solver of this engine handles "
+                    "unconstrained problems only (the reference passes bounds to IPOPT, PDP.py:147-168); remove the "
+                    "bound or enforce it through a penalty in the path cost" % (name, b.tolist()))
+
     def ocSolver_batched(self, ini_state, horizon, auxvar_value, control_init=None, n_starts=1, **opts):
         """Batched optimal-control solve (CUDA Newton / DDP, see ocsolver.py).  ``n_starts`` > 1 tries several
         seeded initial guesses per problem in the same batch and keeps the best stationary point."""
         from pontryagin_differentiable_programming_b200 import ocsolver
+        self._check_unbounded()
         if control_init is None and n_starts > 1:
             return ocsolver.solve_multistart(self._system(), ini_state, int(horizon), auxvar_value, n_starts, **opts)
         return ocsolver.solve(self._system(), ini_state, int(horizon), auxvar_value, control_init, **opts)
@@ -199,6 +212,7 @@ class OCSys:
         Additive keyword arguments: ``control_init`` (H x m warm start) and ``n_starts`` (> 1: seeded multi-start in
         one batch, best stationary point wins; the default 1 is the reference's cold start from all-zero controls)."""
         self._check_defined()
+        self._check_unbounded()
         dev = _device()
         x0 = _dev_tensor(_flat(ini_state, self.n_state, "ini_state")[None, :], dev)
         theta = _dev_tensor(_flat(auxvar_value, self.n_auxvar, "auxvar_value")[None, :], dev)

@@ -30,7 +30,7 @@ typedef void* pdp_stream_t; /* cudaStream_t */
 
 enum { PDP_OK = 0, PDP_ERR_ARG = -1, PDP_ERR_LOAD = -2, PDP_ERR_CUDA = -3, PDP_ERR_WORKSPACE = -4, PDP_ERR_UNSUPPORTED = -5 };
 enum { PDP_KIND_OC = 1, PDP_KIND_SYSID = 2, PDP_KIND_CP = 3, PDP_KIND_LQR = 4, PDP_KIND_FUNCTION = 5 };
-enum { PDP_OP_AUX_LQR = 1, PDP_OP_SWEEP = 2, PDP_OP_SWEEP_HOST = 3 };
+enum { PDP_OP_AUX_LQR = 1, PDP_OP_SWEEP = 2, PDP_OP_SWEEP_HOST = 3, PDP_OP_ROLLOUT_HOST = 4, PDP_OP_SENS_HOST = 5 };
 
 /* Load a generated system module (the product of OCSys.setDyn/setPathCost/setFinalCost + diffPMP,
  * reference PDP/PDP.py:96-119,222-270: here "differentiate PMP" = code-generate + nvcc). */
@@ -138,6 +138,38 @@ int pdp_sweep_host(pdp_system_t* sys, int B, int H, const double* x0_host, const
                    int theta_stride, const double* U_host, const double* Xref_host, const double* Uref_host,
                    double* loss_dp_host, double* cost_host, int keep_dtraj, void* workspace, size_t ws_bytes,
                    pdp_stream_t stream);
+
+/* pdp_sweep_host that also returns the trajectories and the sensitivities themselves to the host (any of X_host[B,H+1,n],
+ * Lam_host[B,H,n], dX_host[B,H+1,n,r], dU_host[B,H,m,r] may be NULL): the return values of OCSys.ocSolver's rollout and of
+ * LQR.lqrSolver (PDP/PDP.py:212-218, 611-615) for a whole batch. */
+int pdp_sweep_host_traj(pdp_system_t* sys, int B, int H, const double* x0_host, const double* theta_host,
+                        int theta_stride, const double* U_host, const double* Xref_host, const double* Uref_host,
+                        double* loss_dp_host, double* cost_host, double* X_host, double* Lam_host, double* dX_host,
+                        double* dU_host, void* workspace, size_t ws_bytes, pdp_stream_t stream);
+
+/* Batch reduction of per-trajectory (loss, dp) rows: loss_dp[B,r+1] -> sums[r+2] = (sum loss, sum dp[0..r-1], B).
+ * This is the averaging step of the outer loops (reference PDP/PDP.py:1293-1294, Examples/IRL/quadrotor/uav_PDP.py:78-81)
+ * up to the division, and the vector the single all-reduce of a multi-GPU run carries.  Deterministic (fixed summation
+ * order, no floating-point atomics).  workspace: pdp_reduce_workspace_bytes(r) bytes, ZERO-INITIALISED by the caller
+ * before its first use (every call leaves it reusable); one workspace per concurrently used stream. */
+size_t pdp_reduce_workspace_bytes(int r);
+int pdp_reduce_loss_dp(int B, int r, const double* loss_dp, double* sums, void* workspace, size_t ws_bytes,
+                       pdp_stream_t stream);
+
+/* Host-buffer variant of pdp_rollout_costate (ControlPlanning.recmat_step for a batch, PDP/PDP.py:1100-1114): copies
+ * x0/theta/U from host, runs rollout + costate (+ dH/du), copies cost[B] / dHu[B,H,m] / X / Lam back (any may be NULL).
+ * workspace: pdp_workspace_bytes(sys, PDP_OP_ROLLOUT_HOST, B, H). */
+int pdp_rollout_costate_host(pdp_system_t* sys, int B, int H, const double* x0_host, const double* theta_host,
+                             int theta_stride, const double* U_host, double* cost_host, double* dHu_host, double* X_host,
+                             double* Lam_host, void* workspace, size_t ws_bytes, pdp_stream_t stream);
+
+/* Host-buffer variant of pdp_sens_fwd with the fused loss (SysID.step / ControlPlanning.step for a batch, PDP/PDP.py:1261-1296,
+ * 850-878): copies x0/theta (and inputs/Xobs for SysID) from host, runs the sweep, copies loss_dp[B,r+1] and/or its batch
+ * reduction sums[r+2] back (either may be NULL).  workspace: pdp_workspace_bytes(sys, PDP_OP_SENS_HOST, B, H), zero-initialised
+ * before its first use (it holds the reduction scratch). */
+int pdp_sens_fwd_host(pdp_system_t* sys, int B, int H, const double* x0_host, const double* theta_host, int theta_stride,
+                      const double* inputs_host, const double* Xobs_host, double* loss_dp_host, double* sums_host,
+                      void* workspace, size_t ws_bytes, pdp_stream_t stream);
 
 #ifdef __cplusplus
 }

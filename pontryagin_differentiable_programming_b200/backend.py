@@ -19,13 +19,14 @@ class PDPBackendError(RuntimeError):
 _lib = None
 _lock = threading.Lock()
 
-OP_AUX_LQR, OP_SWEEP, OP_SWEEP_HOST = 1, 2, 3
+OP_AUX_LQR, OP_SWEEP, OP_SWEEP_HOST, OP_ROLLOUT_HOST, OP_SENS_HOST = 1, 2, 3, 4, 5
 KIND_OC, KIND_SYSID, KIND_CP, KIND_LQR = 1, 2, 3, 4
 
 EXPORTS = ["pdp_load_system", "pdp_free_system", "pdp_system_dims", "pdp_last_error", "pdp_version",
            "pdp_workspace_bytes", "pdp_rollout_costate", "pdp_aux_lqr", "pdp_sweep", "pdp_aux_eval",
            "pdp_sens_fwd", "pdp_sweep_host", "pdp_lqr_dense", "pdp_eval_function", "pdp_aux_lqr_backward",
-           "pdp_aux_lqr_forward", "pdp_rollout_feedback", "pdp_set_sweep_parts"]
+           "pdp_aux_lqr_forward", "pdp_rollout_feedback", "pdp_set_sweep_parts", "pdp_sweep_host_traj",
+           "pdp_reduce_workspace_bytes", "pdp_reduce_loss_dp", "pdp_rollout_costate_host", "pdp_sens_fwd_host"]
 
 
 def library_path():
@@ -39,10 +40,10 @@ def load_library(build_if_missing=True):
         if _lib is not None:
             return _lib
         path = build.LIB_PATH
-        if not os.path.isfile(path):
-            if not build_if_missing:
-                raise PDPBackendError("libpdp_b200.so not built (run __graft_entry__.build())")
-            build.build_library()
+        if not os.path.isfile(path) and not build_if_missing:
+            raise PDPBackendError("libpdp_b200.so not built (run __graft_entry__.build())")
+        if build_if_missing:
+            build.build_library()      # no-op when the library is newer than csrc/pdp_b200.cu and include/pdp_b200.h
         lib = ctypes.CDLL(path)
         i, sz, vp, dp = ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p, c_dp
         lib.pdp_load_system.argtypes = [ctypes.c_char_p, ctypes.POINTER(vp)]
@@ -79,6 +80,16 @@ def load_library(build_if_missing=True):
         lib.pdp_sens_fwd.restype = i
         lib.pdp_sweep_host.argtypes = [vp, i, i, dp, dp, i, dp, dp, dp, dp, dp, i, dp, sz, vp]
         lib.pdp_sweep_host.restype = i
+        lib.pdp_sweep_host_traj.argtypes = [vp, i, i, dp, dp, i, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp, sz, vp]
+        lib.pdp_sweep_host_traj.restype = i
+        lib.pdp_reduce_workspace_bytes.argtypes = [i]
+        lib.pdp_reduce_workspace_bytes.restype = sz
+        lib.pdp_reduce_loss_dp.argtypes = [i, i, dp, dp, dp, sz, vp]
+        lib.pdp_reduce_loss_dp.restype = i
+        lib.pdp_rollout_costate_host.argtypes = [vp, i, i, dp, dp, i, dp, dp, dp, dp, dp, dp, sz, vp]
+        lib.pdp_rollout_costate_host.restype = i
+        lib.pdp_sens_fwd_host.argtypes = [vp, i, i, dp, dp, i, dp, dp, dp, dp, dp, sz, vp]
+        lib.pdp_sens_fwd_host.restype = i
         _lib = lib
         return lib
 

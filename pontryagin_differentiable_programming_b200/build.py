@@ -38,12 +38,22 @@ def compile_module(source: str, key: str, verbose: bool = False, extra_flags=())
     cu = os.path.join(MODULE_DIR, "pdpmod_%s.cu" % key)
     if os.path.isfile(so) and os.path.isfile(cu) and open(cu).read() == source:
         return so
-    with open(cu, "w") as f:
-        f.write(source)
+    # several processes (torchrun ranks, pytest-xdist workers) may generate the same system at the same time: each
+    # compiles from its OWN copy of the source and publishes .cu and .so by atomic renames, so nobody reads a half-written
+    # file; the results are identical, the last rename wins
+    tmp_cu = os.path.join(MODULE_DIR, "pdpmod_%s.tmp%d.cu" % (key, os.getpid()))
     tmp = so + ".tmp.%d" % os.getpid()
-    cmd = [nvcc_path()] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp, cu]
-    out = _run(cmd, "nvcc (system module %s)" % key)
-    os.replace(tmp, so)
+    with open(tmp_cu, "w") as f:
+        f.write(source)
+    try:
+        cmd = [nvcc_path()] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp, tmp_cu]
+        out = _run(cmd, "nvcc (system module %s)" % key)
+        os.replace(tmp, so)
+        os.replace(tmp_cu, cu)
+    finally:
+        for leftover in (tmp_cu, tmp):
+            if os.path.exists(leftover):
+                os.remove(leftover)
     if verbose:
         print(out)
     return so

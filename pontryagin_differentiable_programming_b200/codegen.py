@@ -240,6 +240,13 @@ class OCModuleSource:
             self.bwd_pack = 1          # the two-rows-per-lane layout needs n <= 16 and m + r <= 16
         if self.bwd_pack == 2:
             self.chunk = min(self.chunk, 16)
+        elif self.ns > WARP:
+            # one trajectory per warp: lane j owns stack row j of [P ; . ; W^T] -- there is no lane for a row beyond 31
+            raise ValueError(
+                "the fused aux-LQR kernels hold the stack [P; control rows; W^T] with one row per lane: n + m + r = %d + %d + %d "
+                "= %d exceeds the 32 rows of a warp.  Differentiate with respect to at most %d auxiliary variables per system "
+                "(split the auxvar vector and build one system per group; the columns of dX/dtheta are independent), or use "
+                "the generic LQR.lqrSolver, which splits the columns itself" % (self.n, self.m, self.r, self.ns, WARP - self.n - self.m))
         self._layout()
 
     def _customise(self):

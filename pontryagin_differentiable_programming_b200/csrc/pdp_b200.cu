@@ -42,6 +42,64 @@ inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
 }  // namespace
 
+// ---- batch reduction of the per-trajectory (loss, dp) rows: loss_dp[B, r1] -> sums[r1 + 1] = (column sums, B) ----------
+// The outer loops of the IRL / SysID modes average over the batch (reference PDP/PDP.py:1293-1294,
+// Examples/IRL/quadrotor/uav_PDP.py:78-81); with several GPUs this vector is what the one all-reduce carries.
+// Deterministic (no floating-point atomics): block g sums its slab of rows column-wise with coalesced loads (thread
+// t owns column t % r1 and row lane t / r1), publishes partial[g][.], and the block that draws the last ticket adds the
+// partials in block order.  The ticket counter returns to zero, so the call can be replayed from a CUDA graph.
+constexpr int kRedBlocks = 64, kRedThreads = 256;
+
+extern "C" __global__ void __launch_bounds__(kRedThreads)
+pdp_k_reduce_loss_dp(int B, int r1, const double* __restrict__ ldp, double* __restrict__ sums, double* __restrict__ partial,
+                     unsigned int* __restrict__ ticket) {
+  extern __shared__ double red_sm[];                 // [row lanes][r1] (r1 < blockDim) or unused
+  const int g = blockIdx.x, t = threadIdx.x;
+  const int lo = (int)(((long long)B * g) / gridDim.x), hi = (int)(((long long)B * (g + 1)) / gridDim.x);
+  if (r1 >= kRedThreads) {
+    for (int c = t; c < r1; c += kRedThreads) {      // thread per column, consecutive threads read consecutive doubles
+      double a = 0.0;
+      for (int row = lo; row < hi; ++row) a += ldp[(size_t)row * r1 + c];
+      partial[(size_t)g * r1 + c] = a;
+    }
+  } else {
+    const int k = kRedThreads / r1;                  // row lanes
+    const int c = t % r1, rl = t / r1;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;   // four independent chains, combined in a fixed order
+    if (rl < k) {
+      int row = lo + rl;
+      for (; row + 3 * k < hi; row += 4 * k) {
+        a0 += ldp[(size_t)row * r1 + c];
+        a1 += ldp[(size_t)(row + k) * r1 + c];
+        a2 += ldp[(size_t)(row + 2 * k) * r1 + c];
+        a3 += ldp[(size_t)(row + 3 * k) * r1 + c];
+      }
+      for (; row < hi; row += k) a0 += ldp[(size_t)row * r1 + c];
+      red_sm[rl * r1 + c] = (a0 + a1) + (a2 + a3);
+    }
+    __syncthreads();
+    if (t < r1) {
+      double a = 0.0;
+      for (int j = 0; j < k; ++j) a += red_sm[j * r1 + t];
+      partial[(size_t)g * r1 + t] = a;
+    }
+  }
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (t == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  for (int c = t; c < r1; c += kRedThreads) {
+    double a = 0.0;
+    for (int j = 0; j < (int)gridDim.x; ++j) a += __ldcg(partial + (size_t)j * r1 + c);
+    sums[c] = a;
+  }
+  if (t == 0) { sums[r1] = (double)B; *ticket = 0u; }
+}
+
+
 struct pdp_system {
   void* handle = nullptr;
   int info[16] = {0};
@@ -163,6 +221,15 @@ size_t pdp_workspace_bytes(const pdp_system_t* sys, int op, int B, int H) {
       tot += align256(size_t(B) * H * m * r * 8);    // dU
       return tot;
     }
+    case PDP_OP_ROLLOUT_HOST: {
+      const size_t nth = sys->info[11] > 0 ? sys->info[11] : r;
+      return align256(size_t(B) * n * 8) + align256(size_t(B) * nth * 8) + 2 * align256(size_t(B) * H * m * 8) +
+             align256(size_t(B) * (H + 1) * n * 8) + align256(size_t(B) * H * n * 8) + align256(size_t(B) * 8);
+    }
+    case PDP_OP_SENS_HOST:
+      return align256(pdp_reduce_workspace_bytes((int)r)) + align256(size_t(B) * n * 8) + align256(size_t(B) * r * 8) +
+             align256(size_t(B) * H * m * 8) + align256(size_t(B) * (H + 1) * n * 8) + align256(size_t(B) * (r + 1) * 8) +
+             align256((r + 2) * 8);
     default:
       return 0;
   }
@@ -306,6 +373,29 @@ int pdp_sweep(pdp_system_t* sys, int B, int H, const double* x0, const double* t
                      workspace, ws_bytes, status, stream);
 }
 
+size_t pdp_reduce_workspace_bytes(int r) {
+  if (r < 0) return 0;
+  return align256(size_t(kRedBlocks) * size_t(r + 1) * sizeof(double)) + 256;
+}
+
+int pdp_reduce_loss_dp(int B, int r, const double* loss_dp, double* sums, void* workspace, size_t ws_bytes,
+                       pdp_stream_t stream) {
+  if (B < 1 || r < 0 || !loss_dp || !sums) return fail(PDP_ERR_ARG, "pdp_reduce_loss_dp: bad argument");
+  if (!workspace || ws_bytes < pdp_reduce_workspace_bytes(r))
+    return fail(PDP_ERR_WORKSPACE, "pdp_reduce_loss_dp: workspace too small (%zu < %zu)", ws_bytes,
+                pdp_reduce_workspace_bytes(r));
+  const int r1 = r + 1;
+  // layout: [ticket (256 B, zero on first use, left at zero by every call)] [partial sums kRedBlocks x r1]
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(workspace);
+  double* partial = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 256);
+  const int blocks = B < kRedBlocks ? B : kRedBlocks;
+  const size_t smem = r1 < kRedThreads ? size_t(kRedThreads / r1) * r1 * sizeof(double) : 0;
+  pdp_k_reduce_loss_dp<<<blocks, kRedThreads, smem, (cudaStream_t)stream>>>(B, r1, loss_dp, sums, partial, ticket);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return fail(PDP_ERR_CUDA, "pdp_reduce_loss_dp: %s", cudaGetErrorString(ce));
+  return PDP_OK;
+}
+
 int pdp_aux_eval(pdp_system_t* sys, int B, int H, const double* X, const double* U, const double* Lam,
                  const double* theta, int theta_stride, double* aux, double* term, pdp_stream_t stream) {
   if (!sys || !sys->aux_eval) return fail(PDP_ERR_UNSUPPORTED, "pdp_aux_eval: module has no aux-eval kernel");
@@ -337,10 +427,10 @@ int pdp_eval_function(pdp_system_t* sys, int B, const double* const* inputs, con
   return PDP_OK;
 }
 
-int pdp_sweep_host(pdp_system_t* sys, int B, int H, const double* x0_host, const double* theta_host,
-                   int theta_stride, const double* U_host, const double* Xref_host, const double* Uref_host,
-                   double* loss_dp_host, double* cost_host, int keep_dtraj, void* workspace, size_t ws_bytes,
-                   pdp_stream_t stream) {
+static int sweep_host_impl(pdp_system_t* sys, int B, int H, const double* x0_host, const double* theta_host,
+                           int theta_stride, const double* U_host, const double* Xref_host, const double* Uref_host,
+                           double* loss_dp_host, double* cost_host, int keep_dtraj, double* X_host, double* Lam_host,
+                           double* dX_host, double* dU_host, void* workspace, size_t ws_bytes, pdp_stream_t stream) {
   if (!sys || !sys->aux_lqr || !sys->rollout) return fail(PDP_ERR_UNSUPPORTED, "pdp_sweep_host: not an OC module");
   if (B < 1 || H < 1 || !x0_host || !theta_host || !U_host || !Xref_host || !loss_dp_host)
     return fail(PDP_ERR_ARG, "pdp_sweep_host: bad argument");
@@ -376,6 +466,106 @@ int pdp_sweep_host(pdp_system_t* sys, int B, int H, const double* x0_host, const
   if (e) return e;
   PDP_CK(cudaMemcpyAsync(loss_dp_host, d_ldp, size_t(B) * (r + 1) * 8, cudaMemcpyDeviceToHost, st));
   if (cost_host) PDP_CK(cudaMemcpyAsync(cost_host, d_cost, size_t(B) * 8, cudaMemcpyDeviceToHost, st));
+  if (X_host) PDP_CK(cudaMemcpyAsync(X_host, d_X, size_t(B) * (H + 1) * n * 8, cudaMemcpyDeviceToHost, st));
+  if (Lam_host) PDP_CK(cudaMemcpyAsync(Lam_host, d_L, size_t(B) * H * n * 8, cudaMemcpyDeviceToHost, st));
+  if (dX_host) PDP_CK(cudaMemcpyAsync(dX_host, d_dX, size_t(B) * (H + 1) * n * r * 8, cudaMemcpyDeviceToHost, st));
+  if (dU_host) PDP_CK(cudaMemcpyAsync(dU_host, d_dU, size_t(B) * H * m * r * 8, cudaMemcpyDeviceToHost, st));
+#undef PDP_CK
+  return PDP_OK;
+}
+
+int pdp_sweep_host(pdp_system_t* sys, int B, int H, const double* x0_host, const double* theta_host,
+                   int theta_stride, const double* U_host, const double* Xref_host, const double* Uref_host,
+                   double* loss_dp_host, double* cost_host, int keep_dtraj, void* workspace, size_t ws_bytes,
+                   pdp_stream_t stream) {
+  return sweep_host_impl(sys, B, H, x0_host, theta_host, theta_stride, U_host, Xref_host, Uref_host, loss_dp_host, cost_host,
+                         keep_dtraj, nullptr, nullptr, nullptr, nullptr, workspace, ws_bytes, stream);
+}
+
+int pdp_sweep_host_traj(pdp_system_t* sys, int B, int H, const double* x0_host, const double* theta_host,
+                        int theta_stride, const double* U_host, const double* Xref_host, const double* Uref_host,
+                        double* loss_dp_host, double* cost_host, double* X_host, double* Lam_host, double* dX_host,
+                        double* dU_host, void* workspace, size_t ws_bytes, pdp_stream_t stream) {
+  return sweep_host_impl(sys, B, H, x0_host, theta_host, theta_stride, U_host, Xref_host, Uref_host, loss_dp_host, cost_host,
+                         1, X_host, Lam_host, dX_host, dU_host, workspace, ws_bytes, stream);
+}
+
+// ---- host-buffer variants of the two single-kernel modes (end-to-end use: copies in, kernel, copies out) ----------------
+int pdp_rollout_costate_host(pdp_system_t* sys, int B, int H, const double* x0_host, const double* theta_host,
+                             int theta_stride, const double* U_host, double* cost_host, double* dHu_host, double* X_host,
+                             double* Lam_host, void* workspace, size_t ws_bytes, pdp_stream_t stream) {
+  if (!sys || !sys->rollout) return fail(PDP_ERR_UNSUPPORTED, "pdp_rollout_costate_host: module has no rollout kernel");
+  if (B < 1 || H < 1 || !x0_host || !theta_host || !U_host)
+    return fail(PDP_ERR_ARG, "pdp_rollout_costate_host: bad argument");
+  if (!workspace || ws_bytes < pdp_workspace_bytes(sys, PDP_OP_ROLLOUT_HOST, B, H))
+    return fail(PDP_ERR_WORKSPACE, "pdp_rollout_costate_host: workspace too small");
+  const size_t n = sys->n(), m = sys->m(), nth = sys->info[11] > 0 ? sys->info[11] : sys->r();
+  cudaStream_t st = (cudaStream_t)stream;
+  char* p = reinterpret_cast<char*>(workspace);
+  auto take = [&](size_t bytes) { char* q = p; p += align256(bytes); return reinterpret_cast<double*>(q); };
+  double* d_x0 = take(size_t(B) * n * 8);
+  double* d_th = take(size_t(B) * nth * 8);
+  double* d_U = take(size_t(B) * H * m * 8);
+  double* d_X = take(size_t(B) * (H + 1) * n * 8);
+  double* d_L = take(size_t(B) * H * n * 8);
+  double* d_cost = take(size_t(B) * 8);
+  double* d_dHu = take(size_t(B) * H * m * 8);
+  const size_t thn = theta_stride ? size_t(B) * theta_stride : nth;
+  cudaError_t ce;
+#define PDP_CK(x) if ((ce = (x)) != cudaSuccess) return fail(PDP_ERR_CUDA, "pdp_rollout_costate_host: %s", cudaGetErrorString(ce))
+  PDP_CK(cudaMemcpyAsync(d_x0, x0_host, size_t(B) * n * 8, cudaMemcpyHostToDevice, st));
+  PDP_CK(cudaMemcpyAsync(d_th, theta_host, thn * 8, cudaMemcpyHostToDevice, st));
+  PDP_CK(cudaMemcpyAsync(d_U, U_host, size_t(B) * H * m * 8, cudaMemcpyHostToDevice, st));
+  const bool need_lam = dHu_host || Lam_host;
+  int e = pdp_rollout_costate(sys, B, H, d_x0, d_th, theta_stride, d_U, d_X, need_lam ? d_L : nullptr, d_cost,
+                              dHu_host ? d_dHu : nullptr, nullptr, stream);
+  if (e) return e;
+  if (cost_host) PDP_CK(cudaMemcpyAsync(cost_host, d_cost, size_t(B) * 8, cudaMemcpyDeviceToHost, st));
+  if (dHu_host) PDP_CK(cudaMemcpyAsync(dHu_host, d_dHu, size_t(B) * H * m * 8, cudaMemcpyDeviceToHost, st));
+  if (X_host) PDP_CK(cudaMemcpyAsync(X_host, d_X, size_t(B) * (H + 1) * n * 8, cudaMemcpyDeviceToHost, st));
+  if (Lam_host) PDP_CK(cudaMemcpyAsync(Lam_host, d_L, size_t(B) * H * n * 8, cudaMemcpyDeviceToHost, st));
+#undef PDP_CK
+  return PDP_OK;
+}
+
+int pdp_sens_fwd_host(pdp_system_t* sys, int B, int H, const double* x0_host, const double* theta_host, int theta_stride,
+                      const double* inputs_host, const double* Xobs_host, double* loss_dp_host, double* sums_host,
+                      void* workspace, size_t ws_bytes, pdp_stream_t stream) {
+  if (!sys || !sys->sens) return fail(PDP_ERR_UNSUPPORTED, "pdp_sens_fwd_host: module has no forward-sensitivity kernel");
+  if (B < 1 || H < 1 || !x0_host || !theta_host || (!loss_dp_host && !sums_host))
+    return fail(PDP_ERR_ARG, "pdp_sens_fwd_host: bad argument");
+  if (sys->kind() == PDP_KIND_SYSID && (!inputs_host || !Xobs_host))
+    return fail(PDP_ERR_ARG, "pdp_sens_fwd_host: a SysID module needs inputs and observed states");
+  if (!workspace || ws_bytes < pdp_workspace_bytes(sys, PDP_OP_SENS_HOST, B, H))
+    return fail(PDP_ERR_WORKSPACE, "pdp_sens_fwd_host: workspace too small");
+  const size_t n = sys->n(), m = sys->m(), r = sys->r();
+  cudaStream_t st = (cudaStream_t)stream;
+  char* p = reinterpret_cast<char*>(workspace);
+  auto take = [&](size_t bytes) { char* q = p; p += align256(bytes); return reinterpret_cast<double*>(q); };
+  // the reduction scratch comes first: its ticket word must be zero when the workspace is first used
+  void* red = take(pdp_reduce_workspace_bytes((int)r));
+  double* d_x0 = take(size_t(B) * n * 8);
+  double* d_th = take(size_t(B) * r * 8);
+  double* d_in = take(size_t(B) * H * m * 8);
+  double* d_Xo = take(size_t(B) * (H + 1) * n * 8);
+  double* d_ldp = take(size_t(B) * (r + 1) * 8);
+  double* d_sums = take((r + 2) * 8);
+  const size_t thn = theta_stride ? size_t(B) * r : r;
+  cudaError_t ce;
+#define PDP_CK(x) if ((ce = (x)) != cudaSuccess) return fail(PDP_ERR_CUDA, "pdp_sens_fwd_host: %s", cudaGetErrorString(ce))
+  PDP_CK(cudaMemcpyAsync(d_x0, x0_host, size_t(B) * n * 8, cudaMemcpyHostToDevice, st));
+  PDP_CK(cudaMemcpyAsync(d_th, theta_host, thn * 8, cudaMemcpyHostToDevice, st));
+  if (inputs_host) PDP_CK(cudaMemcpyAsync(d_in, inputs_host, size_t(B) * H * m * 8, cudaMemcpyHostToDevice, st));
+  if (Xobs_host) PDP_CK(cudaMemcpyAsync(d_Xo, Xobs_host, size_t(B) * (H + 1) * n * 8, cudaMemcpyHostToDevice, st));
+  int e = pdp_sens_fwd(sys, B, H, d_x0, d_th, theta_stride, inputs_host ? d_in : nullptr, Xobs_host ? d_Xo : nullptr,
+                       nullptr, nullptr, nullptr, nullptr, d_ldp, nullptr, stream);
+  if (e) return e;
+  if (loss_dp_host) PDP_CK(cudaMemcpyAsync(loss_dp_host, d_ldp, size_t(B) * (r + 1) * 8, cudaMemcpyDeviceToHost, st));
+  if (sums_host) {
+    e = pdp_reduce_loss_dp(B, (int)r, d_ldp, d_sums, red, pdp_reduce_workspace_bytes((int)r), stream);
+    if (e) return e;
+    PDP_CK(cudaMemcpyAsync(sums_host, d_sums, (r + 2) * 8, cudaMemcpyDeviceToHost, st));
+  }
 #undef PDP_CK
   return PDP_OK;
 }

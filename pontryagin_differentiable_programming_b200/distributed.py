@@ -17,12 +17,28 @@ def shard_bounds(global_batch: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def reduce_loss_dp(loss_dp_local: torch.Tensor, group=None):
-    """loss_dp_local[B_local, r+1] (per-trajectory loss and half-gradient) -> (mean loss, mean dp[r])
-    over the global batch.  One all-reduce of r+2 float64 values; identity when not initialised."""
+def batch_sums(loss_dp_local: torch.Tensor) -> torch.Tensor:
+    """loss_dp_local[B_local, r+1] -> partial[r+2] = (sum loss, sum dp, B_local).  CUDA tensors go through the C ABI's
+    deterministic reduction kernel (``pdp_reduce_loss_dp``: one launch, nothing eager between the sweep kernel and the
+    collective); CPU tensors (the gloo tests of the host logic) use torch."""
+    if loss_dp_local.is_cuda:
+        from . import engine
+        return engine.reduce_loss_dp(loss_dp_local.contiguous())
     count = torch.full((1,), float(loss_dp_local.shape[0]), dtype=loss_dp_local.dtype, device=loss_dp_local.device)
-    partial = torch.cat([loss_dp_local.sum(dim=0), count])       # (fill kernel, not a host copy: graph-capturable)
+    return torch.cat([loss_dp_local.sum(dim=0), count])
+
+
+def all_reduce_sums(partial: torch.Tensor, group=None) -> torch.Tensor:
+    """The single collective of an outer iteration: SUM all-reduce of r+2 float64 (in place); identity when the process
+    group is not initialised or has one rank."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=group)
+    return partial
+
+
+def reduce_loss_dp(loss_dp_local: torch.Tensor, group=None):
+    """loss_dp_local[B_local, r+1] (per-trajectory loss and half-gradient) -> (mean loss, mean dp[r])
+    over the global batch.  One reduction kernel + one all-reduce of r+2 float64 values."""
+    partial = all_reduce_sums(batch_sums(loss_dp_local), group)
     count = partial[-1]
     return partial[0] / count, partial[1:-1] / count

@@ -32,6 +32,74 @@ def _chk(t, shape, name, device):
         raise ValueError("%s is on %s, expected %s" % (name, t.device, device))
 
 
+_RED_WS = {}
+
+
+def reduce_loss_dp(loss_dp, out=None):
+    """loss_dp[B, r+1] (CUDA float64) -> sums[r+2] = (sum loss, sum dp[r], B): the batch reduction of the outer loops
+    (reference PDP/PDP.py:1293-1294, Examples/IRL/quadrotor/uav_PDP.py:78-81) as ONE deterministic kernel of the C ABI
+    (``pdp_reduce_loss_dp``); the result is what a multi-GPU run all-reduces.  Stream-ordered, graph-capturable."""
+    require_cuda()
+    dev = loss_dp.device
+    B, r1 = loss_dp.shape
+    _chk(loss_dp, (B, r1), "loss_dp", dev)
+    lib = backend.load_library()
+    st = torch.cuda.current_stream(dev)
+    key = (dev, r1, st.cuda_stream)
+    ws = _RED_WS.get(key)
+    if ws is None:
+        ws = torch.zeros(int(lib.pdp_reduce_workspace_bytes(r1 - 1)), dtype=torch.uint8, device=dev)   # ticket word = 0
+        _RED_WS[key] = ws
+    if out is None:
+        out = torch.empty(r1 + 1, dtype=torch.float64, device=dev)
+    else:
+        _chk(out, (r1 + 1,), "out", dev)
+    with torch.cuda.device(dev):
+        backend.check(lib.pdp_reduce_loss_dp(B, r1 - 1, _ptr(loss_dp), _ptr(out), _ptr(ws), ws.numel(), st.cuda_stream),
+                      "pdp_reduce_loss_dp")
+    return out
+
+
+def _host_chk(t, shape, name):
+    if not (t.is_pinned() and t.is_contiguous() and t.dtype == torch.float64):
+        raise ValueError("%s must be a pinned contiguous float64 host tensor" % name)
+    if tuple(t.shape) != tuple(shape):
+        raise ValueError("%s has shape %s, expected %s" % (name, tuple(t.shape), tuple(shape)))
+
+
+class _ChunkedHostCall:
+    """Shared driver of the *_host entry points: the batch is cut into ``n_chunks`` sub-batches issued alternately on two
+    side streams (copies of one sub-batch overlap the kernels of the other); the call returns with the work ordered
+    into the current stream."""
+
+    def __init__(self):
+        self._side = {}
+
+    def run(self, dev, B, n_chunks, issue):
+        n_chunks = max(1, min(int(n_chunks), B))
+        bounds = [(B * c) // n_chunks for c in range(n_chunks + 1)]
+        cur = torch.cuda.current_stream(dev)
+        if n_chunks == 1:
+            with torch.cuda.device(dev):
+                issue(0, 0, B, cur)
+            return
+        side = self._side.get(dev)
+        if side is None:
+            side = self._side[dev] = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+        start = torch.cuda.Event()
+        start.record(cur)
+        with torch.cuda.device(dev):
+            for c in range(n_chunks):
+                st = side[c % 2]
+                if c < 2:
+                    st.wait_event(start)
+                issue(c, bounds[c], bounds[c + 1] - bounds[c], st)
+            for st in side:
+                done = torch.cuda.Event()
+                done.record(st)
+                cur.wait_event(done)
+
+
 class OCSystem:
     """Compiled optimal-control system: rollout/costate, fused getAuxSys+lqrSolver, dense aux eval."""
 
@@ -74,7 +142,7 @@ class OCSystem:
 
     def _workspace(self, op, B, H, device):
         need = self.handle.workspace_bytes(op, B, H)
-        key = (op, device)
+        key = (op, device, torch.cuda.current_stream(device).cuda_stream)
         ws = self._ws.get(key)
         if ws is None or ws.numel() < need:
             ws = torch.empty(max(need, 256), dtype=torch.uint8, device=device)
@@ -120,6 +188,13 @@ class OCSystem:
         B, H = Uref.shape[0], Uref.shape[1]
         theta, ts = self._theta(theta, B, dev)
         Bx = B * int(group)
+        _chk(x0, (B, self.n), "x0", dev)
+        _chk(Uref, (B, H, self.m), "Uref", dev)
+        _chk(Xref, (B, H + 1, self.n), "Xref", dev)
+        _chk(alpha, (Bx,), "alpha", dev)
+        if not (gains.is_cuda and gains.is_contiguous() and gains.device == dev and
+                gains.numel() * gains.element_size() >= B * H * (self.n + 1) * self.m * 8):
+            raise ValueError("gains must be a contiguous CUDA buffer of at least B*H*(n+1)*m float64 values")
         mk = lambda *shape: torch.empty(shape, dtype=torch.float64, device=dev)
         X, cost, Uout = mk(Bx, H + 1, self.n), mk(Bx), mk(Bx, H, self.m)
         Lam = mk(Bx, H, self.n) if (want_costate or want_dHu) else None
@@ -202,9 +277,16 @@ class OCSystem:
         _chk(x0, (B, self.n), "x0", dev)
         _chk(U, (B, H, self.m), "U", dev)
         theta, ts = self._theta(theta, B, dev)
+        if Xref is not None:
+            _chk(Xref, (B, H + 1, self.n), "Xref", dev)
+        if Uref is not None:
+            if Xref is None:
+                raise ValueError("sweep: Uref needs Xref")
+            _chk(Uref, (B, H, self.m), "Uref", dev)
 
         def buf(name, shape):
             if out is not None and name in out:
+                _chk(out[name], shape, name, dev)
                 return out[name]
             return torch.empty(shape, dtype=torch.float64, device=dev)
 
@@ -228,57 +310,95 @@ class OCSystem:
             res["loss_dp"] = ldp
         return res
 
+    def _host_ws(self, op, sizes, H, dev, zero=False):
+        per = [self.handle.workspace_bytes(op, sz, H) for sz in sizes]
+        key = ("host", op, dev, torch.cuda.current_stream(dev).cuda_stream)
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < sum(per):
+            ws = (torch.zeros if zero else torch.empty)(sum(per), dtype=torch.uint8, device=dev)
+            self._ws[key] = ws
+        return ws, per
+
     def sweep_host(self, x0_h, theta_h, U_h, Xref_h, Uref_h, loss_dp_h, cost_h=None, keep_dtraj=True, n_chunks=4,
-                   device=None):
+                   device=None, X_h=None, Lam_h=None, dX_h=None, dU_h=None):
         """End-to-end sweep from PINNED HOST tensors: per sub-batch H2D of (x0, theta, U, Xref, Uref) -> rollout /
         costate / fused aux-LQR kernels -> D2H of (loss, dp) [and cost], through the C-ABI ``pdp_sweep_host``.
-        The batch is cut into ``n_chunks`` sub-batches issued alternately on two side streams so that the copies
-        of one sub-batch overlap the kernels of the other; the call returns with the work ordered into the
-        current stream (synchronise that stream before reading ``loss_dp_h``)."""
+        With any of ``X_h, Lam_h, dX_h, dU_h`` (pinned host tensors) the trajectories / sensitivities themselves come
+        back as well (``pdp_sweep_host_traj``).  The batch is cut into ``n_chunks`` sub-batches issued alternately on two
+        side streams so that the copies of one sub-batch overlap the kernels of the other; the call returns with the
+        work ordered into the current stream (synchronise that stream before reading the host outputs)."""
         require_cuda()
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
         B, H = U_h.shape[0], U_h.shape[1]
-        for t_, nm_ in ((x0_h, "x0"), (theta_h, "theta"), (U_h, "U"), (Xref_h, "Xref"), (loss_dp_h, "loss_dp")):
-            if not (t_.is_pinned() and t_.is_contiguous() and t_.dtype == torch.float64):
-                raise ValueError("sweep_host: %s must be a pinned contiguous float64 host tensor" % nm_)
-        ts = 0 if theta_h.shape[0] == 1 else self.r
+        n, m, r = self.n, self.m, self.r
+        ts = 0 if (theta_h.dim() == 1 or theta_h.shape[0] == 1) else r
+        _host_chk(x0_h, (B, n), "x0")
+        _host_chk(theta_h, (B, r) if ts else tuple(theta_h.shape), "theta")
+        if theta_h.numel() != (B * r if ts else r):
+            raise ValueError("theta has %d elements, expected %d" % (theta_h.numel(), B * r if ts else r))
+        _host_chk(U_h, (B, H, m), "U")
+        _host_chk(Xref_h, (B, H + 1, n), "Xref")
+        _host_chk(loss_dp_h, (B, r + 1), "loss_dp")
+        for t_, shp, nm_ in ((Uref_h, (B, H, m), "Uref"), (cost_h, (B,), "cost"), (X_h, (B, H + 1, n), "X"),
+                             (Lam_h, (B, H, n), "Lam"), (dX_h, (B, H + 1, n, r), "dX"), (dU_h, (B, H, m, r), "dU")):
+            if t_ is not None:
+                _host_chk(t_, shp, nm_)
+        traj = any(t_ is not None for t_ in (X_h, Lam_h, dX_h, dU_h))
         n_chunks = max(1, min(int(n_chunks), B))
-        bounds = [(B * c) // n_chunks for c in range(n_chunks + 1)]
-        sizes = [bounds[c + 1] - bounds[c] for c in range(n_chunks)]
-        per = [self.handle.workspace_bytes(backend.OP_SWEEP_HOST, sz, H) for sz in sizes]
-        key = ("host", dev)
-        ws = self._ws.get(key)
-        if ws is None or ws.numel() < sum(per):
-            ws = torch.empty(sum(per), dtype=torch.uint8, device=dev)
-            self._ws[key] = ws
-        if getattr(self, "_side", None) is None:
-            self._side = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
-        cur = torch.cuda.current_stream(dev)
-        start = torch.cuda.Event()
-        start.record(cur)
-        lib = self.handle.lib
-        off = 0
-        el = 8
-        with torch.cuda.device(dev):
-            for c in range(n_chunks):
-                lo, sz = bounds[c], sizes[c]
-                st = self._side[c % 2] if n_chunks > 1 else cur
-                if n_chunks > 1 and c < 2:
-                    st.wait_event(start)
-                backend.check(lib.pdp_sweep_host(
-                    self.handle.ptr, sz, H, x0_h.data_ptr() + lo * self.n * el,
-                    theta_h.data_ptr() + (lo * self.r * el if ts else 0), ts, U_h.data_ptr() + lo * H * self.m * el,
-                    Xref_h.data_ptr() + lo * (H + 1) * self.n * el,
-                    (Uref_h.data_ptr() + lo * H * self.m * el) if Uref_h is not None else None,
-                    loss_dp_h.data_ptr() + lo * (self.r + 1) * el,
-                    (cost_h.data_ptr() + lo * el) if cost_h is not None else None, 1 if keep_dtraj else 0,
-                    ws.data_ptr() + off, per[c], st.cuda_stream), "pdp_sweep_host")
-                off += per[c]
-            if n_chunks > 1:
-                for st in self._side:
-                    done = torch.cuda.Event()
-                    done.record(st)
-                    cur.wait_event(done)
+        sizes = [(B * (c + 1)) // n_chunks - (B * c) // n_chunks for c in range(n_chunks)]
+        ws, per = self._host_ws(backend.OP_SWEEP_HOST, sizes, H, dev)
+        offs = [sum(per[:c]) for c in range(n_chunks)]
+        lib, el = self.handle.lib, 8
+        at = lambda t_, lo, row: None if t_ is None else t_.data_ptr() + lo * row * el
+
+        def issue(c, lo, sz, st):
+            common = (self.handle.ptr, sz, H, at(x0_h, lo, n), theta_h.data_ptr() + (lo * r * el if ts else 0), ts,
+                      at(U_h, lo, H * m), at(Xref_h, lo, (H + 1) * n), at(Uref_h, lo, H * m), at(loss_dp_h, lo, r + 1),
+                      at(cost_h, lo, 1))
+            if traj:
+                backend.check(lib.pdp_sweep_host_traj(*common, at(X_h, lo, (H + 1) * n), at(Lam_h, lo, H * n),
+                                                      at(dX_h, lo, (H + 1) * n * r), at(dU_h, lo, H * m * r),
+                                                      ws.data_ptr() + offs[c], per[c], st.cuda_stream), "pdp_sweep_host_traj")
+            else:
+                backend.check(lib.pdp_sweep_host(*common, 1 if keep_dtraj else 0, ws.data_ptr() + offs[c], per[c],
+                                                 st.cuda_stream), "pdp_sweep_host")
+
+        if getattr(self, "_hostcall", None) is None:
+            self._hostcall = _ChunkedHostCall()
+        self._hostcall.run(dev, B, n_chunks, issue)
+
+    def rollout_costate_host(self, x0_h, theta_h, U_h, cost_h=None, dHu_h=None, X_h=None, Lam_h=None, n_chunks=4, device=None):
+        """End-to-end rollout + costate (+ adjoint gradient dH/du) from PINNED HOST tensors through the C-ABI
+        ``pdp_rollout_costate_host`` (the batched ``ControlPlanning.recmat_step``, reference PDP/PDP.py:1100-1114);
+        same sub-batch / two-stream scheme as :meth:`sweep_host`."""
+        require_cuda()
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        B, H = U_h.shape[0], U_h.shape[1]
+        n, m = self.n, self.m
+        nth = theta_h.shape[-1]
+        ts = 0 if (theta_h.dim() == 1 or theta_h.shape[0] == 1) else nth
+        _host_chk(x0_h, (B, n), "x0")
+        _host_chk(theta_h, tuple(theta_h.shape), "theta")
+        _host_chk(U_h, (B, H, m), "U")
+        for t_, shp, nm_ in ((cost_h, (B,), "cost"), (dHu_h, (B, H, m), "dHu"), (X_h, (B, H + 1, n), "X"), (Lam_h, (B, H, n), "Lam")):
+            if t_ is not None:
+                _host_chk(t_, shp, nm_)
+        n_chunks = max(1, min(int(n_chunks), B))
+        sizes = [(B * (c + 1)) // n_chunks - (B * c) // n_chunks for c in range(n_chunks)]
+        ws, per = self._host_ws(backend.OP_ROLLOUT_HOST, sizes, H, dev)
+        offs = [sum(per[:c]) for c in range(n_chunks)]
+        lib, el = self.handle.lib, 8
+        at = lambda t_, lo, row: None if t_ is None else t_.data_ptr() + lo * row * el
+
+        def issue(c, lo, sz, st):
+            backend.check(lib.pdp_rollout_costate_host(
+                self.handle.ptr, sz, H, at(x0_h, lo, n), theta_h.data_ptr() + (lo * nth * el if ts else 0), ts,
+                at(U_h, lo, H * m), at(cost_h, lo, 1), at(dHu_h, lo, H * m), at(X_h, lo, (H + 1) * n), at(Lam_h, lo, H * n),
+                ws.data_ptr() + offs[c], per[c], st.cuda_stream), "pdp_rollout_costate_host")
+
+        if getattr(self, "_hostcall", None) is None:
+            self._hostcall = _ChunkedHostCall()
+        self._hostcall.run(dev, B, n_chunks, issue)
 
     def aux_eval(self, X, U, Lam, theta):
         """Dense auxiliary matrices (legacy getAuxSys return value) as a dict of [B,H,...] tensors."""
@@ -341,6 +461,48 @@ class _SensSystem:
             if v is not None:
                 out[k] = v
         return out
+
+
+    def step_host(self, x0_h, theta_h, H, inputs_h=None, Xobs_h=None, loss_dp_h=None, sums_h=None, n_chunks=4, device=None):
+        """End-to-end fused step from PINNED HOST tensors through the C-ABI ``pdp_sens_fwd_host``: H2D of x0 / theta (and
+        inputs / observed states for SysID) -> ``pdp_k_sens_fwd`` -> D2H of ``loss_dp_h[B,r+1]`` and / or of the per-sub-batch
+        reductions ``sums_h[n_chunks, r+2]`` = (sum loss, sum dp, count) -- add the rows and divide by the count for the
+        batch mean of reference PDP/PDP.py:1293-1294."""
+        require_cuda()
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        B = x0_h.shape[0]
+        n, m, r = self.n, self.m, self.r
+        ts = 0 if (theta_h.dim() == 1 or theta_h.shape[0] == 1) else r
+        _host_chk(x0_h, (B, n), "x0")
+        _host_chk(theta_h, (B, r) if ts else tuple(theta_h.shape), "theta")
+        for t_, shp, nm_ in ((inputs_h, (B, H, m), "inputs"), (Xobs_h, (B, H + 1, n), "Xobs"), (loss_dp_h, (B, r + 1), "loss_dp")):
+            if t_ is not None:
+                _host_chk(t_, shp, nm_)
+        n_chunks = max(1, min(int(n_chunks), B))
+        if sums_h is not None:
+            _host_chk(sums_h, (n_chunks, r + 2), "sums")
+        if loss_dp_h is None and sums_h is None:
+            raise ValueError("step_host: give loss_dp_h and / or sums_h")
+        sizes = [(B * (c + 1)) // n_chunks - (B * c) // n_chunks for c in range(n_chunks)]
+        per = [self.handle.workspace_bytes(backend.OP_SENS_HOST, sz, H) for sz in sizes]
+        key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+        if not hasattr(self, "_hws"):
+            self._hws, self._hostcall = {}, _ChunkedHostCall()
+        ws = self._hws.get(key)
+        if ws is None or ws.numel() < sum(per):
+            ws = self._hws[key] = torch.zeros(sum(per), dtype=torch.uint8, device=dev)      # reduction tickets start at zero
+        offs = [sum(per[:c]) for c in range(n_chunks)]
+        lib, el = self.handle.lib, 8
+        at = lambda t_, lo, row: None if t_ is None else t_.data_ptr() + lo * row * el
+
+        def issue(c, lo, sz, st):
+            backend.check(lib.pdp_sens_fwd_host(
+                self.handle.ptr, sz, H, at(x0_h, lo, n), theta_h.data_ptr() + (lo * r * el if ts else 0), ts,
+                at(inputs_h, lo, H * m), at(Xobs_h, lo, (H + 1) * n), at(loss_dp_h, lo, r + 1),
+                None if sums_h is None else sums_h.data_ptr() + c * (r + 2) * el,
+                ws.data_ptr() + offs[c], per[c], st.cuda_stream), "pdp_sens_fwd_host")
+
+        self._hostcall.run(dev, B, n_chunks, issue)
 
 
 class SysIDSystem(_SensSystem):

@@ -238,6 +238,7 @@ K_AUX_LQR = r'''
 //   The auxiliary matrices are evaluated in chunks of PDP_CH steps with lanes = time steps; they never
 //   exist in HBM.  Two kernels (not one) so that each gets its own register allocation / occupancy.
 // =====================================================================================================
+static_assert(PDP_NS <= 32, "one stack row per lane: n + m + r must not exceed 32 (codegen raises before this)");
 extern "C" __global__ void __launch_bounds__(PDP_WPB * 32, PDP_MINB)
 pdp_k_aux_lqr_bwd(int B, int H, const double* __restrict__ X, const double* __restrict__ U, const double* __restrict__ Lam,
                   const double* __restrict__ theta, int theta_stride, double* __restrict__ gains,

@@ -276,3 +276,37 @@ def test_symbolic_warp_and_recovery_matrix_builders():
     g = cp.recovery_matrix_fn(x0, Uw).full().ravel()
     fd = np.array([(warped(Uw + h * np.eye(3)[i])[0] - warped(Uw - h * np.eye(3)[i])[0]) / (2 * h) for i in range(3)])
     assert np.max(np.abs(g - fd)) < 1e-6 * np.max(np.abs(fd))
+
+
+def test_stack_larger_than_a_warp_is_refused():
+    """n + m + r > 32 has no lane for the stack rows beyond 31 (one-trajectory-per-warp kernel): the generator must raise
+    instead of emitting a kernel that silently drops rows (round-1 advisor finding)."""
+    from pontryagin_differentiable_programming_b200 import codegen
+    from pontryagin_differentiable_programming_b200.symbolic import SX, dot, vertcat
+    x, u, th = SX.sym("x", 20), SX.sym("u", 5), SX.sym("th", 10)
+    dyn = x + 0.1 * vertcat(*[x[(i + 1) % 20] * th[i % 10] + (u[i % 5] if i < 5 else 0) for i in range(20)])
+    with pytest.raises(ValueError, match="exceeds the 32 rows"):
+        codegen.OCModuleSource(x, u, th, dyn, dot(x, x) + dot(u, u), dot(x, x))
+    th7 = SX.sym("th", 7)
+    dyn7 = x + 0.1 * vertcat(*[x[(i + 1) % 20] * th7[i % 7] + (u[i % 5] if i < 5 else 0) for i in range(20)])
+    ok = codegen.OCModuleSource(x, u, th7, dyn7, dot(x, x) + dot(u, u), dot(x, x))             # 20 + 5 + 7 = 32 fits
+    assert ok.ns == 32 and ok.bwd_pack == 1 and "static_assert(PDP_NS <= 32" in ok.source()
+
+
+def test_ocsolver_refuses_finite_bounds():
+    """The reference passes state / control bounds to IPOPT (PDP.py:147-168); the unconstrained CUDA solver must not
+    silently ignore them."""
+    from PDP import PDP
+    from JinEnv import JinEnv
+    env = JinEnv.SinglePendulum()
+    env.initDyn(l=1, m=1, damping_ratio=0.1)
+    env.initCost(wq=10, wdq=1, wu=0.1)
+    oc = PDP.OCSys()
+    oc.setAuxvarVariable()
+    oc.setStateVariable(env.X)
+    oc.setControlVariable(env.U, control_lb=[-2.0], control_ub=[2.0])
+    oc.setDyn(env.X + 0.1 * env.f)
+    oc.setPathCost(env.path_cost)
+    oc.setFinalCost(env.final_cost)
+    with pytest.raises(NotImplementedError, match="control_lb"):
+        oc.ocSolver([0, 0], 10)

@@ -89,3 +89,33 @@ print("legacy-chain modules built")
 # the one-trajectory-per-warp build of the quadrotor module (tests/test_gpu_fullsize.py compares the two layouts)
 from tools.tune_aux_lqr import make, V1  # noqa: E402
 print("quadrotor, one trajectory per warp", make(**V1).module_path)
+
+# modules of tests/test_gpu_dropin_run.py (the unmodified reference scripts executed on the GPU box)
+cpl25 = PDP.ControlPlanning()
+cpl25.setStateVariable(cart.X)
+cpl25.setControlVariable(cart.U)
+cpl25.setDyn(cart.X + 0.05 * cart.f)
+cpl25.setPathCost(cart.path_cost)
+cpl25.setFinalCost(cart.final_cost)
+cpl25.init_step(25)
+print("cartpole ControlPlanning poly H=25", cpl25._cp_system().module_path)
+toc = PDP.OCSys()
+toc.setStateVariable(cart.X)
+toc.setControlVariable(cart.U)
+toc.setDyn(cart.X + 0.05 * cart.f)
+toc.setPathCost(cart.path_cost)
+toc.setFinalCost(cart.final_cost)
+toc.setAuxvarVariable()
+print("cartpole ground-truth OCSys", ocsolver.newton_system(toc._system()).module_path)
+pen = JinEnv.SinglePendulum()
+pen.initDyn()
+pen.initCost()
+poc = PDP.OCSys()
+poc.setAuxvarVariable(vertcat(pen.dyn_auxvar, pen.cost_auxvar))
+poc.setStateVariable(pen.X)
+poc.setControlVariable(pen.U)
+poc.setDyn(pen.X + dt11 * pen.f)
+poc.setPathCost(pen.path_cost)
+poc.setFinalCost(pen.final_cost)
+print("pendulum IRL script", ocsolver.newton_system(poc._system()).module_path)
+engine.DenseLQR.get(2, 1, 5)
