@@ -510,7 +510,6 @@ class SysIDSystem(_SensSystem):
 
     def __init__(self, state, control, auxvar, dyn, verbose=False, **kw):
         from . import codegen_sens
-        kw.setdefault("max_group_cols", 3)     # measured on B200 (profiles/r1d_secondary_configs.json): 2 groups of <= 3
         super().__init__(codegen_sens.SensModuleSource(codegen_sens.KIND_SYSID, state, control, auxvar, dyn, **kw), verbose)
 
     def step(self, inputs, Xobs, theta, x0=None, want_traj=False, want_sens=False, status=None):

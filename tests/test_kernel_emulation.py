@@ -96,34 +96,67 @@ def test_emulated_two_trajectory_kernel_chunk_tails_and_per_trajectory_theta():
             assert _rel(ldp[b, 1:], np.asarray(dp).ravel()) < 1e-10
 
 
-@pytest.mark.parametrize("env", ["quadrotor", "pendulum", "cartpole"])
-def test_emulated_rollout_costate_kernel_matches_oracle(env):
-    """pdp_k_rollout_costate (thread per trajectory; two-stage prefetched row loads with both address parities:
-    rows of n = 13 doubles alternate between 16-byte aligned and misaligned) vs the oracle's rollout / PMP costate
-    recursion (PDP.py:158-175, 203-209)."""
+@pytest.mark.parametrize("env,B,H", [("quadrotor", 37, 9), ("quadrotor", 5, 1), ("pendulum", 33, 21), ("cartpole", 3, 8),
+                                     ("rocket", 2, 6)])
+def test_emulated_rollout_costate_kernel_matches_oracle(env, B, H):
+    """pdp_k_rollout_costate (lane = trajectory; rows staged through shared tiles by warp-cooperative coalesced copies,
+    results written in place over the consumed rows) vs the oracle's rollout / PMP costate recursion / dH/du
+    (PDP.py:158-175, 203-209): batches that end inside a warp, horizons that end inside a chunk, one-step horizon."""
     from pontryagin_differentiable_programming_b200 import systems
     src = systems.OC_BUILDERS[env](0.1).src
     builder, kw = ORACLE_ENVS[env]
     oc = pdp_oracle.build_oc(builder(**kw), 0.1)
     rng = np.random.default_rng(2)
-    B, H = 5, 9
     x0 = 0.3 * rng.standard_normal((B, src.n))
-    if env == "quadrotor":
+    if env in ("quadrotor", "rocket"):
         x0[:, 6] += 1.0
     theta = 1.0 + 0.2 * rng.uniform(-1, 1, (B, src.r))
     U = 0.5 * rng.standard_normal((B, H, src.m)) + (2.5 if env == "quadrotor" else 0.0)
     emu = warp_emu.Emulator(src)
-    for shift in (0, 1):                      # both parities of the base address
-        buf = np.zeros(B * H * src.m + 1)
-        Ush = buf[shift:shift + B * H * src.m].reshape(B, H, src.m)
-        Ush[...] = U
-        X, L, cost, dHu = emu.rollout(x0, theta, U if shift == 0 else Ush, want_dHu=True)
-        for b in range(B):
-            Xr, c = oc.rollout(x0[b], U[b], theta[b])
-            Lr = oc.costate(Xr, U[b], theta[b])
-            assert np.max(np.abs(X[b] - Xr)) < 1e-12
-            assert _rel(L[b], Lr) < 1e-12
-            assert abs(cost[b] - float(c)) < 1e-11 * max(1.0, abs(float(c)))
+    X, L, cost, dHu = emu.rollout(x0, theta, U, want_dHu=True)
+    assert not np.isnan(X).any() and not np.isnan(L).any() and not np.isnan(dHu).any()
+    for b in sorted({0, 1, B // 2, B - 1}):
+        Xr, c = oc.rollout(x0[b], U[b], theta[b])
+        Lr = oc.costate(Xr, U[b], theta[b])
+        assert np.max(np.abs(X[b] - Xr)) < 1e-12
+        assert _rel(L[b], Lr) < 1e-12
+        assert abs(cost[b] - float(c)) < 1e-11 * max(1.0, abs(float(c)))
+        assert _rel(dHu[b], oc.dHu_traj(Xr, U[b], Lr, theta[b])) < 1e-11
+    X2, L2, cost2, _ = emu.rollout(x0, theta, U)                      # without dH/du: same X / Lam / cost
+    assert np.array_equal(X, X2) and np.array_equal(L, L2) and np.array_equal(cost, cost2)
+
+
+def test_emulated_closed_loop_rollout_with_candidate_groups():
+    """Closed-loop mode of the rollout kernel (the batched ocSolver's line search): u_t = U[t] + alpha k_t + K_t (x_t - Xref[t])
+    with `group` candidates per source trajectory in one launch, vs a NumPy restatement on the oracle's dynamics."""
+    from pontryagin_differentiable_programming_b200 import systems
+    src = systems.OC_BUILDERS["pendulum"](0.1).src
+    oc = pdp_oracle.build_oc(envs.pendulum(), 0.1)
+    rng = np.random.default_rng(3)
+    Bs, H, group = 13, 11, 3
+    n, m = src.n, src.m
+    x0 = 0.3 * rng.standard_normal((Bs, n))
+    theta = 1.0 + 0.2 * rng.uniform(-1, 1, (Bs, src.r))
+    U = 0.5 * rng.standard_normal((Bs, H, m))
+    Xref = np.stack([oc.rollout(x0[b], U[b], theta[b])[0] for b in range(Bs)])
+    gains = 0.1 * rng.standard_normal((Bs, H, (n + 1) * m))
+    alpha = rng.uniform(0.1, 1.0, Bs * group)
+    emu = warp_emu.Emulator(src)
+    X, L, cost, dHu, Uout = emu.rollout(x0, theta, U, want_dHu=True, feedback=dict(gains=gains, X=Xref, alpha=alpha, group=group))
+    for b in (0, 1, 17, Bs * group - 1):
+        bs = b // group
+        x = x0[bs].copy()
+        Ua = np.zeros((H, m))
+        for t in range(H):
+            K = gains[bs, t, :n * m].reshape(n, m)               # record layout: rows 0..n-1 = columns of K, then k
+            k = gains[bs, t, n * m:]
+            Ua[t] = U[bs, t] + alpha[b] * k + (x - Xref[bs, t]) @ K
+            assert np.max(np.abs(X[b, t] - x)) < 1e-12
+            x = np.asarray(oc.dyn_fn(x, Ua[t], theta[bs]), dtype=np.float64).reshape(n)
+        assert np.max(np.abs(Uout[b] - Ua)) < 1e-12
+        Xr, c = oc.rollout(x0[bs], Ua, theta[bs])
+        assert abs(cost[b] - float(c)) < 1e-11 * max(1.0, abs(float(c)))
+        assert _rel(L[b], oc.costate(Xr, Ua, theta[bs])) < 1e-11
 
 
 @pytest.mark.parametrize("env", ["quadrotor", "pendulum"])
@@ -201,6 +234,44 @@ def test_emulated_sysid_kernel_matches_k1_golden_and_oracle():
         X = sid.integrateDyn(states[b, 0], inputs[b], theta)
         assert _rel(out["X"][b], X) < 1e-13
         assert _rel(out["dX"][b], np.stack(sid.sens(X, inputs[b], theta))) < 1e-12
+    fused = emu.run(states[:, 0], theta, H, inputs=inputs, Xobs=states, fused_only=True)     # pdp_k_sens_fwd (no outputs)
+    assert np.array_equal(fused["loss_dp"], out["loss_dp"])
+
+
+@pytest.mark.parametrize("groups", [0, 2, 5])
+def test_emulated_sysid_kernel_ragged_batch_and_chunk_tails(groups):
+    """35 trajectories (a second block with three live lanes), H = 11 (not a multiple of either chunk length), column
+    groups = warps of a block (default one column per warp / two columns per warp / everything in one warp): every
+    output vs the oracle, fused-only entry point identical."""
+    from JinEnv import JinEnv
+    from pontryagin_differentiable_programming_b200 import codegen_sens
+    env = JinEnv.Quadrotor()
+    env.initDyn(c=0.01)
+    src = codegen_sens.SensModuleSource(codegen_sens.KIND_SYSID, env.X, env.U, env.dyn_auxvar, env.X + 0.1 * env.f,
+                                        max_group_cols=groups)
+    assert len(src.groups) == {0: 5, 2: 3, 5: 1}[groups]
+    rng = np.random.default_rng(4)
+    B, H = 35, 11
+    inputs = rng.uniform(-3, 3, (B, H, 4))
+    x0 = np.tile(np.array([-8, -6, 9., 0, 0, 0, 1, 0, 0, 0, 0, 0, 0]), (B, 1)) + 0.05 * rng.standard_normal((B, 13))
+    th_true = np.array([1, 1, 1, 1, 0.4])
+    theta = th_true + np.array([0.1, -0.2, 0.15, 0.2, -0.05])
+    e = envs.quadrotor(c=0.01)
+    sid = pdp_oracle.OracleSysID(e["X"], e["U"], e["dyn_params"], e["X"] + 0.1 * e["f"])
+    Xobs = np.stack([sid.integrateDyn(x0[b], inputs[b], th_true) for b in range(B)])
+    emu = warp_emu.SensEmulator(src)
+    out = emu.run(x0, theta, H, inputs=inputs, Xobs=Xobs)
+    assert not np.isnan(out["X"]).any() and not np.isnan(out["dX"]).any()
+    for b in (0, 1, 31, 32, 34):
+        X = sid.integrateDyn(x0[b], inputs[b], theta)
+        S = np.stack(sid.sens(X, inputs[b], theta))
+        loss, dp = sid.step([inputs[b]], [Xobs[b]], theta)
+        assert _rel(out["X"][b], X) < 1e-13 and _rel(out["dX"][b], S) < 1e-12
+        assert abs(out["loss_dp"][b, 0] - loss) < 1e-12 * loss and _rel(out["loss_dp"][b, 1:], dp) < 1e-11
+    fused = emu.run(x0, theta, H, inputs=inputs, Xobs=Xobs, fused_only=True)
+    assert np.array_equal(fused["loss_dp"], out["loss_dp"])
+    roll = emu.run(x0, th_true, H, inputs=inputs)                     # rollout only (no observations): X = Xobs
+    assert np.max(np.abs(roll["X"] - Xobs)) < 1e-13
 
 
 @pytest.mark.parametrize("policy", ["poly", "neural"])

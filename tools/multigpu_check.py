@@ -43,23 +43,24 @@ def main():
     e1 = max(float((loss - loss_ref).abs() / loss_ref.abs()), float((dp - dp_ref).abs().max() / dp_ref.abs().max()))
     report["sysid_sharded_vs_single_gpu_rel"] = e1
     assert e1 < 1e-12, e1
+    lr_gd = 0.01 / float(dp_ref.abs().max())      # random +-10 inputs over 100 steps make the loss (and dp) huge: scale the step
     for opt in ("gd", "adam"):
-        eager = irl.SysIDTrainer(s, t(inputs[lo:hi]), Xobs[lo:hi].contiguous(), lr=1e-5 if opt == "gd" else 1e-3, optimizer=opt)
-        graph = irl.SysIDTrainer(s, t(inputs[lo:hi]), Xobs[lo:hi].contiguous(), lr=1e-5 if opt == "gd" else 1e-3, optimizer=opt)
+        eager = irl.SysIDTrainer(s, t(inputs[lo:hi]), Xobs[lo:hi].contiguous(), lr=lr_gd if opt == "gd" else 1e-3, optimizer=opt)
+        graph = irl.SysIDTrainer(s, t(inputs[lo:hi]), Xobs[lo:hi].contiguous(), lr=lr_gd if opt == "gd" else 1e-3, optimizer=opt)
         th_e = th_g = t(theta)
         for k in range(6):
             le, th_e = eager.step(th_e)
             lg, th_g = graph.step_graph(th_g)
             lg, th_g = lg.clone(), th_g.clone()
             err = max(float((le - lg).abs() / le.abs()), float((th_e - th_g).abs().max()))
-            assert err < 1e-12, (opt, k, err)
+            assert err < 1e-12, (opt, k, err, float(le), float(lg))
         report["sysid_graph_vs_eager_%s" % opt] = err
         report["sysid_loss_after_6_%s" % opt] = float(lg)
     # iterations per second of the captured iteration at the C5 per-GPU size
     B5 = 32768
     inputs5, x05, _, _ = bench.synth_sysid(B5, H, seed=(5, rank))
     X5 = s.step(t(inputs5), None, t(th_true), x0=t(x05), want_traj=True)["X"]
-    tr5 = irl.SysIDTrainer(s, t(inputs5), X5, lr=1e-5)
+    tr5 = irl.SysIDTrainer(s, t(inputs5), X5, lr=1e-3, optimizer="adam")
     th = t(theta)
     for _ in range(5):
         th = tr5.step_graph(th)[1].clone()

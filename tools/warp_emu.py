@@ -14,9 +14,8 @@ on the GPU).
     emu = warp_emu.Emulator(src)                       # src: an OCModuleSource / NewtonModuleSource / LQRModuleSource
     gains, status = emu.backward(X, U, Lam, theta)     # numpy float64 in / out
     dX, dU, loss_dp, status = emu.forward(X, U, theta, gains)
-    X, Lam, cost, dHu = emu.rollout(x0, theta, U)      # thread-per-trajectory kernel; multi_warp=True: whole blocks of
-                                                       # the multi-warp kernel as host threads, __syncthreads = barrier
-    emu.fused(...), emu.backward_dense(aux, term), emu.forward_dense(aux, gains)
+    X, Lam, cost, dHu = emu.rollout(x0, theta, U)      # warp-cooperative rollout / costate kernel (lane = trajectory)
+    emu.backward_dense(aux, term), emu.forward_dense(aux, gains)
     warp_emu.SensEmulator(sens_src).run(...)           # SysID / ControlPlanning sensitivity kernel
 """
 from __future__ import annotations
@@ -86,13 +85,6 @@ static void* emu_lane(void* p) {
   threadIdx.x = EA.tx0 + lane; threadIdx.y = threadIdx.z = 0;
   blockIdx.x = EA.bx; blockIdx.y = blockIdx.z = 0;
   blockDim.x = EA.bdim; blockDim.y = blockDim.z = 1;
-#ifdef PDP_FUSED_DOUBLES
-  if (EA.kernel == 2) {
-    pdp_k_aux_lqr_fused(EA.B, EA.H, EA.X, EA.U, EA.Lam, EA.theta, EA.theta_stride, EA.X0a, EA.x0a_stride, EA.dX, EA.dU,
-                        EA.gains, EA.Xref, EA.Uref, EA.loss_dp, EA.auxrec, EA.termrec, EA.status);
-    return nullptr;
-  }
-#endif
   if (EA.kernel == 0)
     EMU_BWD_KERNEL(EA.B, EA.H, EA.X, EA.U, EA.Lam, EA.theta, EA.theta_stride, EA.gains, EA.auxrec, EA.termrec, EA.status);
   else
@@ -132,49 +124,32 @@ extern "C" void emu_forward(int B, int H, const double* X, const double* U, cons
   emu_run((B + per_block - 1) / per_block, PDP_WPBF);
 }
 extern "C" int emu_grec() { return PDP_GREC; }
-#ifdef PDP_FUSED_DOUBLES
-extern "C" void emu_fused(int B, int H, const double* X, const double* U, const double* Lam, const double* theta,
-                          int theta_stride, double* dX, double* dU, double* gains, const double* Xref, const double* Uref,
-                          double* loss_dp, int* status) {
-  memset(&EA, 0, sizeof(EA));
-  EA.kernel = 2; EA.B = B; EA.H = H; EA.X = X; EA.U = U; EA.Lam = Lam; EA.theta = theta; EA.theta_stride = theta_stride;
-  EA.dX = dX; EA.dU = dU; EA.gains = gains; EA.Xref = Xref; EA.Uref = Uref; EA.loss_dp = loss_dp; EA.status = status;
-  emu_run((B + PDP_WPB * 2 - 1) / (PDP_WPB * 2), PDP_WPB);
-}
-#endif
-#ifdef PDP_RP
-// multi-warp rollout kernel: a whole block (PDP_RP warps) runs as PDP_RP * 32 host threads, __syncthreads = block barrier
-struct emu_mw_args { int B, H, theta_stride; const double *x0, *theta, *U; double *X, *Lam, *cost, *dHu; int* status; unsigned bx; };
-static emu_mw_args MW;
-static void* emu_mw_thread(void* p) {
+#ifdef EMU_HAS_ROLLOUT
+// rollout / costate kernel: one warp (32 host threads, __syncwarp = barrier) per block of 32 trajectories
+struct emu_ro_args { int B, H, theta_stride, fb_group; const double *x0, *theta, *U, *fb_gains, *fb_X, *fb_alpha;
+                     double *X, *Lam, *cost, *dHu, *Uout; int* status; unsigned bx; };
+static emu_ro_args RO;
+static void* emu_ro_lane(void* p) {
   threadIdx.x = (unsigned)(uintptr_t)p; threadIdx.y = threadIdx.z = 0;
-  blockIdx.x = MW.bx; blockIdx.y = blockIdx.z = 0; blockDim.x = PDP_RP * 32;
-  pdp_k_rollout_costate_mw(MW.B, MW.H, MW.x0, MW.theta, MW.theta_stride, MW.U, MW.X, MW.Lam, MW.cost, MW.dHu, MW.status);
+  blockIdx.x = RO.bx; blockIdx.y = blockIdx.z = 0; blockDim.x = 32;
+  pdp_k_rollout_costate(RO.B, RO.H, RO.x0, RO.theta, RO.theta_stride, RO.U, RO.X, RO.Lam, RO.cost, RO.dHu, RO.status,
+                        RO.fb_gains, RO.fb_X, RO.fb_alpha, RO.Uout, RO.fb_group);
   return nullptr;
 }
-extern "C" void emu_rollout_mw(int B, int H, const double* x0, const double* theta, int theta_stride, const double* U,
-                               double* X, double* Lam, double* cost, double* dHu, int* status) {
-  MW.B = B; MW.H = H; MW.theta_stride = theta_stride; MW.x0 = x0; MW.theta = theta; MW.U = U; MW.X = X; MW.Lam = Lam;
-  MW.cost = cost; MW.dHu = dHu; MW.status = status;
-  const unsigned nt = PDP_RP * 32;
-  pthread_barrier_init(&emu_block_bar, nullptr, nt);
-  for (unsigned bx = 0; bx < (unsigned)(B + 31) / 32; ++bx) {
-    MW.bx = bx;
-    pthread_t th[256];
-    for (unsigned l = 0; l < nt; ++l) pthread_create(&th[l], nullptr, emu_mw_thread, (void*)(uintptr_t)l);
-    for (unsigned l = 0; l < nt; ++l) pthread_join(th[l], nullptr);
-  }
-  pthread_barrier_destroy(&emu_block_bar);
-}
-#endif
-#ifdef EMU_HAS_ROLLOUT
-// thread-per-trajectory kernel without warp-level primitives: the threads run one after the other
 extern "C" void emu_rollout(int B, int H, const double* x0, const double* theta, int theta_stride, const double* U,
-                            double* X, double* Lam, double* cost, double* dHu, int* status) {
-  for (int b = 0; b < B; ++b) {
-    threadIdx.x = b % 128; blockIdx.x = b / 128; blockDim.x = 128;
-    pdp_k_rollout_costate(B, H, x0, theta, theta_stride, U, X, Lam, cost, dHu, status, nullptr, nullptr, nullptr, nullptr, 1);
+                            double* X, double* Lam, double* cost, double* dHu, int* status,
+                            const double* fb_gains, const double* fb_X, const double* fb_alpha, double* Uout, int fb_group) {
+  RO.B = B; RO.H = H; RO.theta_stride = theta_stride; RO.x0 = x0; RO.theta = theta; RO.U = U; RO.X = X; RO.Lam = Lam;
+  RO.cost = cost; RO.dHu = dHu; RO.status = status; RO.fb_gains = fb_gains; RO.fb_X = fb_X; RO.fb_alpha = fb_alpha;
+  RO.Uout = Uout; RO.fb_group = fb_group;
+  pthread_barrier_init(&emu_bar, nullptr, 32);
+  for (unsigned bx = 0; bx < (unsigned)(B + 31) / 32; ++bx) {
+    RO.bx = bx;
+    pthread_t th[32];
+    for (unsigned l = 0; l < 32; ++l) pthread_create(&th[l], nullptr, emu_ro_lane, (void*)(uintptr_t)l);
+    for (unsigned l = 0; l < 32; ++l) pthread_join(th[l], nullptr);
   }
+  pthread_barrier_destroy(&emu_bar);
 }
 #endif
 '''
@@ -188,7 +163,7 @@ def translate(cuda_source: str) -> str:
     if cut >= 0:
         cut = cuda_source.rfind("// ====", 0, cut)
     else:
-        cut = cuda_source.find('extern "C" void pdpmod_info')      # sensitivity modules: launchers follow the kernel
+        cut = cuda_source.find('extern "C" void pdpmod_info')      # sensitivity modules: launchers follow the kernels
     if cut < 0:
         raise ValueError("launcher marker not found in the generated source")
     body = cuda_source[:cut]
@@ -229,41 +204,27 @@ class Emulator:
     def _p(a):
         return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
-    def rollout(self, x0, theta, U, want_dHu=False, multi_warp=False):
-        """pdp_k_rollout_costate (or, for modules generated with rollout_parts > 1, pdp_k_rollout_costate_mw) -> X, Lam,
-        cost[, dHu]."""
-        B, H = U.shape[0], U.shape[1]
+    def rollout(self, x0, theta, U, want_dHu=False, feedback=None):
+        """pdp_k_rollout_costate -> X, Lam, cost[, dHu].  ``feedback`` = dict(gains[Bs,H,(n+1)*m], X[Bs,H+1,n], alpha[B],
+        group): closed-loop mode (B = group * Bs candidates); then the applied controls are returned as a fifth item."""
         x0, U = (np.ascontiguousarray(a, dtype=np.float64) for a in (x0, U))
+        H = U.shape[1]
         theta = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
         ts = 0 if theta.shape[0] == 1 else theta.shape[1]
+        group = int(feedback["group"]) if feedback else 1
+        B = U.shape[0] * group
         X = np.full((B, H + 1, self.n), np.nan)
         Lam = np.full((B, H, self.n), np.nan)
         cost = np.full(B, np.nan)
         dHu = np.full((B, H, self.m), np.nan) if want_dHu else None
         status = np.zeros(B, dtype=np.int32)
-        fn = self.lib.emu_rollout_mw if multi_warp else self.lib.emu_rollout
-        fn(B, H, self._p(x0), self._p(theta), ts, self._p(U), self._p(X), self._p(Lam), self._p(cost), self._p(dHu),
-           self._p(status))
-        return X, Lam, cost, dHu
-
-    def fused(self, X, U, Lam, theta, Xref=None, Uref=None):
-        """pdp_k_aux_lqr_fused (modules generated with fused=1) -> dX, dU, loss_dp, gains, status."""
-        B, H = U.shape[0], U.shape[1]
-        n, m, r = self.n, self.m, self.r
-        X, U, Lam = (np.ascontiguousarray(a, dtype=np.float64) for a in (X, U, Lam))
-        theta = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
-        ts = 0 if theta.shape[0] == 1 else theta.shape[1]
-        dX, dU = np.full((B, H + 1, n, r), np.nan), np.full((B, H, m, r), np.nan)
-        gains = np.full((B, H, self.grec), np.nan)
-        status = np.zeros(B, dtype=np.int32)
-        ldp = None
-        if Xref is not None:
-            Xref = np.ascontiguousarray(Xref, dtype=np.float64)
-            Uref = None if Uref is None else np.ascontiguousarray(Uref, dtype=np.float64)
-            ldp = np.full((B, r + 1), np.nan)
-        self.lib.emu_fused(B, H, self._p(X), self._p(U), self._p(Lam), self._p(theta), ts, self._p(dX), self._p(dU),
-                           self._p(gains), self._p(Xref), self._p(Uref), self._p(ldp), self._p(status))
-        return dX, dU, ldp, gains, status
+        fg = fx = fa = Uout = None
+        if feedback:
+            fg, fx, fa = (np.ascontiguousarray(feedback[k], dtype=np.float64) for k in ("gains", "X", "alpha"))
+            Uout = np.full((B, H, self.m), np.nan)
+        self.lib.emu_rollout(B, H, self._p(x0), self._p(theta), ts, self._p(U), self._p(X), self._p(Lam), self._p(cost),
+                             self._p(dHu), self._p(status), self._p(fg), self._p(fx), self._p(fa), self._p(Uout), group)
+        return (X, Lam, cost, dHu, Uout) if feedback else (X, Lam, cost, dHu)
 
     def backward_dense(self, aux, term):
         """Generic dense LQR module: aux[B,H,NDENSE] (per step [F|G|E|Hxx|Hxu|Hxe|Hux|Huu|Hue] row-major), term[B,n*n+n*r]."""
@@ -316,14 +277,33 @@ class Emulator:
 
 
 SENS_DRIVER = r'''
-// pdp_k_sens_fwd: one thread per (trajectory, column group), no warp-level primitives: threads run one after the other
+// block = PDP_NG warps x 32 lanes as host threads; __syncthreads = block barrier
+struct emu_sens_args { int B, H, theta_stride; const double *x0, *theta, *inputs, *Xobs; double *X, *Uout, *dX, *dU, *loss_dp;
+                       int* status; unsigned bx; int out; };
+static emu_sens_args SA;
+static void* emu_sens_thread(void* p) {
+  threadIdx.x = (unsigned)(uintptr_t)p; threadIdx.y = threadIdx.z = 0;
+  blockIdx.x = SA.bx; blockIdx.y = blockIdx.z = 0; blockDim.x = PDP_NG * 32;
+  if (SA.out)
+    pdp_k_sens_fwd_out(SA.B, SA.H, SA.x0, SA.theta, SA.theta_stride, SA.inputs, SA.Xobs, SA.X, SA.Uout, SA.dX, SA.dU, SA.loss_dp, SA.status);
+  else
+    pdp_k_sens_fwd(SA.B, SA.H, SA.x0, SA.theta, SA.theta_stride, SA.inputs, SA.Xobs, SA.loss_dp, SA.status);
+  return nullptr;
+}
 extern "C" void emu_sens(int B, int H, const double* x0, const double* theta, int theta_stride, const double* inputs,
                          const double* Xobs, double* X, double* Uout, double* dX, double* dU, double* loss_dp, int* status) {
-  for (int g = 0; g < PDP_NG; ++g)
-    for (int b = 0; b < B; ++b) {
-      threadIdx.x = b % PDP_BLOCK; blockIdx.x = b / PDP_BLOCK; blockIdx.y = g; blockDim.x = PDP_BLOCK;
-      pdp_k_sens_fwd(B, H, x0, theta, theta_stride, inputs, Xobs, X, Uout, dX, dU, loss_dp, status);
-    }
+  SA.B = B; SA.H = H; SA.theta_stride = theta_stride; SA.x0 = x0; SA.theta = theta; SA.inputs = inputs; SA.Xobs = Xobs;
+  SA.X = X; SA.Uout = Uout; SA.dX = dX; SA.dU = dU; SA.loss_dp = loss_dp; SA.status = status;
+  SA.out = (X || Uout || dX || dU) ? 1 : 0;
+  const unsigned nt = PDP_NG * 32;
+  pthread_barrier_init(&emu_block_bar, nullptr, nt);
+  for (unsigned bx = 0; bx < (unsigned)(B + 31) / 32; ++bx) {
+    SA.bx = bx;
+    pthread_t th[512];
+    for (unsigned l = 0; l < nt; ++l) pthread_create(&th[l], nullptr, emu_sens_thread, (void*)(uintptr_t)l);
+    for (unsigned l = 0; l < nt; ++l) pthread_join(th[l], nullptr);
+  }
+  pthread_barrier_destroy(&emu_block_bar);
 }
 '''
 
@@ -350,8 +330,9 @@ class SensEmulator:
             os.replace(so + ".tmp", so)
         self.lib = ctypes.CDLL(so)
 
-    def run(self, x0, theta, H, inputs=None, Xobs=None, policy=False):
-        """-> X[B,H+1,n], U[B,H,m] (policy modules), dX[B,H+1,n,r], dU[B,H,m,r] (policy), loss_dp[B,r+1]."""
+    def run(self, x0, theta, H, inputs=None, Xobs=None, policy=False, fused_only=False):
+        """-> X[B,H+1,n], U[B,H,m] (policy modules), dX[B,H+1,n,r], dU[B,H,m,r] (policy), loss_dp[B,r+1].
+        ``fused_only``: the entry point without trajectory outputs (pdp_k_sens_fwd) -> loss_dp only."""
         p = Emulator._p
         x0 = np.ascontiguousarray(np.atleast_2d(x0), dtype=np.float64)
         B = x0.shape[0]
@@ -359,10 +340,10 @@ class SensEmulator:
         ts = 0 if theta.shape[0] == 1 else theta.shape[1]
         inputs = None if inputs is None else np.ascontiguousarray(inputs, dtype=np.float64)
         Xobs = None if Xobs is None else np.ascontiguousarray(Xobs, dtype=np.float64)
-        X = np.full((B, H + 1, self.n), np.nan)
-        dX = np.full((B, H + 1, self.n, self.r), np.nan)
-        Uo = np.full((B, H, self.m), np.nan) if policy else None
-        dU = np.full((B, H, self.m, self.r), np.nan) if policy else None
+        X = None if fused_only else np.full((B, H + 1, self.n), np.nan)
+        dX = None if fused_only else np.full((B, H + 1, self.n, self.r), np.nan)
+        Uo = np.full((B, H, self.m), np.nan) if (policy and not fused_only) else None
+        dU = np.full((B, H, self.m, self.r), np.nan) if (policy and not fused_only) else None
         ldp = np.zeros((B, self.r + 1))
         status = np.zeros(B, dtype=np.int32)
         self.lib.emu_sens(B, H, p(x0), p(theta), ts, p(inputs), p(Xobs), p(X), p(Uo), p(dX), p(dU), p(ldp), p(status))
