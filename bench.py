@@ -511,16 +511,18 @@ class C5(Workload):
         self.dominant = "pdp_k_sens_fwd"
 
     def step(self):
-        self.res = self.sys.step(self.inputs, self.Xobs, self.theta, status=self.status)
+        self.res = self.sys.step(self.inputs, self.Xobs, self.theta, x0=self.x0, status=self.status)
         self.finish(self.res["loss_dp"])
 
     def kernel_split(self, steps):
         torch, st = self.torch, self.stream
         kev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(steps)]
+        for _ in range(2):
+            self.step()
         torch.cuda.synchronize(self.dev)
         for k in range(steps):
             kev[k][0].record(st)
-            res = self.sys.step(self.inputs, self.Xobs, self.theta, status=self.status)
+            res = self.sys.step(self.inputs, self.Xobs, self.theta, x0=self.x0, status=self.status)
             kev[k][1].record(st)
             self.finish(res["loss_dp"])
             kev[k][2].record(st)

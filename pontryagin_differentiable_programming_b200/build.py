@@ -38,22 +38,22 @@ def compile_module(source: str, key: str, verbose: bool = False, extra_flags=())
     cu = os.path.join(MODULE_DIR, "pdpmod_%s.cu" % key)
     if os.path.isfile(so) and os.path.isfile(cu) and open(cu).read() == source:
         return so
-    # several processes (torchrun ranks, pytest-xdist workers) may generate the same system at the same time: each
-    # compiles from its OWN copy of the source and publishes .cu and .so by atomic renames, so nobody reads a half-written
-    # file; the results are identical, the last rename wins
+    # several processes (torchrun ranks, pytest-xdist workers) may generate the same system at the same time: each writes
+    # its OWN temporary copy of the source and publishes it under the final name by an atomic rename (identical content, so
+    # the last rename wins harmlessly and nvcc never reads a half-written file; compiling the final path keeps -lineinfo
+    # pointing at a file that exists); the .so is published the same way
     tmp_cu = os.path.join(MODULE_DIR, "pdpmod_%s.tmp%d.cu" % (key, os.getpid()))
     tmp = so + ".tmp.%d" % os.getpid()
     with open(tmp_cu, "w") as f:
         f.write(source)
+    os.replace(tmp_cu, cu)
     try:
-        cmd = [nvcc_path()] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp, tmp_cu]
+        cmd = [nvcc_path()] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp, cu]
         out = _run(cmd, "nvcc (system module %s)" % key)
         os.replace(tmp, so)
-        os.replace(tmp_cu, cu)
     finally:
-        for leftover in (tmp_cu, tmp):
-            if os.path.exists(leftover):
-                os.remove(leftover)
+        if os.path.exists(tmp):
+            os.remove(tmp)
     if verbose:
         print(out)
     return so

@@ -929,10 +929,6 @@ class OCModuleSource:
             "PF": getattr(self, "prefetch", 0), "PFD": max(1, getattr(self, "prefetch_dist", 3)),
             "PFL": max(0, getattr(self, "prefetch_l1_lead", 0)),
         }
-        # rollout / costate kernel: chunk length such that its two staging tiles ([x rows | u rows | x_H] x 33 lanes) stay
-        # within ~44 KB per warp (five resident warps per SM)
-        rc = max(1, min(8, (44 * 1024 // (2 * 33 * 8) - n) // (n + m)))
-        defs["RC"], defs["RTILE"] = rc, rc * (n + m) + n
         header = ["// GENERATED by pontryagin_differentiable_programming_b200/codegen.py -- do not edit",
                   "#include <cuda_runtime.h>", "#include <math.h>", "#include <stdint.h>"]
         header += ["#define PDP_%s %d" % kv for kv in defs.items()]
@@ -1033,7 +1029,7 @@ class OCModuleSource:
 
     def _kernel_text(self):
         bwd = _K_AUX_LQR_BWD2 if getattr(self, "bwd_pack", 1) == 2 else _K_AUX_LQR_BWD
-        return _K_PRELUDE + _K_STAGING + _K_ROLLOUT_AUXEVAL + _K_AUX_LQR_HEAD + bwd + _K_AUX_LQR_FWD + _K_LAUNCH_COMMON + _K_LAUNCH_LQR
+        return _K_PRELUDE + _K_ROLLOUT_AUXEVAL + _K_AUX_LQR_HEAD + bwd + _K_AUX_LQR_FWD + _K_LAUNCH_COMMON + _K_LAUNCH_LQR
 
     def _eval_macros(self):
         el = "tl" if getattr(self, "bwd_pack", 1) == 2 else "lane"       # evaluation lane = time step of the chunk
@@ -1273,4 +1269,4 @@ class LQRModuleSource(OCModuleSource):
 from .kernel_templates import (  # noqa: E402
     K_AUX_LQR_BWD as _K_AUX_LQR_BWD, K_AUX_LQR_BWD2 as _K_AUX_LQR_BWD2, K_AUX_LQR_FWD as _K_AUX_LQR_FWD,
     K_AUX_LQR_HEAD as _K_AUX_LQR_HEAD, K_AUX_LQR as _K_AUX_LQR, K_LAUNCH_COMMON as _K_LAUNCH_COMMON, K_LAUNCH_LQR as _K_LAUNCH_LQR,
-    K_PRELUDE as _K_PRELUDE, K_ROLLOUT_AUXEVAL as _K_ROLLOUT_AUXEVAL, K_STAGING as _K_STAGING)
+    K_PRELUDE as _K_PRELUDE, K_ROLLOUT_AUXEVAL as _K_ROLLOUT_AUXEVAL)

@@ -50,40 +50,52 @@ inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 // partials in block order.  The ticket counter returns to zero, so the call can be replayed from a CUDA graph.
 constexpr int kRedBlocks = 64, kRedThreads = 256;
 
+// Column sums of rows [lo, hi) of a row-major [rows, r1] array by one block, in a fixed order: thread t owns column t % r1 and
+// row lane t / r1 (consecutive threads read consecutive doubles), four independent chains per thread, then the row lanes are
+// added in lane order.  `load_cg`: read through L2 (the partial sums other blocks have just published).
+template <bool LOAD_CG>
+__device__ __forceinline__ void pdp_block_colsum(const double* __restrict__ src, int lo, int hi, int r1, double* red_sm,
+                                                 double* __restrict__ out) {
+  const int t = threadIdx.x;
+  auto ld = [&](size_t i) { return LOAD_CG ? __ldcg(src + i) : src[i]; };
+  if (r1 >= kRedThreads) {
+    for (int c = t; c < r1; c += kRedThreads) {      // thread per column, consecutive threads read consecutive doubles
+      double a = 0.0;
+      for (int row = lo; row < hi; ++row) a += ld((size_t)row * r1 + c);
+      out[c] = a;
+    }
+    return;
+  }
+  const int k = kRedThreads / r1;                    // row lanes
+  const int c = t % r1, rl = t / r1;
+  if (rl < k) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int row = lo + rl;
+    for (; row + 3 * k < hi; row += 4 * k) {
+      a0 += ld((size_t)row * r1 + c);
+      a1 += ld((size_t)(row + k) * r1 + c);
+      a2 += ld((size_t)(row + 2 * k) * r1 + c);
+      a3 += ld((size_t)(row + 3 * k) * r1 + c);
+    }
+    for (; row < hi; row += k) a0 += ld((size_t)row * r1 + c);
+    red_sm[rl * r1 + c] = (a0 + a1) + (a2 + a3);
+  }
+  __syncthreads();
+  if (t < r1) {
+    double a = 0.0;
+    for (int j = 0; j < k; ++j) a += red_sm[j * r1 + t];
+    out[t] = a;
+  }
+  __syncthreads();
+}
+
 extern "C" __global__ void __launch_bounds__(kRedThreads)
 pdp_k_reduce_loss_dp(int B, int r1, const double* __restrict__ ldp, double* __restrict__ sums, double* __restrict__ partial,
                      unsigned int* __restrict__ ticket) {
   extern __shared__ double red_sm[];                 // [row lanes][r1] (r1 < blockDim) or unused
   const int g = blockIdx.x, t = threadIdx.x;
   const int lo = (int)(((long long)B * g) / gridDim.x), hi = (int)(((long long)B * (g + 1)) / gridDim.x);
-  if (r1 >= kRedThreads) {
-    for (int c = t; c < r1; c += kRedThreads) {      // thread per column, consecutive threads read consecutive doubles
-      double a = 0.0;
-      for (int row = lo; row < hi; ++row) a += ldp[(size_t)row * r1 + c];
-      partial[(size_t)g * r1 + c] = a;
-    }
-  } else {
-    const int k = kRedThreads / r1;                  // row lanes
-    const int c = t % r1, rl = t / r1;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;   // four independent chains, combined in a fixed order
-    if (rl < k) {
-      int row = lo + rl;
-      for (; row + 3 * k < hi; row += 4 * k) {
-        a0 += ldp[(size_t)row * r1 + c];
-        a1 += ldp[(size_t)(row + k) * r1 + c];
-        a2 += ldp[(size_t)(row + 2 * k) * r1 + c];
-        a3 += ldp[(size_t)(row + 3 * k) * r1 + c];
-      }
-      for (; row < hi; row += k) a0 += ldp[(size_t)row * r1 + c];
-      red_sm[rl * r1 + c] = (a0 + a1) + (a2 + a3);
-    }
-    __syncthreads();
-    if (t < r1) {
-      double a = 0.0;
-      for (int j = 0; j < k; ++j) a += red_sm[j * r1 + t];
-      partial[(size_t)g * r1 + t] = a;
-    }
-  }
+  pdp_block_colsum<false>(ldp, lo, hi, r1, red_sm, partial + (size_t)g * r1);
   __shared__ bool last;
   __threadfence();
   __syncthreads();
@@ -91,11 +103,7 @@ pdp_k_reduce_loss_dp(int B, int r1, const double* __restrict__ ldp, double* __re
   __syncthreads();
   if (!last) return;
   __threadfence();
-  for (int c = t; c < r1; c += kRedThreads) {
-    double a = 0.0;
-    for (int j = 0; j < (int)gridDim.x; ++j) a += __ldcg(partial + (size_t)j * r1 + c);
-    sums[c] = a;
-  }
+  pdp_block_colsum<true>(partial, 0, (int)gridDim.x, r1, red_sm, sums);
   if (t == 0) { sums[r1] = (double)B; *ticket = 0u; }
 }
 

@@ -510,6 +510,7 @@ class SysIDSystem(_SensSystem):
 
     def __init__(self, state, control, auxvar, dyn, verbose=False, **kw):
         from . import codegen_sens
+        kw.setdefault("max_group_cols", 3)     # measured on B200 (profiles/r1d_secondary_configs.json): 2 groups of <= 3
         super().__init__(codegen_sens.SensModuleSource(codegen_sens.KIND_SYSID, state, control, auxvar, dyn, **kw), verbose)
 
     def step(self, inputs, Xobs, theta, x0=None, want_traj=False, want_sens=False, status=None):
@@ -530,6 +531,9 @@ class CPSystem(_SensSystem):
 
     def __init__(self, state, control, auxvar, dyn, policy, tvar, path_cost, final_cost, verbose=False, **kw):
         from . import codegen_sens
+        # column groups of <= 3 (measured at C2, B = 4096: 0.174 ms vs 0.201 ms in one group, all outputs written); large
+        # parameter vectors (neural policies) keep groups of <= 12 so that a thread's columns fit its shared-memory slice
+        kw.setdefault("max_group_cols", 3 if auxvar.numel() <= 12 else 12)
         super().__init__(codegen_sens.SensModuleSource(codegen_sens.KIND_CP, state, control, auxvar, dyn, policy=policy,
                                                        tvar=tvar, path_cost=path_cost, final_cost=final_cost, **kw), verbose)
 

@@ -148,10 +148,12 @@ class SysIDTrainer:
         self.sys, self.inputs, self.states, self.lr, self.group = system, inputs.contiguous(), states.contiguous(), float(lr), group
         self.update = _Update(optimizer, lr, system.r, self.inputs.device)
         self.status = torch.zeros(self.inputs.shape[0], dtype=torch.int32, device=self.inputs.device)
+        self._x0 = self.states[:, 0, :].contiguous()          # once, not one strided-copy kernel per iteration
 
     def gradient(self, theta):
         th = theta.reshape(1, -1).to(self.inputs.device, torch.float64)
-        return distributed.reduce_loss_dp(self.sys.step(self.inputs, self.states, th, status=self.status)["loss_dp"], self.group)
+        res = self.sys.step(self.inputs, self.states, th, x0=self._x0, status=self.status)
+        return distributed.reduce_loss_dp(res["loss_dp"], self.group)
 
     def step(self, theta):
         loss, dp = self.gradient(theta)
@@ -163,7 +165,6 @@ class SysIDTrainer:
         dev = self.inputs.device
         if getattr(self, "_graph", None) is None:
             self._theta_in = theta.detach().reshape(-1).to(dev, torch.float64).clone()
-            self._x0 = self.states[:, 0, :].contiguous()
 
             def it():
                 res = self.sys.step(self.inputs, self.states, self._theta_in.reshape(1, -1), x0=self._x0, status=self.status)

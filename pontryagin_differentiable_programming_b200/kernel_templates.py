@@ -22,52 +22,34 @@ __device__ __forceinline__ void pdp_prefetch_l1(const void* p) {
 
 '''
 
-K_STAGING = r'''
-// =====================================================================================================
-// Warp-cooperative staging of per-trajectory rows (lane = trajectory).
-//   The rows a lane reads / writes for consecutive time steps are contiguous in HBM per trajectory, but 32 lanes touching
-//   "their own" row element by element hit 32 different sectors per instruction (the L1 tag stage then serves one
-//   instruction in ~32 cycles -- the limiter of the round-1 thread-per-trajectory kernels, with their loads on the critical
-//   path as well).  Here the warp moves one trajectory after the other with consecutive lanes on consecutive doubles (full
-//   sectors) between HBM and a shared tile laid out [element][lane] with a row stride of 33 doubles, which is
-//   conflict-free both for the cooperative copies and for the lane-private accesses of the compute code.  Loads are
-//   cp.async (global -> shared without registers), issued one chunk of PDP_RC time steps ahead.
-// =====================================================================================================
-#define PDP_TLD 33
-__device__ __forceinline__ void pdp_cp_async8(double* dst_shared, const double* src_global) {
-#ifdef __CUDACC__
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(dst_shared)), "l"(src_global) : "memory");
-#else
-  *dst_shared = *src_global;      /* CPU emulation: immediate copy */
-#endif
-}
-__device__ __forceinline__ void pdp_cp_async_wait_all() {
-#ifdef __CUDACC__
-  asm volatile("cp.async.wait_all;" ::: "memory");
-#endif
-}
-// (the 32 trajectories' copies can be split over the warps of a block: warp w takes j = w, w + jstep, ...)
-// `count` doubles per trajectory, at base + traj * traj_stride + offset, for the warp's 32 trajectories b0 .. b0+31 (trajectory
-// index clamped to B-1 and divided by `group`) -> tile[(row0 + e) * 33 + j]
-__device__ __forceinline__ void pdp_stage_in(double* tile, int row0, const double* __restrict__ base, size_t traj_stride, size_t offset,
-                                             int count, int b0, int B, int group, int lane, int j0, int jstep) {
-  double* dst = tile + (size_t)(row0 + lane) * PDP_TLD;
-  #pragma unroll 4
-  for (int j = j0; j < 32; j += jstep) {
-    const int bc = b0 + j < B ? b0 + j : B - 1;
-    const int bj = group > 1 ? bc / group : bc;
-    const double* src = base + (size_t)bj * traj_stride + offset + lane;
-    for (int e = lane, k = 0; e < count; e += 32, ++k) pdp_cp_async8(dst + (size_t)k * 32 * PDP_TLD + j, src + k * 32);
+K_ROW_IO = r'''
+// Row I/O of the thread-per-trajectory kernel.  A thread's 8-byte accesses each cost one 32-byte sector request;
+// rows are only 8-byte aligned (n doubles per row), so pick the 16-byte pairing that matches the row's parity.
+template <int LEN>
+__device__ __forceinline__ void pdp_row_store(double* __restrict__ g, const double* x) {
+  if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+    #pragma unroll
+    for (int i = 0; i + 1 < LEN; i += 2) *reinterpret_cast<double2*>(g + i) = make_double2(x[i], x[i + 1]);
+    if (LEN & 1) g[LEN - 1] = x[LEN - 1];
+  } else {
+    g[0] = x[0];
+    #pragma unroll
+    for (int i = 1; i + 1 < LEN; i += 2) *reinterpret_cast<double2*>(g + i) = make_double2(x[i], x[i + 1]);
+    if (!(LEN & 1)) g[LEN - 1] = x[LEN - 1];
   }
 }
-// tile[(row0 + e) * 33 + j] -> `count` doubles per trajectory at base + (b0 + j) * traj_stride + offset, valid trajectories only
-__device__ __forceinline__ void pdp_stage_out(const double* tile, int row0, double* __restrict__ base, size_t traj_stride, size_t offset,
-                                              int count, int b0, int nvalid, int lane, int j0, int jstep) {
-  const double* src = tile + (size_t)(row0 + lane) * PDP_TLD;
-  #pragma unroll 4
-  for (int j = j0; j < nvalid; j += jstep) {
-    double* dst = base + (size_t)(b0 + j) * traj_stride + offset + lane;
-    for (int e = lane, k = 0; e < count; e += 32, ++k) dst[k * 32] = src[(size_t)k * 32 * PDP_TLD + j];
+
+template <int LEN>
+__device__ __forceinline__ void pdp_row_load(double* x, const double* g) {
+  if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+    #pragma unroll
+    for (int i = 0; i + 1 < LEN; i += 2) { const double2 v = *reinterpret_cast<const double2*>(g + i); x[i] = v.x; x[i + 1] = v.y; }
+    if (LEN & 1) x[LEN - 1] = g[LEN - 1];
+  } else {
+    x[0] = g[0];
+    #pragma unroll
+    for (int i = 1; i + 1 < LEN; i += 2) { const double2 v = *reinterpret_cast<const double2*>(g + i); x[i] = v.x; x[i + 1] = v.y; }
+    if (!(LEN & 1)) x[LEN - 1] = g[LEN - 1];
   }
 }
 
@@ -75,15 +57,49 @@ __device__ __forceinline__ void pdp_stage_out(const double* tile, int row0, doub
 
 K_ROLLOUT_AUXEVAL = r'''
 // =====================================================================================================
-// Kernel 1: forward rollout + cost + costate recursion (+ optional dH/du), one LANE per trajectory, one warp per block.
+// Kernel 1: forward rollout + cost + costate recursion (+ optional dH/du), one thread per trajectory.
 //   restates reference OCSys.ocSolver's rollout semantics at given controls (PDP.py:158-175) and the PMP
 //   costate recursion (PDP.py:203-209): Lam[t] = lambda_{t+1}, lambda_H = dh/dx(x_H).
-//   Time runs in chunks of PDP_RC steps.  Two shared tiles of PDP_RTILE rows [x rows (RC*n) | u rows (RC*m) | x_H (n)]:
-//   while the lanes work on one tile, the rows of the next chunk stream into the other (cp.async).  Results are written
-//   IN PLACE over the rows just consumed (forward: x_t into the x slots next to the u_t that was read; backward: lambda_{t+1}
-//   over x_t, dH/du_t over u_t) and leave through the cooperative, coalesced write-out at the end of the chunk.
 // =====================================================================================================
-extern "C" __global__ void __launch_bounds__(32)
+
+''' + K_ROW_IO + r'''
+// Two-stage form of pdp_row_load for PREFETCHED rows: `issue` puts the row into a raw buffer with the same loads for
+// both address parities (16-byte pairs starting at element `par`, the one or two left-over elements as scalars), and
+// `unpack` sorts the buffer into x[] with selects when the row is consumed one step later.  (With pdp_row_load the
+// two parity paths fill different registers and nvcc merges them with MOVs right behind the loads -- which wait
+// for the data at once: 60 % of the rollout kernel's stall samples in the ncu source view.)
+template <int LEN>
+struct pdp_row_raw { double2 p[(LEN - 1) / 2 > 0 ? (LEN - 1) / 2 : 1]; double s0, s1; int par; };
+
+template <int LEN>
+__device__ __forceinline__ void pdp_row_issue(pdp_row_raw<LEN>& r, const double* g) {
+  constexpr int NP = (LEN - 1) / 2;
+  const int par = (int)((reinterpret_cast<uintptr_t>(g) >> 3) & 1);
+  r.par = par;
+  #pragma unroll
+  for (int k = 0; k < NP; ++k) r.p[k] = *reinterpret_cast<const double2*>(g + par + 2 * k);
+  if (LEN & 1) { r.s0 = g[par ? 0 : LEN - 1]; r.s1 = 0.0; }
+  else { r.s0 = g[par ? 0 : LEN - 2]; r.s1 = g[LEN - 1]; }
+}
+
+template <int LEN>
+__device__ __forceinline__ void pdp_row_unpack(double* x, const pdp_row_raw<LEN>& r) {
+  constexpr int NP = (LEN - 1) / 2;
+  const bool odd = r.par != 0;
+  #pragma unroll
+  for (int i = 0; i < LEN; ++i) {
+    // candidate of the aligned layout / of the layout shifted by one element
+    double c0, c1;
+    if (i < 2 * NP) c0 = (i & 1) ? r.p[i / 2].y : r.p[i / 2].x;
+    else c0 = (i == LEN - 1 && !(LEN & 1)) ? r.s1 : r.s0;
+    if (i == 0) c1 = r.s0;
+    else if (i <= 2 * NP) c1 = ((i - 1) & 1) ? r.p[(i - 1) / 2].y : r.p[(i - 1) / 2].x;
+    else c1 = r.s1;
+    x[i] = odd ? c1 : c0;
+  }
+}
+
+extern "C" __global__ void __launch_bounds__(128)
 pdp_k_rollout_costate(int B, int H, const double* __restrict__ x0, const double* __restrict__ theta, int theta_stride,
                       const double* __restrict__ U, double* __restrict__ X, double* __restrict__ Lam,
                       double* __restrict__ cost, double* __restrict__ dHu, int* __restrict__ status,
@@ -93,128 +109,98 @@ pdp_k_rollout_costate(int B, int H, const double* __restrict__ x0, const double*
   // Optional closed-loop mode (batched ocSolver line search): with fb_gains != NULL the applied control is
   //   u_t = U[t] + alpha_b * k_t + K_t (x_t - fb_X[t])   (gains in the (K|k) record layout of the Riccati
   // sweep with one column) and is written to Uout.  With fb_group > 1 the launch holds fb_group candidates per source
-  // trajectory (lane b reads x0 / theta / U / fb_X / fb_gains of trajectory b / fb_group and its own alpha): a whole
+  // trajectory (thread b reads x0 / theta / U / fb_X / fb_gains of trajectory b / fb_group and its own alpha): a whole
   // back-tracking line search in one launch.
-  extern __shared__ __align__(16) double pdp_smem[];
-  const int lane = threadIdx.x & 31;
-  const int b0 = blockIdx.x * 32;
-  if (b0 >= B) return;
-  const bool live = b0 + lane < B;
-  const int b = live ? b0 + lane : B - 1;                 // tail lanes shadow a valid trajectory (they take part in the copies)
-  const int nvalid = B - b0 < 32 ? B - b0 : 32;
-  const bool fb = fb_gains != nullptr;
-  const int grp = (fb && fb_group > 1) ? fb_group : 1;
-  const int bs = b / grp;                                 // source trajectory of this lane
-  auto tile_of = [&](int k) { return pdp_smem + (size_t)k * (PDP_RTILE * PDP_TLD); };
-  constexpr int XR = 0, UR = PDP_RC * PDP_N, FR = PDP_RC * (PDP_N + PDP_M);     // first row of the x / u / final-state slots
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int bs = (fb_gains != nullptr && fb_group > 1) ? b / fb_group : b;     // source trajectory of this thread
   double x[PDP_N], xn[PDP_N], th[PDP_NTH], u[PDP_M], tmp[1];
   #pragma unroll
   for (int i = 0; i < PDP_NTH; ++i) th[i] = theta[(size_t)bs * theta_stride + i];
   #pragma unroll
   for (int i = 0; i < PDP_N; ++i) x[i] = x0[(size_t)bs * PDP_N + i];
   double J = 0.0;
-  const double fb_a = fb ? fb_alpha[b] : 0.0;
-  // ---------------------------------------------------------------- forward: rollout and cost
-  pdp_stage_in(tile_of(0), UR, U, (size_t)H * PDP_M, 0, (H < PDP_RC ? H : PDP_RC) * PDP_M, b0, B, grp, lane, 0, 1);
-  int buf = 0;
-  #pragma unroll 1
-  for (int t0 = 0; t0 < H; t0 += PDP_RC, buf ^= 1) {
-    const int nst = H - t0 < PDP_RC ? H - t0 : PDP_RC;
-    double* T = tile_of(buf) + lane;
-    pdp_cp_async_wait_all();
-    __syncwarp();
-    if (t0 + PDP_RC < H) {
-      const int nn = H - t0 - PDP_RC < PDP_RC ? H - t0 - PDP_RC : PDP_RC;
-      pdp_stage_in(tile_of(buf ^ 1), UR, U, (size_t)H * PDP_M, (size_t)(t0 + PDP_RC) * PDP_M, nn * PDP_M, b0, B, grp, lane, 0, 1);
-    }
-    #pragma unroll 1
-    for (int s = 0; s < nst; ++s) {
-      const int t = t0 + s;
+  double* Xb = X + (size_t)b * (H + 1) * PDP_N;
+  const double* Ub = U + (size_t)bs * H * PDP_M;
+  const double fb_a = fb_gains ? fb_alpha[b] : 0.0;
+  // software prefetch TWO steps ahead: two raw buffers used by alternate steps of a loop unrolled by two, so that no
+  // register move (which would wait for the load) sits between the issue of a row and its use two steps later
+  pdp_row_raw<PDP_M> una, unb;
+  pdp_row_issue<PDP_M>(una, Ub);
+  pdp_row_issue<PDP_M>(unb, Ub + (H > 1 ? 1 : 0) * PDP_M);
+  auto fstep = [&](const int t, pdp_row_raw<PDP_M>& un) {
+    pdp_row_unpack<PDP_M>(u, un);
+    pdp_row_issue<PDP_M>(un, Ub + (t + 2 < H ? t + 2 : H - 1) * PDP_M);    // unconditional, index clamped
+    if (fb_gains != nullptr) {
+      const double* g = fb_gains + ((size_t)bs * H + t) * ((PDP_N + 1) * PDP_M);
+      const double* xo = fb_X + ((size_t)bs * (H + 1) + t) * PDP_N;
       #pragma unroll
-      for (int i = 0; i < PDP_M; ++i) u[i] = T[(UR + s * PDP_M + i) * PDP_TLD];
-      if (fb) {
-        const double* g = fb_gains + ((size_t)bs * H + t) * ((PDP_N + 1) * PDP_M);
-        const double* xo = fb_X + ((size_t)bs * (H + 1) + t) * PDP_N;
+      for (int a = 0; a < PDP_M; ++a) u[a] = fma(fb_a, g[PDP_N * PDP_M + a], u[a]);
+      #pragma unroll
+      for (int l = 0; l < PDP_N; ++l) {
+        const double dx = x[l] - xo[l];
         #pragma unroll
-        for (int a = 0; a < PDP_M; ++a) u[a] = fma(fb_a, g[PDP_N * PDP_M + a], u[a]);
-        #pragma unroll
-        for (int l = 0; l < PDP_N; ++l) {
-          const double dx = x[l] - xo[l];
-          #pragma unroll
-          for (int a = 0; a < PDP_M; ++a) u[a] = fma(g[l * PDP_M + a], dx, u[a]);
-        }
-        #pragma unroll
-        for (int i = 0; i < PDP_M; ++i) T[(UR + s * PDP_M + i) * PDP_TLD] = u[i];       // applied control, written out below
+        for (int a = 0; a < PDP_M; ++a) u[a] = fma(g[l * PDP_M + a], dx, u[a]);
       }
       #pragma unroll
-      for (int i = 0; i < PDP_N; ++i) T[(XR + s * PDP_N + i) * PDP_TLD] = x[i];
-      pdp_f_path_cost(x, u, th, tmp);
-      J += tmp[0];
-      pdp_f_dyn(x, u, th, xn);
-      #pragma unroll
-      for (int i = 0; i < PDP_N; ++i) x[i] = xn[i];
+      for (int i = 0; i < PDP_M; ++i) Uout[((size_t)b * H + t) * PDP_M + i] = u[i];
     }
-    const bool last = t0 + PDP_RC >= H;
-    if (last) {                                           // x_H rides with the last chunk (rows are contiguous in X)
-      #pragma unroll
-      for (int i = 0; i < PDP_N; ++i) T[(XR + nst * PDP_N + i) * PDP_TLD] = x[i];
-    }
-    __syncwarp();
-    pdp_stage_out(tile_of(buf), XR, X, (size_t)(H + 1) * PDP_N, (size_t)t0 * PDP_N, (nst + (last ? 1 : 0)) * PDP_N, b0, nvalid, lane, 0, 1);
-    if (fb) pdp_stage_out(tile_of(buf), UR, Uout, (size_t)H * PDP_M, (size_t)t0 * PDP_M, nst * PDP_M, b0, nvalid, lane, 0, 1);
+    pdp_row_store<PDP_N>(Xb + t * PDP_N, x);
+    pdp_f_path_cost(x, u, th, tmp);
+    J += tmp[0];
+    pdp_f_dyn(x, u, th, xn);
+    #pragma unroll
+    for (int i = 0; i < PDP_N; ++i) x[i] = xn[i];
+  };
+  #pragma unroll 1
+  for (int t = 0; t < H; t += 2) {
+    fstep(t, una);
+    if (t + 1 < H) fstep(t + 1, unb);
   }
+  pdp_row_store<PDP_N>(Xb + H * PDP_N, x);
   pdp_f_final_cost(x, th, tmp);
   J += tmp[0];
-  if (cost && live) cost[b] = J;
-  const bool bad = !isfinite(J);
+  if (cost) cost[b] = J;
+  bool bad = !isfinite(J);
   if (Lam != nullptr) {
-    // ---------------------------------------------------------------- backward: costates (and dH/du)
     double lam[PDP_N], ln[PDP_N], gu[PDP_M];
+    double* Lb = Lam + (size_t)b * H * PDP_N;
     pdp_f_dhx(x, th, lam);
-    const double* Ua = fb ? Uout : U;                     // the controls actually applied
-    const int ga = fb ? 1 : grp;
-    __syncwarp();                                         // the X / Uout rows written above are read back by other lanes' copies
-    const int tlast = ((H - 1) / PDP_RC) * PDP_RC;
-    {
-      const int nn = H - tlast;
-      pdp_stage_in(tile_of(0), XR, X, (size_t)(H + 1) * PDP_N, (size_t)tlast * PDP_N, nn * PDP_N, b0, B, 1, lane, 0, 1);
-      pdp_stage_in(tile_of(0), UR, Ua, (size_t)H * PDP_M, (size_t)tlast * PDP_M, nn * PDP_M, b0, B, ga, lane, 0, 1);
-    }
-    buf = 0;
+    const double* Ua = fb_gains ? Uout + (size_t)b * H * PDP_M : Ub;      // the controls actually applied
+    // (x_{t-2}, u_{t-2}) are fetched while step t is being processed: two buffer pairs, loop unrolled by two
+    pdp_row_raw<PDP_N> xpa, xpb;
+    pdp_row_raw<PDP_M> upa, upb;
+    pdp_row_issue<PDP_N>(xpa, Xb + (H - 1) * PDP_N);
+    pdp_row_issue<PDP_M>(upa, Ua + (H - 1) * PDP_M);
+    pdp_row_issue<PDP_N>(xpb, Xb + (H > 1 ? H - 2 : 0) * PDP_N);
+    pdp_row_issue<PDP_M>(upb, Ua + (H > 1 ? H - 2 : 0) * PDP_M);
+    auto bstep = [&](const int t, pdp_row_raw<PDP_N>& xp, pdp_row_raw<PDP_M>& up) {
+      pdp_row_store<PDP_N>(Lb + t * PDP_N, lam);
+      pdp_row_unpack<PDP_N>(x, xp);
+      pdp_row_unpack<PDP_M>(u, up);
+      {
+        const int tq = t > 1 ? t - 2 : 0;       // unconditional, index clamped
+        pdp_row_issue<PDP_N>(xp, Xb + tq * PDP_N);
+        pdp_row_issue<PDP_M>(up, Ua + tq * PDP_M);
+      }
+      if (dHu != nullptr) {
+        pdp_f_dHu(x, u, lam, th, gu);
+        #pragma unroll
+        for (int i = 0; i < PDP_M; ++i) dHu[((size_t)b * H + t) * PDP_M + i] = gu[i];
+      }
+      if (t > 0) {
+        pdp_f_dHx(x, u, lam, th, ln);
+        #pragma unroll
+        for (int i = 0; i < PDP_N; ++i) lam[i] = ln[i];
+      }
+    };
     #pragma unroll 1
-    for (int tc = tlast; tc >= 0; tc -= PDP_RC, buf ^= 1) {
-      const int nst = H - tc < PDP_RC ? H - tc : PDP_RC;
-      double* T = tile_of(buf) + lane;
-      pdp_cp_async_wait_all();
-      __syncwarp();
-      if (tc > 0) {
-        pdp_stage_in(tile_of(buf ^ 1), XR, X, (size_t)(H + 1) * PDP_N, (size_t)(tc - PDP_RC) * PDP_N, PDP_RC * PDP_N, b0, B, 1, lane, 0, 1);
-        pdp_stage_in(tile_of(buf ^ 1), UR, Ua, (size_t)H * PDP_M, (size_t)(tc - PDP_RC) * PDP_M, PDP_RC * PDP_M, b0, B, ga, lane, 0, 1);
-      }
-      #pragma unroll 1
-      for (int s = nst - 1; s >= 0; --s) {
-        const int t = tc + s;
-        #pragma unroll
-        for (int i = 0; i < PDP_N; ++i) { x[i] = T[(XR + s * PDP_N + i) * PDP_TLD]; T[(XR + s * PDP_N + i) * PDP_TLD] = lam[i]; }
-        #pragma unroll
-        for (int i = 0; i < PDP_M; ++i) u[i] = T[(UR + s * PDP_M + i) * PDP_TLD];
-        if (dHu != nullptr) {
-          pdp_f_dHu(x, u, lam, th, gu);
-          #pragma unroll
-          for (int i = 0; i < PDP_M; ++i) T[(UR + s * PDP_M + i) * PDP_TLD] = gu[i];
-        }
-        if (t > 0) {
-          pdp_f_dHx(x, u, lam, th, ln);
-          #pragma unroll
-          for (int i = 0; i < PDP_N; ++i) lam[i] = ln[i];
-        }
-      }
-      __syncwarp();
-      pdp_stage_out(tile_of(buf), XR, Lam, (size_t)H * PDP_N, (size_t)tc * PDP_N, nst * PDP_N, b0, nvalid, lane, 0, 1);
-      if (dHu != nullptr) pdp_stage_out(tile_of(buf), UR, dHu, (size_t)H * PDP_M, (size_t)tc * PDP_M, nst * PDP_M, b0, nvalid, lane, 0, 1);
+    for (int t = H - 1; t >= 0; t -= 2) {
+      bstep(t, xpa, upa);
+      if (t > 0) bstep(t - 1, xpb, upb);
     }
   }
-  if (status && bad && live) atomicOr(&status[b], 1);
+  if (status && bad) atomicOr(&status[b], 1);
 }
 
 // =====================================================================================================
@@ -590,11 +576,8 @@ extern "C" int pdpmod_rollout_costate(int B, int H, const double* x0, const doub
                                       const double* fb_gains, const double* fb_X, const double* fb_alpha, double* Uout,
                                       int fb_group, cudaStream_t st) {
   if (B <= 0) return 0;
-  const size_t smem = (size_t)2 * PDP_RTILE * PDP_TLD * sizeof(double);
-  cudaError_t e = pdp_opt_in_smem((const void*)pdp_k_rollout_costate, smem);
-  if (e != cudaSuccess) return (int)e;
-  pdp_k_rollout_costate<<<(B + 31) / 32, 32, smem, st>>>(B, H, x0, theta, theta_stride, U, X, Lam, cost, dHu, status,
-                                                        fb_gains, fb_X, fb_alpha, Uout, fb_group);
+  pdp_k_rollout_costate<<<(B + 127) / 128, 128, 0, st>>>(B, H, x0, theta, theta_stride, U, X, Lam, cost, dHu, status,
+                                                         fb_gains, fb_X, fb_alpha, Uout, fb_group);
   return (int)cudaGetLastError();
 }
 

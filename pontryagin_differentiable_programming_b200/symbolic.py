@@ -424,7 +424,15 @@ def emit_c(outputs: Sequence[Node], leaf_names: Dict[int, str], prefix: str = "w
         elif op == "mul":
             e = "%s * %s" % (a[0], a[1])
         elif op == "div":
-            e = "%s / %s" % (a[0], a[1])
+            d = n.args[1]
+            if d.op == "const" and d.val != 0.0 and math.isfinite(1.0 / d.val):
+                # division by a compile-time constant -> multiplication by its reciprocal (an FP64 division is ~30
+                # instructions on the GPU; the Lagrange-polynomial policies of ControlPlanning divide by pivot differences
+                # 30 times per step).  At most one ulp from the quotient, far inside every parity tolerance.
+                r_ = 1.0 / d.val
+                e = "%s * %s" % (a[0], _c_literal(r_) if r_ >= 0 else "(%s)" % _c_literal(r_))
+            else:
+                e = "%s / %s" % (a[0], a[1])
         elif op == "neg":
             e = "-%s" % a[0]
         elif op == "sq":

@@ -99,9 +99,9 @@ def test_emulated_two_trajectory_kernel_chunk_tails_and_per_trajectory_theta():
 @pytest.mark.parametrize("env,B,H", [("quadrotor", 37, 9), ("quadrotor", 5, 1), ("pendulum", 33, 21), ("cartpole", 3, 8),
                                      ("rocket", 2, 6)])
 def test_emulated_rollout_costate_kernel_matches_oracle(env, B, H):
-    """pdp_k_rollout_costate (lane = trajectory; rows staged through shared tiles by warp-cooperative coalesced copies,
-    results written in place over the consumed rows) vs the oracle's rollout / PMP costate recursion / dH/du
-    (PDP.py:158-175, 203-209): batches that end inside a warp, horizons that end inside a chunk, one-step horizon."""
+    """pdp_k_rollout_costate (thread per trajectory; two-stage prefetched row loads with both address parities: rows of
+    n = 13 doubles alternate between 16-byte aligned and misaligned) vs the oracle's rollout / PMP costate recursion /
+    dH/du (PDP.py:158-175, 203-209): odd and even horizons, one-step horizon, batches beyond one block."""
     from pontryagin_differentiable_programming_b200 import systems
     src = systems.OC_BUILDERS[env](0.1).src
     builder, kw = ORACLE_ENVS[env]
@@ -238,20 +238,19 @@ def test_emulated_sysid_kernel_matches_k1_golden_and_oracle():
     assert np.array_equal(fused["loss_dp"], out["loss_dp"])
 
 
-@pytest.mark.parametrize("groups", [0, 2, 5])
-def test_emulated_sysid_kernel_ragged_batch_and_chunk_tails(groups):
-    """35 trajectories (a second block with three live lanes), H = 11 (not a multiple of either chunk length), column
-    groups = warps of a block (default one column per warp / two columns per warp / everything in one warp): every
-    output vs the oracle, fused-only entry point identical."""
+@pytest.mark.parametrize("groups", [1, 2, 12])
+def test_emulated_sysid_kernel_ragged_batch_and_column_groups(groups):
+    """70 trajectories (a second block with six live threads), H = 11, column groups of 1 / 2 / all columns (grid
+    dimension x): every output vs the oracle, the fused-only call identical, rollout-only mode without observations."""
     from JinEnv import JinEnv
     from pontryagin_differentiable_programming_b200 import codegen_sens
     env = JinEnv.Quadrotor()
     env.initDyn(c=0.01)
     src = codegen_sens.SensModuleSource(codegen_sens.KIND_SYSID, env.X, env.U, env.dyn_auxvar, env.X + 0.1 * env.f,
                                         max_group_cols=groups)
-    assert len(src.groups) == {0: 5, 2: 3, 5: 1}[groups]
+    assert len(src.groups) == {1: 5, 2: 3, 12: 1}[groups]
     rng = np.random.default_rng(4)
-    B, H = 35, 11
+    B, H = 70, 11
     inputs = rng.uniform(-3, 3, (B, H, 4))
     x0 = np.tile(np.array([-8, -6, 9., 0, 0, 0, 1, 0, 0, 0, 0, 0, 0]), (B, 1)) + 0.05 * rng.standard_normal((B, 13))
     th_true = np.array([1, 1, 1, 1, 0.4])
@@ -262,7 +261,7 @@ def test_emulated_sysid_kernel_ragged_batch_and_chunk_tails(groups):
     emu = warp_emu.SensEmulator(src)
     out = emu.run(x0, theta, H, inputs=inputs, Xobs=Xobs)
     assert not np.isnan(out["X"]).any() and not np.isnan(out["dX"]).any()
-    for b in (0, 1, 31, 32, 34):
+    for b in (0, 1, 63, 64, 69):
         X = sid.integrateDyn(x0[b], inputs[b], theta)
         S = np.stack(sid.sens(X, inputs[b], theta))
         loss, dp = sid.step([inputs[b]], [Xobs[b]], theta)

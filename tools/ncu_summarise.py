@@ -58,6 +58,7 @@ def source_mix(rep, kernel):
 
 def main():
     rep, prefix = sys.argv[1], sys.argv[2]
+    what = sys.argv[3] if len(sys.argv) > 3 else "bench.py --steps 1 --warmup 1, C3 B=16384, shipped configuration"
     names, units, rows = raw_page(rep)
     kcol = names.index("Kernel Name")
     kernels = [r[kcol] for r in rows]
@@ -75,12 +76,40 @@ def main():
         scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1e3, "us": 1.0, "ns": 1e-3, "s": 1e6}
         return v * scale.get(u, 1.0)
 
-    traffic = {"source": "%s_ncu_summary.csv (ncu --set full --clock-control none, bench.py --steps 1 --warmup 1, "
-                         "C3 B=16384, shipped configuration)" % prefix}
+    traffic = {"source": "%s_ncu_summary.csv (ncu --set full --clock-control none, %s)" % (prefix, what)}
     for r in rows:
         traffic[r[kcol]] = {"dram_bytes_read": val(r, "dram__bytes_read.sum"), "dram_bytes_write": val(r, "dram__bytes_write.sum"),
                             "gpu_time_us": val(r, "gpu__time_duration.sum")}
     json.dump(traffic, open(prefix + "_ncu_traffic.json", "w"), indent=1)
+    # the few metrics the roofline discussion in DESIGN.md / profiles/README.md quotes, one readable table
+    KEY = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+           "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+           "sm__warps_active.avg.per_cycle_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+           "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+           "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts.sum",
+           "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+           "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+           "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+           "lts__throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum",
+           "dram__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum", "sm__cycles_active.avg",
+           "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
+           "smsp__average_warp_latency_per_inst_issued.ratio", "local_load_requests", "smsp__inst_executed_op_local_ld.sum",
+           "smsp__inst_executed_op_local_st.sum"]
+    with open(prefix + "_ncu_key_metrics.csv", "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["metric", "unit"] + kernels)
+        for nm in KEY:
+            if nm in names:
+                j = names.index(nm)
+                w.writerow([nm, units[j]] + [r[j] for r in rows])
     with open(prefix + "_ncu_source_mix.txt", "w") as f:
         for k in sorted(set(kernels)):
             mix = source_mix(rep, k)
@@ -92,7 +121,7 @@ def main():
                     % (k, sum(ex.values()), sum(wf.values()), sum(wfi.values())))
             for op, c in ex.most_common(40):
                 f.write("  %-22s %12d  smem wavefronts %12d (ideal %d)\n" % (op, c, wf[op], wfi[op]))
-    print("wrote", prefix + "_ncu_{summary.csv,traffic.json,source_mix.txt}")
+    print("wrote", prefix + "_ncu_{summary.csv,key_metrics.csv,traffic.json,source_mix.txt}")
 
 
 if __name__ == "__main__":

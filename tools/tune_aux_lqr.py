@@ -26,6 +26,11 @@ VARIANTS = [
 # forward kernel's chunk rows (fwd 0.605), multi-warp rollout with 2 / 4 warps per 32 trajectories (0.120 / 0.178),
 # backward + forward of a warp's trajectories fused in one kernel (1.096 vs 1.054 for the two launches).  Streaming
 # stores of dX / dU (fwd 0.400) were adopted unconditionally.
+# Also measured and removed (profiles/r2f_tune_lean_backward.json): a register-lean backward step (columns of Z streamed from
+# the staging tile, [F|G] re-read from the chunk buffer) -- 0.667 ms at the same 8 warps per SM (+40 shared-memory wavefronts
+# per step), and SLOWER with every extra resident warp the smaller register budget allows: 10 warps/SM 0.770, 12: 0.957,
+# 14: 1.232, 16: 1.369 ms.  The kernel is not latency-bound: two warps per scheduler already saturate what the shared-memory
+# data path and the FP64 pipe deliver together; more warps only shrink the chunk (fewer evaluation lanes) and add spills.
 
 
 def make(verbose=False, **kw):

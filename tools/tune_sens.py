@@ -11,10 +11,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-SYSID_VARIANTS = [dict(max_group_cols=5), dict(max_group_cols=5, min_blocks=2), dict(max_group_cols=3), dict(max_group_cols=3, min_blocks=5),
-                  dict(max_group_cols=2), dict(max_group_cols=2, min_blocks=4), dict(max_group_cols=1), dict(max_group_cols=1, min_blocks=3),
-                  dict(max_group_cols=5, tile_kb_per_warp=36), dict(max_group_cols=3, tile_kb_per_warp=24)]
-CP_VARIANTS = [dict(max_group_cols=6), dict(max_group_cols=3), dict(max_group_cols=2), dict(max_group_cols=1)]
+SYSID_VARIANTS = [dict(max_group_cols=3), dict(max_group_cols=2), dict(max_group_cols=5), dict(max_group_cols=3, block=32)]
+CP_VARIANTS = [dict(max_group_cols=12), dict(max_group_cols=3)]
 
 
 def sysid(**kw):
@@ -83,7 +81,7 @@ def main():
             err = float((ldp - ref).abs().max() / ref.abs().max())
             ms = timeit(torch, lambda: s.step(inputs, Xobs, theta))
             ms_full = timeit(torch, lambda: s.step(inputs, Xobs, theta, want_traj=True, want_sens=True), iters=5)
-            rows.append({"kernel": "sens C5", "variant": v, "groups": len(s.src.groups), "rcf": s.src.rcf, "rco": s.src.rco, "ms_fused": ms,
+            rows.append({"kernel": "sens C5", "variant": v, "groups": len(s.src.groups), "ms_fused": ms,
                          "ms_full_outputs": ms_full, "alg_GBps": bench.alg_bytes_sysid(13, 4, 5, H) * B / ms / 1e6, "rel_diff_vs_first": err})
             print(json.dumps(rows[-1]), flush=True)
         # ---- C2

@@ -14,7 +14,7 @@ on the GPU).
     emu = warp_emu.Emulator(src)                       # src: an OCModuleSource / NewtonModuleSource / LQRModuleSource
     gains, status = emu.backward(X, U, Lam, theta)     # numpy float64 in / out
     dX, dU, loss_dp, status = emu.forward(X, U, theta, gains)
-    X, Lam, cost, dHu = emu.rollout(x0, theta, U)      # warp-cooperative rollout / costate kernel (lane = trajectory)
+    X, Lam, cost, dHu = emu.rollout(x0, theta, U)      # thread-per-trajectory rollout / costate kernel (threads run one by one)
     emu.backward_dense(aux, term), emu.forward_dense(aux, gains)
     warp_emu.SensEmulator(sens_src).run(...)           # SysID / ControlPlanning sensitivity kernel
 """
@@ -125,31 +125,14 @@ extern "C" void emu_forward(int B, int H, const double* X, const double* U, cons
 }
 extern "C" int emu_grec() { return PDP_GREC; }
 #ifdef EMU_HAS_ROLLOUT
-// rollout / costate kernel: one warp (32 host threads, __syncwarp = barrier) per block of 32 trajectories
-struct emu_ro_args { int B, H, theta_stride, fb_group; const double *x0, *theta, *U, *fb_gains, *fb_X, *fb_alpha;
-                     double *X, *Lam, *cost, *dHu, *Uout; int* status; unsigned bx; };
-static emu_ro_args RO;
-static void* emu_ro_lane(void* p) {
-  threadIdx.x = (unsigned)(uintptr_t)p; threadIdx.y = threadIdx.z = 0;
-  blockIdx.x = RO.bx; blockIdx.y = blockIdx.z = 0; blockDim.x = 32;
-  pdp_k_rollout_costate(RO.B, RO.H, RO.x0, RO.theta, RO.theta_stride, RO.U, RO.X, RO.Lam, RO.cost, RO.dHu, RO.status,
-                        RO.fb_gains, RO.fb_X, RO.fb_alpha, RO.Uout, RO.fb_group);
-  return nullptr;
-}
+// thread-per-trajectory kernel without warp-level primitives: the threads run one after the other
 extern "C" void emu_rollout(int B, int H, const double* x0, const double* theta, int theta_stride, const double* U,
                             double* X, double* Lam, double* cost, double* dHu, int* status,
                             const double* fb_gains, const double* fb_X, const double* fb_alpha, double* Uout, int fb_group) {
-  RO.B = B; RO.H = H; RO.theta_stride = theta_stride; RO.x0 = x0; RO.theta = theta; RO.U = U; RO.X = X; RO.Lam = Lam;
-  RO.cost = cost; RO.dHu = dHu; RO.status = status; RO.fb_gains = fb_gains; RO.fb_X = fb_X; RO.fb_alpha = fb_alpha;
-  RO.Uout = Uout; RO.fb_group = fb_group;
-  pthread_barrier_init(&emu_bar, nullptr, 32);
-  for (unsigned bx = 0; bx < (unsigned)(B + 31) / 32; ++bx) {
-    RO.bx = bx;
-    pthread_t th[32];
-    for (unsigned l = 0; l < 32; ++l) pthread_create(&th[l], nullptr, emu_ro_lane, (void*)(uintptr_t)l);
-    for (unsigned l = 0; l < 32; ++l) pthread_join(th[l], nullptr);
+  for (int b = 0; b < B; ++b) {
+    threadIdx.x = b % 128; blockIdx.x = b / 128; blockDim.x = 128;
+    pdp_k_rollout_costate(B, H, x0, theta, theta_stride, U, X, Lam, cost, dHu, status, fb_gains, fb_X, fb_alpha, Uout, fb_group);
   }
-  pthread_barrier_destroy(&emu_bar);
 }
 #endif
 '''
@@ -170,7 +153,7 @@ def translate(cuda_source: str) -> str:
     body = body.replace("#include <cuda_runtime.h>", "")
     body = body.replace("extern __shared__ __align__(16) double pdp_smem[];", "extern double pdp_smem[];")
     body = _RCP.sub(lambda mo: "%s = 1.0 / %s;" % (mo.group(1), mo.group(2)), body)
-    body = re.sub(r'asm volatile\("prefetch\.global\.L[12] \[%0\];" :: "l"\(p\)\);', "(void)p;", body)
+    body = re.sub(r'asm volatile\("prefetch\.global\.L[12] \[%0\];" :: "l"\(([^;]*?)\)\);', r"(void)(\1);", body)
     if "asm(" in body:
         raise ValueError("untranslated inline asm in the generated source")
     return body
@@ -277,33 +260,13 @@ class Emulator:
 
 
 SENS_DRIVER = r'''
-// block = PDP_NG warps x 32 lanes as host threads; __syncthreads = block barrier
-struct emu_sens_args { int B, H, theta_stride; const double *x0, *theta, *inputs, *Xobs; double *X, *Uout, *dX, *dU, *loss_dp;
-                       int* status; unsigned bx; int out; };
-static emu_sens_args SA;
-static void* emu_sens_thread(void* p) {
-  threadIdx.x = (unsigned)(uintptr_t)p; threadIdx.y = threadIdx.z = 0;
-  blockIdx.x = SA.bx; blockIdx.y = blockIdx.z = 0; blockDim.x = PDP_NG * 32;
-  if (SA.out)
-    pdp_k_sens_fwd_out(SA.B, SA.H, SA.x0, SA.theta, SA.theta_stride, SA.inputs, SA.Xobs, SA.X, SA.Uout, SA.dX, SA.dU, SA.loss_dp, SA.status);
-  else
-    pdp_k_sens_fwd(SA.B, SA.H, SA.x0, SA.theta, SA.theta_stride, SA.inputs, SA.Xobs, SA.loss_dp, SA.status);
-  return nullptr;
-}
 extern "C" void emu_sens(int B, int H, const double* x0, const double* theta, int theta_stride, const double* inputs,
                          const double* Xobs, double* X, double* Uout, double* dX, double* dU, double* loss_dp, int* status) {
-  SA.B = B; SA.H = H; SA.theta_stride = theta_stride; SA.x0 = x0; SA.theta = theta; SA.inputs = inputs; SA.Xobs = Xobs;
-  SA.X = X; SA.Uout = Uout; SA.dX = dX; SA.dU = dU; SA.loss_dp = loss_dp; SA.status = status;
-  SA.out = (X || Uout || dX || dU) ? 1 : 0;
-  const unsigned nt = PDP_NG * 32;
-  pthread_barrier_init(&emu_block_bar, nullptr, nt);
-  for (unsigned bx = 0; bx < (unsigned)(B + 31) / 32; ++bx) {
-    SA.bx = bx;
-    pthread_t th[512];
-    for (unsigned l = 0; l < nt; ++l) pthread_create(&th[l], nullptr, emu_sens_thread, (void*)(uintptr_t)l);
-    for (unsigned l = 0; l < nt; ++l) pthread_join(th[l], nullptr);
-  }
-  pthread_barrier_destroy(&emu_block_bar);
+  for (int g = 0; g < PDP_NG; ++g)
+    for (int b = 0; b < B; ++b) {
+      threadIdx.x = b % PDP_BLOCK; blockIdx.y = b / PDP_BLOCK; blockIdx.x = g; blockDim.x = PDP_BLOCK;
+      pdp_k_sens_fwd(B, H, x0, theta, theta_stride, inputs, Xobs, X, Uout, dX, dU, loss_dp, status);
+    }
 }
 '''
 
