@@ -146,6 +146,32 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measure_fp64_peak(torch, dev):
+    """FP64 FMA peak of this GPU in TFLOP/s from tools/microbench (8 independent DFMA chains per thread, 4 blocks of 256
+    threads per SM, CUDA events); None if the microbenchmark library is not built."""
+    import ctypes
+    so = os.path.join(ROOT, "tools", "microbench", "libpdp_microbench.so")
+    if not os.path.isfile(so):
+        return None
+    lib = ctypes.CDLL(so)
+    lib.pdp_fp64_peak.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    blocks, iters = sms * 4, 4096
+    out = torch.zeros(blocks * 256, dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream(dev)
+    best = 0.0
+    for k in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        if lib.pdp_fp64_peak(iters, blocks, out.data_ptr(), st.cuda_stream) != 0:
+            return None
+        e1.record(st)
+        torch.cuda.synchronize(dev)
+        if k:
+            best = max(best, 2.0 * 8 * 32 * iters * blocks * 256 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
+
+
 class ClockSampler:
     """SM clock / throttle reasons sampled through NVML by a polling thread DURING the timed region."""
 
@@ -880,8 +906,10 @@ def run_gpu(args, cfg):
         if args.config == "c3":
             n, m, r = wl.sys.n, wl.sys.m, wl.sys.r
             line["roofline"]["fp64_tflops_alg_bwd"] = alg_flops_bwd(n, m, r, H) * B / (k_ms * 1e-3) / 1e12
-            line["roofline"]["fp64_note"] = "dense-equivalent flop count; the executed-instruction FP64 pipe utilisation is " \
-                                            "the ncu figure in profiles/ (sm__inst_executed_pipe_fp64)"
+            line["roofline"]["fp64_peak_tflops_measured"] = measure_fp64_peak(torch, dev)
+            line["roofline"]["fp64_note"] = "fp64_tflops_alg_bwd is a dense-equivalent flop count (SURVEY 8(d)); the kernel exploits " \
+                                            "sparsity, so its executed-instruction FP64 pipe utilisation is the ncu figure in " \
+                                            "profiles/ (sm__inst_executed_pipe_fp64), not this number over the measured peak"
             line["config"]["step"] = "OCSystem.sweep -> pdp_sweep: 1 rollout/costate launch + %d sub-batches x (bwd, fwd) on two " \
                                      "streams, then pdp_reduce_loss_dp" % wl.parts
         if extra is not None:

@@ -73,3 +73,16 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         print(out)
     return LIB_PATH
+
+
+def build_microbench(force: bool = False) -> str:
+    """tools/microbench/fp64_peak.cu -> libpdp_microbench.so (measures the FP64 FMA peak that bench.py reports beside the
+    HBM roofline; bench / test infrastructure, not part of the product path)."""
+    d = os.path.join(os.path.dirname(PKG_DIR), "tools", "microbench")
+    src, so = os.path.join(d, "fp64_peak.cu"), os.path.join(d, "libpdp_microbench.so")
+    if not force and os.path.isfile(so) and os.path.getmtime(so) >= os.path.getmtime(src):
+        return so
+    tmp = so + ".tmp.%d" % os.getpid()
+    _run([nvcc_path()] + NVCC_FLAGS + ["-o", tmp, src], "nvcc (libpdp_microbench.so)")
+    os.replace(tmp, so)
+    return so

@@ -87,20 +87,32 @@ def _pad_ld(n):
 
 
 def _emit_function(name: str, inputs: Sequence[Tuple[str, SX]], outputs: Sequence[Node], out_expr,
-                   qualifiers="__device__ __forceinline__") -> str:
+                   qualifiers="__device__ __forceinline__", recips=None) -> str:
     """``void name(const double* in0, ..., double* out)`` computing ``outputs``.
 
     ``out_expr(i)`` gives the C lvalue for output ``i``.  Inputs are read into locals first so the
-    stores to ``out`` can never alias the loads."""
+    stores to ``out`` can never alias the loads.  ``recips = (param name, first index, [divisor nodes])``: the reciprocals
+    of these parameter-only divisors sit behind the parameters in the same array (``param[first + k]``, filled once per
+    trajectory by ``pdp_f_recips``) and divisions by them are emitted as multiplications."""
     leaf: Dict[int, str] = {}
-    used = {n.uid for n in S.topo_order(outputs) if n.op == "sym"}
+    order = S.topo_order(outputs)
+    used = {n.uid for n in order if n.op == "sym"}
     loads = []
     for pname, sx in inputs:
         for k, e in enumerate(sx.elements()):
             if e.uid in used:
                 loads.append("  const double %s_%d = %s[%d];" % (pname, k, pname, k))
                 leaf[e.uid] = "%s_%d" % (pname, k)
-    lines, names = S.emit_c(outputs, leaf)
+    rmap = None
+    if recips and recips[2]:
+        pname, first, nodes = recips
+        divisors = {n.args[1].uid for n in order if n.op == "div"}
+        rmap = {}
+        for k, d in enumerate(nodes):
+            if d.uid in divisors:
+                loads.append("  const double rcp_%d = %s[%d];" % (k, pname, first + k))
+                rmap[d.uid] = "rcp_%d" % k
+    lines, names = S.emit_c(outputs, leaf, recip=rmap)
     sig = ", ".join("const double* __restrict__ %s" % p for p, _ in inputs)
     body = ["%s void %s(%s, double* __restrict__ out) {" % (qualifiers, name, sig)]
     body += loads + lines
@@ -411,35 +423,47 @@ class OCModuleSource:
         self.h_conflicts = best
 
     # ---- device functions ----------------------------------------------------------------------
-    def _device_functions(self) -> str:
+    def _function_table(self):
+        """(name, inputs, outputs, qualifiers) of every generated device function."""
         x, u, th, lam = ("x", self.x), ("u", self.u), ("th", self.th), ("lam", self.lam)
-        parts = []
-        parts.append(_emit_function("pdp_f_dyn", [x, u, th], self.dyn.elements(), lambda i: "out[%d]" % i))
-        parts.append(_emit_function("pdp_f_path_cost", [x, u, th], self.c.elements(), lambda i: "out[%d]" % i))
-        parts.append(_emit_function("pdp_f_final_cost", [x, th], self.h.elements(), lambda i: "out[%d]" % i))
-        parts.append(_emit_function("pdp_f_dHx", [x, u, lam, th], self.dHx.elements(), lambda i: "out[%d]" % i))
-        parts.append(_emit_function("pdp_f_dHu", [x, u, lam, th], self.dHu.elements(), lambda i: "out[%d]" % i))
-        parts.append(_emit_function("pdp_f_dhx", [x, th], self.dhx.elements(), lambda i: "out[%d]" % i))
-        # all aux slots / only the dynamics-Jacobian slots
         # the two slot evaluators are deliberately NOT inlined: they run once per chunk on a few lanes and would
         # otherwise dictate the register allocation (hence the occupancy) of the per-step hot loops
         # (option inline_eval: the two-trajectory backward kernel runs at the 255-register cap anyway, so inlining costs
         # no occupancy there -- but it does not pay either)
         inl = getattr(self, "inline_eval", -1)
         inl = False if inl < 0 else bool(inl)      # measured on the two-trajectory kernel: 0.6695 vs 0.6689 ms -- no gain
-        parts.append(_emit_function("pdp_f_aux_slots", [x, u, lam, th], self.slots.nodes, lambda i: "out[%d]" % i,
-                                    qualifiers="__device__ __forceinline__" if inl else "__device__ __noinline__"))
-        parts.append(_emit_function("pdp_f_dyn_slots", [x, u, th], self.slots.nodes[:self.nvar_s] or [S.ZERO],
-                                    lambda i: "out[%d]" % i, qualifiers="__device__ __noinline__"))
+        fi, ni = "__device__ __forceinline__", "__device__ __noinline__"
         # terminal Hessians, dense row-major [hxx (n*n) | hxe (n*r)]
         term = [self.ddhxx.at(i, j) for i in range(self.n) for j in range(self.n)] + \
                [self.ddhxe.at(i, j) for i in range(self.n) for j in range(self.r)]
-        parts.append(_emit_function("pdp_f_terminal", [x, th], term, lambda i: "out[%d]" % i))
         # dense aux matrices for the legacy API: F G E Hxx Hxu Hxe Hux Huu Hue, each row-major
         dense = []
         for M in (self.dfx, self.dfu, self.dfe, self.ddHxx, self.ddHxu, self.ddHxe, self.ddHux, self.ddHuu, self.ddHue):
             dense += [M.at(i, j) for i in range(M.shape[0]) for j in range(M.shape[1])]
-        parts.append(_emit_function("pdp_f_aux_dense", [x, u, lam, th], dense, lambda i: "out[%d]" % i))
+        return [("pdp_f_dyn", [x, u, th], self.dyn.elements(), fi), ("pdp_f_path_cost", [x, u, th], self.c.elements(), fi),
+                ("pdp_f_final_cost", [x, th], self.h.elements(), fi), ("pdp_f_dHx", [x, u, lam, th], self.dHx.elements(), fi),
+                ("pdp_f_dHu", [x, u, lam, th], self.dHu.elements(), fi), ("pdp_f_dhx", [x, th], self.dhx.elements(), fi),
+                # all aux slots / only the dynamics-Jacobian slots
+                ("pdp_f_aux_slots", [x, u, lam, th], self.slots.nodes, fi if inl else ni),
+                ("pdp_f_dyn_slots", [x, u, th], self.slots.nodes[:self.nvar_s] or [S.ZERO], ni),
+                ("pdp_f_terminal", [x, th], term, fi), ("pdp_f_aux_dense", [x, u, lam, th], dense, fi)]
+
+    def _param_recips(self):
+        """Divisors that depend on the parameters only (masses, inertias, lengths ...): their reciprocals are computed once
+        per trajectory (``pdp_f_recips``) and kept behind the parameters in the same array, so the per-step code multiplies."""
+        if getattr(self, "_recips", None) is None:
+            outs = [e for _, _, o, _ in self._function_table() for e in o]
+            self._recips = S.param_divisors(outs, {e.uid for e in self.th.elements()})
+        return self._recips
+
+    def _device_functions(self) -> str:
+        rc = self._param_recips()
+        recips = ("th", self.nth, rc)
+        parts = [_emit_function(nm, ins, outs, lambda i: "out[%d]" % i, qualifiers=q, recips=recips)
+                 for nm, ins, outs, q in self._function_table()]
+        if rc:
+            parts.append(_emit_function("pdp_f_recips", [("th", self.th)], [S.div(S.ONE, d) for d in rc],
+                                        lambda i: "out[%d]" % i))
         return "\n\n".join(parts)
 
     # ---- the Riccati step body ---------------------------------------------------------------------
@@ -783,6 +807,10 @@ class OCModuleSource:
 
     fwd_smem_budget = 18 * 1024
 
+    def _nthx(self):
+        """Length of a trajectory's parameter array in the kernels: theta followed by the hoisted reciprocals."""
+        return self.nth + len(self._param_recips())
+
     def _fwd_group_stride(self):
         """Lanes per trajectory group of the forward kernel: r rounded up to even (see the kernel template)."""
         r = max(self.r, 1)
@@ -798,7 +826,7 @@ class OCModuleSource:
         ch = getattr(self, "fwd_chunk", 0)
         if not ch:
             per_step = _pad_ld(self.nvar_s) + self.n + self.m
-            fit = (self.fwd_smem_budget // (8 * fg) - self.n * self.m - max(self.nth, 1) - 16) // per_step
+            fit = (self.fwd_smem_budget // (8 * fg) - self.n * self.m - max(self._nthx(), 1) - 16) // per_step
             ch = min(WARP // fg if fg > 1 else self.chunk, max(fit, 1))
         ch = max(1, min(ch, WARP // fg))
         return fg, ch
@@ -901,7 +929,7 @@ class OCModuleSource:
         off_ks = off_zt + zt_size
         off_quu = off_ks + ks_size
         off_th = off_quu + _even(m * m)
-        warp_doubles = _even(off_th + max(self.nth, 1))
+        warp_doubles = _even(off_th + max(self._nthx(), 1))
         bp = getattr(self, "bwd_pack", 1)
         half_stride = _pad_ld(warp_doubles)       # two-trajectory kernel: per-trajectory regions = 2 (mod 16) doubles apart
         if bp == 2:
@@ -911,7 +939,7 @@ class OCModuleSource:
         fld = _pad_ld(self.nvar_s)
         foff_ks = _even(chf * fld)
         foff_th = foff_ks + _even(n * m)
-        foff_dl = foff_th + _even(max(self.nth, 1))               # residuals x - xref [CHF*n], u - uref [CHF*m]
+        foff_dl = foff_th + _even(max(self._nthx(), 1))           # residuals x - xref [CHF*n], u - uref [CHF*m]
         foff_du = foff_dl + chf * n
         fts = _pad_ld(foff_du + chf * m)
         fwarp_doubles = max(fg * fts, WARP)
@@ -922,7 +950,7 @@ class OCModuleSource:
             "FLD": fld, "FOFF_KS": foff_ks, "FOFF_TH": foff_th, "FOFF_DL": foff_dl, "FG": fg, "CHF": chf, "FTS": fts,
             "FOFF_DU": foff_du, "FGS": self._fwd_group_stride(),
             "FWARP_DOUBLES": fwarp_doubles, "WPBF": getattr(self, "wpbf", 4), "MINBF": getattr(self, "min_blocks_f", 1),
-            "WARP_DOUBLES": warp_doubles, "NTH": self.nth, "MINB": getattr(self, "min_blocks", 1), "GREC": (n + r) * m,
+            "WARP_DOUBLES": warp_doubles, "NTH": self.nth, "NRCP": self._nthx() - self.nth, "NTHX": max(self._nthx(), 1), "MINB": getattr(self, "min_blocks", 1), "GREC": (n + r) * m,
             "NDENSE": n * n + n * m + n * r + n * n + n * m + n * r + m * n + m * m + m * r,
             "BP": bp, "HS": half_stride,
             "ZMASK": sum(1 << j for j in self._zero_z_columns()) if (bp == 2 and hasattr(self, "S_ent")) else 0,
@@ -1231,6 +1259,9 @@ class LQRModuleSource(OCModuleSource):
 
     def _device_functions(self) -> str:
         return ""
+
+    def _param_recips(self):
+        return []
 
     def _extra_tables(self):
         return ["__device__ const int pdp_slot_src[%d] = {%s};" % (len(self.src_off), ", ".join(map(str, self.src_off)))]

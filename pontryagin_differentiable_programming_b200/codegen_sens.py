@@ -71,6 +71,22 @@ class SensModuleSource:
         self.gmax = max(len(g) for g in self.groups)
 
     # ------------------------------------------------------------------------------------------
+    def _param_recips(self):
+        """Divisors that depend on theta only: reciprocals computed once per thread before the time loop (see
+        ``symbolic.param_divisors``)."""
+        if getattr(self, "_recips", None) is None:
+            outs = list(self.dyn.elements())
+            for M in (self.F, self.G, self.E):
+                outs += M.elements()
+            if self.kind == KIND_CP:
+                outs += self.policy.elements() + self.Ux.elements() + self.Ue.elements() + self.cx.elements() + \
+                    self.cu.elements() + self.hx.elements() + self.c.elements() + self.h.elements()
+            self._recips = S.param_divisors(outs, {e.uid for e in self.th.elements()})
+        return self._recips
+
+    def _rmap(self):
+        return {d.uid: "rcp%d" % k for k, d in enumerate(self._param_recips())}
+
     def _leaf(self) -> Dict[int, str]:
         leaf = {}
         for k, e in enumerate(self.x.elements()):
@@ -100,7 +116,7 @@ class SensModuleSource:
         outs: List[Node] = []
         if cp:
             # the policy must be evaluated first (u is an input of everything else)
-            plines, pnames = S.emit_c(self.policy.elements(), leaf, prefix="p", indent=ind)
+            plines, pnames = S.emit_c(self.policy.elements(), leaf, prefix="p", indent=ind, recip=self._rmap())
             L += plines
             for a in range(m):
                 L.append(ind + "const double u%d = %s;" % (a, pnames[a]))
@@ -115,7 +131,7 @@ class SensModuleSource:
             outs += self.c.elements()
         else:
             outs += [self.E.at(i, c) for i in range(n) for c in cols if self.E.at(i, c).op != "const"]
-        lines, names_list = S.emit_c(outs, leaf, prefix="w", indent=ind)
+        lines, names_list = S.emit_c(outs, leaf, prefix="w", indent=ind, recip=self._rmap())
         L += lines
         names = {o.uid: nm for o, nm in zip(outs, names_list)}
         dyn_names = [names[e.uid] for e in self.dyn.elements()]
@@ -208,7 +224,7 @@ class SensModuleSource:
         leaf = self._leaf()
         if cp:
             outs = self.h.elements() + [e for e in self.hx.elements() if e.op != "const"]
-            lines, nl = S.emit_c(outs, leaf, prefix="h", indent=ind)
+            lines, nl = S.emit_c(outs, leaf, prefix="h", indent=ind, recip=self._rmap())
             L += lines
             names = {o.uid: nm for o, nm in zip(outs, nl)}
             L.append(ind + "if (grp == 0) loss += %s;" % names[self.h.elements()[0].uid])
@@ -265,6 +281,11 @@ pdp_k_sens_fwd(int B, int H, const double* __restrict__ x0, const double* __rest
   const double* th = theta + (size_t)b * theta_stride;
   for (int k = 0; k < PDP_GMAX * PDP_N; ++k) SM[k * PDP_BLOCK] = 0.0;
   double loss = 0.0;''')
+        rc = self._param_recips()
+        if rc:
+            rl, rn = S.emit_c([S.div(S.ONE, d) for d in rc], self._leaf(), prefix="q", indent="  ")
+            body += rl
+            body.append("  " + " ".join("const double rcp%d = %s;" % (k, nm) for k, nm in enumerate(rn)))
         body.append("  double " + ", ".join("xs%d = x0[(size_t)b * %d + %d]" % (i, n, i) for i in range(n)) + ";")
         body.append("  double " + ", ".join("g%d = 0.0" % k for k in range(self.gmax)) + ";")
         if not cp:

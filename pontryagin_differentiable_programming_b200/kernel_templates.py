@@ -114,9 +114,12 @@ pdp_k_rollout_costate(int B, int H, const double* __restrict__ x0, const double*
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int bs = (fb_gains != nullptr && fb_group > 1) ? b / fb_group : b;     // source trajectory of this thread
-  double x[PDP_N], xn[PDP_N], th[PDP_NTH], u[PDP_M], tmp[1];
+  double x[PDP_N], xn[PDP_N], th[PDP_NTHX], u[PDP_M], tmp[1];
   #pragma unroll
   for (int i = 0; i < PDP_NTH; ++i) th[i] = theta[(size_t)bs * theta_stride + i];
+#if PDP_NRCP > 0
+  pdp_f_recips(th, th + PDP_NTH);       // reciprocals of the parameter-only divisors, once per trajectory
+#endif
   #pragma unroll
   for (int i = 0; i < PDP_N; ++i) x[i] = x0[(size_t)bs * PDP_N + i];
   double J = 0.0;
@@ -215,7 +218,12 @@ pdp_k_aux_eval(int B, int H, const double* __restrict__ X, const double* __restr
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * (H + 1)) return;
   const int b = idx / (H + 1), t = idx - b * (H + 1);
-  const double* th = theta + (size_t)b * theta_stride;
+  double th[PDP_NTHX];
+  #pragma unroll
+  for (int i = 0; i < PDP_NTH; ++i) th[i] = theta[(size_t)b * theta_stride + i];
+#if PDP_NRCP > 0
+  pdp_f_recips(th, th + PDP_NTH);
+#endif
   if (t == H) {
     if (term) pdp_f_terminal(X + ((size_t)b * (H + 1) + H) * PDP_N, th, term + (size_t)b * (PDP_N * PDP_N + PDP_N * PDP_R));
     return;
@@ -268,6 +276,10 @@ pdp_k_aux_lqr_bwd(int B, int H, const double* __restrict__ X, const double* __re
 @@TABLOAD@@
   if (theta != nullptr) for (int i = lane; i < PDP_NTH; i += 32) TH[i] = theta[(size_t)b * theta_stride + i];
   __syncwarp();
+#if PDP_NRCP > 0
+  if (lane == 0) pdp_f_recips(TH, TH + PDP_NTH);
+  __syncwarp();
+#endif
   // ---- terminal condition P = hxx(x_H), W = hxe(x_H)  (PDP.py:561-562)
 @@EVAL_TERM@@
   __syncwarp();
@@ -334,6 +346,10 @@ pdp_k_aux_lqr_fwd(int B, int H, const double* __restrict__ X, const double* __re
       const int tb = (b0 + tg < B) ? b0 + tg : B - 1;
       wbase[tg * PDP_FTS + PDP_FOFF_TH + ti] = theta[(size_t)tb * theta_stride + ti];
     }
+#endif
+#if PDP_NRCP > 0
+  __syncwarp();
+  if (lane < PDP_FG) pdp_f_recips(wbase + lane * PDP_FTS + PDP_FOFF_TH, wbase + lane * PDP_FTS + PDP_FOFF_TH + PDP_NTH);
 #endif
   @@XDECL@@
   {
@@ -505,6 +521,10 @@ pdp_k_aux_lqr_bwd(int B, int H, const double* __restrict__ X, const double* __re
   if (theta != nullptr) for (int i = tl; i < PDP_NTH; i += 16) TH[i] = theta[(size_t)b * theta_stride + i];
   if (tl < PDP_LDZ) ZT[PDP_NS * PDP_LDZ + tl] = 0.0;
   __syncwarp();
+#if PDP_NRCP > 0
+  if (tl == 0) pdp_f_recips(TH, TH + PDP_NTH);
+  __syncwarp();
+#endif
   // ---- terminal condition P = hxx(x_H), W = hxe(x_H)  (PDP.py:561-562)
 @@EVAL_TERM@@
   __syncwarp();

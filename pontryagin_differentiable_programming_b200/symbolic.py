@@ -388,13 +388,39 @@ def _c_literal(v: float) -> str:
     return r
 
 
+def param_divisors(outputs: Iterable[Node], param_uids) -> List[Node]:
+    """Divisors of ``outputs``' divisions that depend on nothing but the symbols ``param_uids`` (and constants), each once,
+    in dependency order.  They are loop-invariant along a trajectory (parameters such as masses and inertias), so a
+    kernel computes their reciprocals ONCE per trajectory and the generated per-step code multiplies (``emit_c(...,
+    recip=...)``) instead of running a ~30-instruction FP64 division per occurrence and time step."""
+    param_uids = set(param_uids)
+    order = topo_order(outputs)
+    only_params: Dict[int, bool] = {}
+    for n in order:
+        if n.op == "const":
+            only_params[n.uid] = True
+        elif n.op == "sym":
+            only_params[n.uid] = n.uid in param_uids
+        else:
+            only_params[n.uid] = all(only_params[a.uid] for a in n.args)
+    out, seen = [], set()
+    for n in order:
+        if n.op == "div":
+            d = n.args[1]
+            if d.op != "const" and only_params[d.uid] and d.uid not in seen:
+                seen.add(d.uid)
+                out.append(d)
+    return out
+
+
 def emit_c(outputs: Sequence[Node], leaf_names: Dict[int, str], prefix: str = "w", real: str = "double",
-           indent: str = "  ") -> Tuple[List[str], List[str]]:
+           indent: str = "  ", recip: Dict[int, str] = None) -> Tuple[List[str], List[str]]:
     """Straight-line C for ``outputs``.
 
     ``leaf_names`` maps symbol uid -> C expression.  Returns ``(lines, names)`` where ``names[i]``
     is the C expression holding ``outputs[i]`` after ``lines`` have run.  Shared sub-expressions
-    are computed once; constants and leaves are inlined.
+    are computed once; constants and leaves are inlined.  ``recip`` maps the uid of a divisor node to a C
+    expression holding its precomputed reciprocal: divisions by it become multiplications.
     """
     order = topo_order(outputs)
     uses: Dict[int, int] = {}
@@ -425,7 +451,9 @@ def emit_c(outputs: Sequence[Node], leaf_names: Dict[int, str], prefix: str = "w
             e = "%s * %s" % (a[0], a[1])
         elif op == "div":
             d = n.args[1]
-            if d.op == "const" and d.val != 0.0 and math.isfinite(1.0 / d.val):
+            if recip and d.uid in recip:
+                e = "%s * %s" % (a[0], recip[d.uid])
+            elif d.op == "const" and d.val != 0.0 and math.isfinite(1.0 / d.val):
                 # division by a compile-time constant -> multiplication by its reciprocal (an FP64 division is ~30
                 # instructions on the GPU; the Lagrange-polynomial policies of ControlPlanning divide by pivot differences
                 # 30 times per step).  At most one ulp from the quotient, far inside every parity tolerance.
