@@ -335,6 +335,8 @@ int pdp_sweep(pdp_system_t* sys, int B, int H, const double* x0, const double* t
               int* status, pdp_stream_t stream) {
   if (B == 0) return PDP_OK;
   if (!Lam) return fail(PDP_ERR_ARG, "pdp_sweep: Lam buffer required");
+  // the rollout / costate kernel runs once for the whole batch: it is latency-bound (0.1 ms whatever the batch), and running
+  // it per sub-batch on the side streams measured slower (profiles/r2k_sweep_pipeline_ab.json: 1.143 vs 1.067 ms at 4 parts)
   int e = pdp_rollout_costate(sys, B, H, x0, theta, theta_stride, U, X, Lam, cost, nullptr, status, stream);
   if (e) return e;
   int parts = sys->sweep_parts > 0 ? sys->sweep_parts : (B >= 16384 ? 4 : (B >= 8192 ? 2 : 1));

@@ -61,7 +61,17 @@ def _capture(owner, fn, dev, restore):
     return graph, out
 
 
-class IRLTrainer:
+class _GraphOwner:
+    def release_graph(self):
+        """Drop the captured CUDA graph (and the tensors it pins).  In a sharded run the graph holds a captured NCCL
+        all-reduce: release it on every rank BEFORE ``torch.distributed.destroy_process_group()``, which otherwise
+        waits forever for the communicator's outstanding (captured) work."""
+        if getattr(self, "_graph", None) is not None:
+            torch.cuda.synchronize()
+            self._graph = self._g_out = self._graph_keepalive = self._graph_stream = None
+
+
+class IRLTrainer(_GraphOwner):
     """Inverse-RL / inverse-OC mode for a compiled ``OCSystem`` and a (per-rank shard of a) batch of demonstrations."""
 
     def __init__(self, system, demo_states, demo_controls, lr, warm_start=True, group=None, optimizer="gd"):
@@ -140,7 +150,7 @@ class IRLTrainer:
         return self._g_out
 
 
-class SysIDTrainer:
+class SysIDTrainer(_GraphOwner):
     """System-identification mode for a compiled ``SysIDSystem`` (reference PDP.py:1261-1296 + the GD loop of
     Examples/SysID/quadrotor/uav_PDP.py:42-48) on a (per-rank shard of a) batch of input / state trajectories."""
 

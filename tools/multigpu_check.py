@@ -30,6 +30,11 @@ def main():
     t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
     report = {"world": world}
 
+    def stage(msg):
+        if rank == 0:
+            print("[multigpu_check] %s (%.1f s)" % (msg, time.perf_counter() - t_start), file=sys.stderr, flush=True)
+    t_start = time.perf_counter()
+
     # ---------------- (a) SysID, global batch 4096 + 3 (ragged split), H = 100
     Bg, H = 4099, 100
     inputs, x0, th_true, theta = bench.synth_sysid(Bg, H, seed=21)
@@ -42,6 +47,7 @@ def main():
     loss, dp = tr.gradient(t(theta))
     e1 = max(float((loss - loss_ref).abs() / loss_ref.abs()), float((dp - dp_ref).abs().max() / dp_ref.abs().max()))
     report["sysid_sharded_vs_single_gpu_rel"] = e1
+    stage("sharded SysID gradient ok")
     assert e1 < 1e-12, e1
     lr_gd = 0.01 / float(dp_ref.abs().max())      # random +-10 inputs over 100 steps make the loss (and dp) huge: scale the step
     for opt in ("gd", "adam"):
@@ -55,6 +61,7 @@ def main():
             err = max(float((le - lg).abs() / le.abs()), float((th_e - th_g).abs().max()))
             assert err < 1e-12, (opt, k, err, float(le), float(lg))
         report["sysid_graph_vs_eager_%s" % opt] = err
+        stage("SysID graph vs eager (%s) ok" % opt)
         report["sysid_loss_after_6_%s" % opt] = float(lg)
     # iterations per second of the captured iteration at the C5 per-GPU size
     B5 = 32768
@@ -71,6 +78,7 @@ def main():
         th = tr5.step_graph(th)[1]
     torch.cuda.synchronize(); dist.barrier()
     dt = (time.perf_counter() - t0) / n_it
+    stage("C5 outer loop timed")
     report["c5_outer_loop_graph"] = {"global_batch": B5 * world, "iters_per_s": 1 / dt, "ms_per_iter": dt * 1e3,
                                      "traj_sweeps_per_s": B5 * world / dt}
 
@@ -85,16 +93,28 @@ def main():
     th_e = th_g = th0
     for k in range(4):
         le, th_e = eager.step(th_e)
+        stage("IRL eager step %d" % k)
         lg, th_g, resid = graph.step_graph(th_g, n_newton=12)
         lg, th_g = lg.clone(), th_g.clone()
+        stage("IRL graph step %d" % k)
     err = max(float((le - lg).abs() / le.abs()), float((th_e - th_g).abs().max() / th_e.abs().max()))
     report["irl_graph_vs_eager_sharded"] = err
     report["irl_diagnostics"] = eager.diagnostics()
     assert err < 1e-6, err
     if rank == 0:
-        print(json.dumps(report))
+        print(json.dumps(report), flush=True)
+    # captured NCCL collectives must be gone before the communicator is torn down (destroy_process_group hangs otherwise)
+    for tr_ in (tr5, eager, graph):
+        tr_.release_graph()
+    del tr5, eager, graph
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
     dist.barrier()
+    import threading
+    threading.Timer(60.0, lambda: os._exit(0)).start()      # belt and braces: never let a teardown problem hang the box
     dist.destroy_process_group()
+    os._exit(0)
 
 
 if __name__ == "__main__":
