@@ -16,7 +16,7 @@ def test_sharded_outer_loops_two_gpus():
         pytest.skip("needs two GPUs")
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                         "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tools", "multigpu_check.py")],
-                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+                       capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert p.returncode == 0, (p.stdout[-1500:], p.stderr[-3000:])
     rep = json.loads([ln for ln in p.stdout.splitlines() if ln.startswith("{")][-1])
     assert rep["world"] == 2 and rep["sysid_sharded_vs_single_gpu_rel"] < 1e-12
@@ -30,7 +30,7 @@ def test_single_gpu_graph_iterations():
         pytest.skip("no CUDA device")
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "1", "--master-addr",
                         "127.0.0.1", "--master-port", "29518", os.path.join(ROOT, "tools", "multigpu_check.py")],
-                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+                       capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert p.returncode == 0, (p.stdout[-1500:], p.stderr[-3000:])
     rep = json.loads([ln for ln in p.stdout.splitlines() if ln.startswith("{")][-1])
     assert rep["world"] == 1 and rep["sysid_graph_vs_eager_adam"] < 1e-12 and rep["irl_graph_vs_eager_sharded"] < 1e-6

@@ -76,11 +76,19 @@ def main():
         scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1e3, "us": 1.0, "ns": 1e-3, "s": 1e6}
         return v * scale.get(u, 1.0)
 
-    traffic = {"source": "%s_ncu_summary.csv (ncu --set full --clock-control none, %s)" % (prefix, what)}
-    for r in rows:
-        traffic[r[kcol]] = {"dram_bytes_read": val(r, "dram__bytes_read.sum"), "dram_bytes_write": val(r, "dram__bytes_write.sum"),
-                            "gpu_time_us": val(r, "gpu__time_duration.sum")}
-    json.dump(traffic, open(prefix + "_ncu_traffic.json", "w"), indent=1)
+    # per-config traffic files: argv[4] = "c3:4,c5:2,c4:1,c2:1" says how many consecutive captured launches belong to which
+    # config (the order tools/ncu_case.py runs them in); the first group keeps the plain name bench.py looks up for C3
+    split = sys.argv[4] if len(sys.argv) > 4 else "c3:%d" % len(rows)
+    pos = 0
+    for k, item in enumerate(split.split(",")):
+        cfg, cnt = item.split(":")
+        traffic = {"source": "%s_ncu_summary.csv (ncu --set full --clock-control none, %s), config %s" % (prefix, what, cfg)}
+        for r in rows[pos:pos + int(cnt)]:
+            traffic[r[kcol]] = {"dram_bytes_read": val(r, "dram__bytes_read.sum"), "dram_bytes_write": val(r, "dram__bytes_write.sum"),
+                                "gpu_time_us": val(r, "gpu__time_duration.sum")}
+        pos += int(cnt)
+        name = prefix + ("_ncu_traffic.json" if k == 0 else "_%s_ncu_traffic.json" % cfg)
+        json.dump(traffic, open(name, "w"), indent=1)
     # the few metrics the roofline discussion in DESIGN.md / profiles/README.md quotes, one readable table
     KEY = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
            "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
