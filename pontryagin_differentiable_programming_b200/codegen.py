@@ -207,8 +207,9 @@ class OCModuleSource:
                  chunk: int = 8, warps_per_block: int = 4, min_blocks: int = 1, fwd_warps_per_block: int = 4,
                  fwd_min_blocks: int = 1, keep_fg: bool = True, fast_rcp: bool = False, early_solve: bool = False,
                  fwd_pack: int = 0, fwd_chunk: int = 0, bwd_pack: int = 1, fwd_vec: int = -1, prefetch: int = 2,
-                 prefetch_dist: int = 2, inline_eval: int = -1, h_group: int = 1, prefetch_l1_lead: int = 0):
+                 prefetch_dist: int = 2, inline_eval: int = -1, h_group: int = 1, prefetch_l1_lead: int = 0, rollout_tma: int = 1, tma_chunk: int = 0):
         self.keep_fg = bool(keep_fg)
+        self.rollout_tma, self.tma_chunk = int(rollout_tma), max(0, int(tma_chunk))
         self.prefetch_l1_lead = int(prefetch_l1_lead)
         self.h_group = int(h_group)
         self.inline_eval = int(inline_eval)
@@ -957,6 +958,23 @@ class OCModuleSource:
             "PF": getattr(self, "prefetch", 0), "PFD": max(1, getattr(self, "prefetch_dist", 3)),
             "PFL": max(0, getattr(self, "prefetch_l1_lead", 0)),
         }
+        if getattr(self, "rollout_tma", 0):
+            # thread-private slots of the TMA rollout kernel (doubles): x rows / u rows in (double-buffered), x-or-lambda rows and
+            # dH/du rows out, two mbarriers; +2 per slot for the parity shift and the rounding of a copy to 16 bytes.  The chunk
+            # is the longest whose slots leave room for two warps per SM (<= 110 KB per warp), at most 16 steps.
+            def tma_layout(tc):
+                txs, tus, tls = _even(tc * n + 2), _even(tc * m + 2), _even((tc + 1) * n + 2)
+                tstride = 2 * (txs + tus) + tls + tus + 2
+                while tstride % 4 != 2:          # 2 (mod 4) doubles: the 16 lanes of a half-warp spread over 8 bank pairs
+                    tstride += 2
+                return txs, tus, tls, tstride
+            tc = self.tma_chunk
+            if not tc:
+                tc = 1
+                while tc < 16 and 32 * 8 * tma_layout(tc + 1)[3] <= 110 * 1024:
+                    tc += 1
+            txs, tus, tls, tstride = tma_layout(tc)
+            defs.update({"TC": tc, "TB": 32, "TXS": txs, "TUS": tus, "TLS": tls, "TSTRIDE": tstride})
         header = ["// GENERATED by pontryagin_differentiable_programming_b200/codegen.py -- do not edit",
                   "#include <cuda_runtime.h>", "#include <math.h>", "#include <stdint.h>"]
         header += ["#define PDP_%s %d" % kv for kv in defs.items()]
@@ -1057,7 +1075,11 @@ class OCModuleSource:
 
     def _kernel_text(self):
         bwd = _K_AUX_LQR_BWD2 if getattr(self, "bwd_pack", 1) == 2 else _K_AUX_LQR_BWD
-        return _K_PRELUDE + _K_ROLLOUT_AUXEVAL + _K_AUX_LQR_HEAD + bwd + _K_AUX_LQR_FWD + _K_LAUNCH_COMMON + _K_LAUNCH_LQR
+        tma, launch_common = "", _K_LAUNCH_COMMON
+        if getattr(self, "rollout_tma", 0):
+            from .kernel_templates import K_ROLLOUT_TMA, rollout_tma_launcher
+            tma, launch_common = K_ROLLOUT_TMA, rollout_tma_launcher(_K_LAUNCH_COMMON)
+        return _K_PRELUDE + _K_ROLLOUT_AUXEVAL + tma + _K_AUX_LQR_HEAD + bwd + _K_AUX_LQR_FWD + launch_common + _K_LAUNCH_LQR
 
     def _eval_macros(self):
         el = "tl" if getattr(self, "bwd_pack", 1) == 2 else "lane"       # evaluation lane = time step of the chunk

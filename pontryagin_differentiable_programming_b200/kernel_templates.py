@@ -234,6 +234,290 @@ pdp_k_aux_eval(int B, int H, const double* __restrict__ X, const double* __restr
 
 '''
 
+# ---- open-loop rollout / costate kernel with per-thread TMA (1-D bulk async copies) for all row traffic ------------------
+K_ROLLOUT_TMA = r'''
+// =====================================================================================================
+// Kernel 1t: the open-loop rollout / costate kernel with all row traffic on the TMA engine.
+//   Same thread-per-trajectory arithmetic as pdp_k_rollout_costate.  What changes is how rows move: the rows a thread
+//   needs (u_t forward; x_t, u_t backward) and produces (x_t forward; lambda_{t+1}, dH/du_t backward) for PDP_TC consecutive
+//   time steps are contiguous in HBM, so each thread moves them with ONE 1-D bulk async copy per array and chunk
+//   (cp.async.bulk, completion on a thread-private mbarrier) between HBM and a thread-private shared-memory slot: no
+//   per-lane sector requests in the load-store unit (the limiter of the register-prefetch kernel: 0.8 L1 sector requests
+//   per cycle per SM, long_scoreboard 5.3 of 7.6 stall cycles per issue), no extra instructions on the critical path, loads
+//   one chunk ahead.  Bulk copies need 16-byte aligned addresses and sizes while rows are only 8-byte aligned (n = 13
+//   doubles): a load starts at the aligned address below the chunk (the data then sits 0 or 8 bytes into its slot), a
+//   store sends the aligned middle as a bulk copy and the possible first / last element with plain stores.
+// =====================================================================================================
+__device__ __forceinline__ unsigned pdp_smem_u32(const void* p) {
+#ifdef __CUDACC__
+  return (unsigned)__cvta_generic_to_shared(p);
+#else
+  return 0u;
+#endif
+}
+__device__ __forceinline__ void pdp_mbar_init(double* mbar) {
+#ifdef __CUDACC__
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(pdp_smem_u32(mbar)) : "memory");
+#endif
+}
+__device__ __forceinline__ void pdp_mbar_init_fence() {
+#ifdef __CUDACC__
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdp_mbar_expect(double* mbar, unsigned bytes) {
+#ifdef __CUDACC__
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(pdp_smem_u32(mbar)), "r"(bytes) : "memory");
+#endif
+}
+__device__ __forceinline__ void pdp_mbar_wait(double* mbar, unsigned phase) {
+#ifdef __CUDACC__
+  unsigned done = 0;
+  const unsigned a = pdp_smem_u32(mbar);
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(a), "r"(phase) : "memory");
+  } while (!done);
+#endif
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void pdp_bulk_g2s(double* dst_shared, const void* src, unsigned bytes, double* mbar) {
+#ifdef __CUDACC__
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(pdp_smem_u32(dst_shared)), "l"(src), "r"(bytes), "r"(pdp_smem_u32(mbar)) : "memory");
+#else
+  memcpy(dst_shared, src, bytes);        /* CPU emulation: immediate copy */
+#endif
+}
+__device__ __forceinline__ void pdp_bulk_s2g(void* dst, const double* src_shared, unsigned bytes) {
+#ifdef __CUDACC__
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"(pdp_smem_u32(src_shared)), "r"(bytes) : "memory");
+#else
+  memcpy(dst, src_shared, bytes);
+#endif
+}
+__device__ __forceinline__ void pdp_bulk_store_fence() {     // generic-proxy writes to shared memory -> visible to the bulk store
+#ifdef __CUDACC__
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdp_bulk_commit() {
+#ifdef __CUDACC__
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdp_bulk_wait_read() {       // the committed stores have finished READING shared memory
+#ifdef __CUDACC__
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#endif
+}
+// A planned load of `count` doubles starting at g (8-byte aligned) into a 16-byte aligned slot: the copy starts at the aligned
+// address at or below g, so the data sits `off` (0 or 1) doubles into the slot.  A copy that would read past `end` (the end of
+// the tensor) is shortened by 16 bytes; the one or two doubles it leaves out are fetched with plain loads at issue time.
+struct pdp_tma_plan { const double* src; unsigned bytes; int off, total; };
+__device__ __forceinline__ pdp_tma_plan pdp_tma_plan_load(const double* g, int count, const double* end) {
+  pdp_tma_plan p;
+  p.off = (int)((reinterpret_cast<uintptr_t>(g) >> 3) & 1);
+  p.src = g - p.off;
+  p.total = p.off + count;
+  p.bytes = (unsigned)((p.total * 8 + 15) & ~15);
+  if (p.src + p.bytes / 8 > end) p.bytes -= 16;
+  return p;
+}
+__device__ __forceinline__ void pdp_tma_issue_load(double* slot, const pdp_tma_plan& p, double* mbar) {
+  for (int e = (int)(p.bytes / 8); e < p.total; ++e) slot[e] = p.src[e];       // only at the very end of a tensor
+  if (p.bytes) pdp_bulk_g2s(slot, p.src, p.bytes, mbar);
+}
+// Send `count` doubles that sit in `slot` at offset `off` (= parity of g) to g: aligned middle as one bulk copy, the
+// possible first / last element with plain stores.
+__device__ __forceinline__ void pdp_tma_send(const double* slot, int off, double* g, int count) {
+  int first = 0;
+  if (off) { g[0] = slot[off]; first = 1; }
+  const int mid = (count - first) & ~1;
+  if (mid > 0) pdp_bulk_s2g(g + first, slot + off + first, (unsigned)mid * 8);
+  if (first + mid < count) g[count - 1] = slot[off + count - 1];
+}
+
+extern "C" __global__ void __launch_bounds__(PDP_TB)
+pdp_k_rollout_costate_tma(int B, int H, const double* __restrict__ x0, const double* __restrict__ theta, int theta_stride,
+                          const double* __restrict__ U, double* __restrict__ X, double* __restrict__ Lam,
+                          double* __restrict__ cost, double* __restrict__ dHu, int* __restrict__ status)
+{
+  extern __shared__ __align__(16) double pdp_smem[];
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;                                   // no block-level synchronisation anywhere: every thread is on its own
+  // thread-private slots (PDP_TSTRIDE doubles apart): 2 x [x rows | u rows] in (the next chunk streams in while this one is
+  // computed), [x / lambda rows] and [dH/du rows] out (double-buffering these as well measured no different), 2 mbarriers
+  double* my = pdp_smem + (size_t)threadIdx.x * PDP_TSTRIDE;
+  auto XS = [&](int k) { return my + k * (PDP_TXS + PDP_TUS); };
+  auto US = [&](int k) { return my + k * (PDP_TXS + PDP_TUS) + PDP_TXS; };
+  double* LS = my + 2 * (PDP_TXS + PDP_TUS);
+  double* GS = LS + PDP_TLS;
+  double* MB = GS + PDP_TUS;                            // two 8-byte mbarriers
+  pdp_mbar_init(MB);
+  pdp_mbar_init(MB + 1);
+  pdp_mbar_init_fence();
+  unsigned phase0 = 0, phase1 = 0;
+  double x[PDP_N], xn[PDP_N], th[PDP_NTHX], u[PDP_M], tmp[1];
+  #pragma unroll
+  for (int i = 0; i < PDP_NTH; ++i) th[i] = theta[(size_t)b * theta_stride + i];
+#if PDP_NRCP > 0
+  pdp_f_recips(th, th + PDP_NTH);
+#endif
+  #pragma unroll
+  for (int i = 0; i < PDP_N; ++i) x[i] = x0[(size_t)b * PDP_N + i];
+  double J = 0.0;
+  double* Xb = X + (size_t)b * (H + 1) * PDP_N;
+  const double* Ub = U + (size_t)b * H * PDP_M;
+  const double* Uend = U + (size_t)B * H * PDP_M;
+  const double* Xend = X + (size_t)B * (H + 1) * PDP_N;
+  // ---------------------------------------------------------------- forward: rollout and cost
+  int offu0 = 0, offu1 = 0, offx0 = 0, offx1 = 0;
+  {
+    const pdp_tma_plan pu = pdp_tma_plan_load(Ub, (H < PDP_TC ? H : PDP_TC) * PDP_M, Uend);
+    pdp_mbar_expect(MB, pu.bytes);
+    pdp_tma_issue_load(US(0), pu, MB);
+    offu0 = pu.off;
+  }
+  int buf = 0;
+  #pragma unroll 1
+  for (int t0 = 0; t0 < H; t0 += PDP_TC, buf ^= 1) {
+    const int nst = H - t0 < PDP_TC ? H - t0 : PDP_TC;
+    if (t0 + PDP_TC < H) {                               // next chunk's controls into the other slot
+      const int nn = H - t0 - PDP_TC < PDP_TC ? H - t0 - PDP_TC : PDP_TC;
+      const pdp_tma_plan pu = pdp_tma_plan_load(Ub + (size_t)(t0 + PDP_TC) * PDP_M, nn * PDP_M, Uend);
+      pdp_mbar_expect(MB + (buf ^ 1), pu.bytes);
+      pdp_tma_issue_load(US(buf ^ 1), pu, MB + (buf ^ 1));
+      if (buf) offu0 = pu.off; else offu1 = pu.off;
+    }
+    if (buf == 0) { pdp_mbar_wait(MB, phase0); phase0 ^= 1; } else { pdp_mbar_wait(MB + 1, phase1); phase1 ^= 1; }
+    pdp_bulk_wait_read();                                // the previous chunk's stores have left the output slot
+    const double* us = US(buf) + (buf ? offu1 : offu0);
+    double* Xg = Xb + (size_t)t0 * PDP_N;
+    const int offl = (int)((reinterpret_cast<uintptr_t>(Xg) >> 3) & 1);
+    double* ls = LS + offl;
+    #pragma unroll 1
+    for (int s = 0; s < nst; ++s) {
+      #pragma unroll
+      for (int i = 0; i < PDP_M; ++i) u[i] = us[s * PDP_M + i];
+      #pragma unroll
+      for (int i = 0; i < PDP_N; ++i) ls[s * PDP_N + i] = x[i];
+      pdp_f_path_cost(x, u, th, tmp);
+      J += tmp[0];
+      pdp_f_dyn(x, u, th, xn);
+      #pragma unroll
+      for (int i = 0; i < PDP_N; ++i) x[i] = xn[i];
+    }
+    const bool last = t0 + PDP_TC >= H;
+    if (last) {                                          // x_H rides with the last chunk (rows are contiguous in X)
+      #pragma unroll
+      for (int i = 0; i < PDP_N; ++i) ls[nst * PDP_N + i] = x[i];
+    }
+    pdp_bulk_store_fence();
+    pdp_tma_send(LS, offl, Xg, (nst + (last ? 1 : 0)) * PDP_N);
+    pdp_bulk_commit();
+  }
+  pdp_f_final_cost(x, th, tmp);
+  J += tmp[0];
+  if (cost) cost[b] = J;
+  const bool bad = !isfinite(J);
+  if (Lam != nullptr) {
+    // ---------------------------------------------------------------- backward: costates (and dH/du)
+    double lam[PDP_N], ln[PDP_N], gu[PDP_M];
+    double* Lb = Lam + (size_t)b * H * PDP_N;
+    pdp_f_dhx(x, th, lam);
+    // the X rows written above are read back by this thread's own bulk loads: wait until the stores have completed
+#ifdef __CUDACC__
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    asm volatile("fence.proxy.async;" ::: "memory");      // the first / last elements went out as plain stores (generic proxy)
+#endif
+    const int tlast = ((H - 1) / PDP_TC) * PDP_TC;
+    buf = 0;
+    // which mbarrier phase each slot is in after the forward pass is tracked in phase0 / phase1; slot 0 is used first again
+    {
+      const int nn = H - tlast;
+      const pdp_tma_plan px = pdp_tma_plan_load(Xb + (size_t)tlast * PDP_N, nn * PDP_N, Xend);
+      const pdp_tma_plan pu = pdp_tma_plan_load(Ub + (size_t)tlast * PDP_M, nn * PDP_M, Uend);
+      pdp_mbar_expect(MB, px.bytes + pu.bytes);
+      pdp_tma_issue_load(XS(0), px, MB);
+      pdp_tma_issue_load(US(0), pu, MB);
+      offx0 = px.off; offu0 = pu.off;
+    }
+    #pragma unroll 1
+    for (int tc = tlast; tc >= 0; tc -= PDP_TC, buf ^= 1) {
+      const int nst = H - tc < PDP_TC ? H - tc : PDP_TC;
+      if (tc > 0) {
+        const pdp_tma_plan px = pdp_tma_plan_load(Xb + (size_t)(tc - PDP_TC) * PDP_N, PDP_TC * PDP_N, Xend);
+        const pdp_tma_plan pu = pdp_tma_plan_load(Ub + (size_t)(tc - PDP_TC) * PDP_M, PDP_TC * PDP_M, Uend);
+        pdp_mbar_expect(MB + (buf ^ 1), px.bytes + pu.bytes);
+        pdp_tma_issue_load(XS(buf ^ 1), px, MB + (buf ^ 1));
+        pdp_tma_issue_load(US(buf ^ 1), pu, MB + (buf ^ 1));
+        if (buf) { offx0 = px.off; offu0 = pu.off; } else { offx1 = px.off; offu1 = pu.off; }
+      }
+      if (buf == 0) { pdp_mbar_wait(MB, phase0); phase0 ^= 1; } else { pdp_mbar_wait(MB + 1, phase1); phase1 ^= 1; }
+      pdp_bulk_wait_read();
+      const double* xs = XS(buf) + (buf ? offx1 : offx0);
+      const double* us = US(buf) + (buf ? offu1 : offu0);
+      double* Lg = Lb + (size_t)tc * PDP_N;
+      double* Gg = dHu ? dHu + ((size_t)b * H + tc) * PDP_M : nullptr;
+      const int offl = (int)((reinterpret_cast<uintptr_t>(Lg) >> 3) & 1);
+      const int offg = (int)((reinterpret_cast<uintptr_t>(Gg) >> 3) & 1);
+      double* ls = LS + offl;
+      double* gs = GS + offg;
+      #pragma unroll 1
+      for (int s = nst - 1; s >= 0; --s) {
+        #pragma unroll
+        for (int i = 0; i < PDP_N; ++i) { ls[s * PDP_N + i] = lam[i]; x[i] = xs[s * PDP_N + i]; }
+        #pragma unroll
+        for (int i = 0; i < PDP_M; ++i) u[i] = us[s * PDP_M + i];
+        if (dHu != nullptr) {
+          pdp_f_dHu(x, u, lam, th, gu);
+          #pragma unroll
+          for (int i = 0; i < PDP_M; ++i) gs[s * PDP_M + i] = gu[i];
+        }
+        if (tc + s > 0) {
+          pdp_f_dHx(x, u, lam, th, ln);
+          #pragma unroll
+          for (int i = 0; i < PDP_N; ++i) lam[i] = ln[i];
+        }
+      }
+      pdp_bulk_store_fence();
+      pdp_tma_send(LS, offl, Lg, nst * PDP_N);
+      if (dHu != nullptr) pdp_tma_send(GS, offg, Gg, nst * PDP_M);
+      pdp_bulk_commit();
+    }
+  }
+#ifdef __CUDACC__
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // shared memory must outlive the stores that read it
+#endif
+  if (status && bad) atomicOr(&status[b], 1);
+}
+'''
+
+K_LAUNCH_ROLLOUT_TMA_BRANCH = r'''  // Open-loop rollouts of SMALL batches go to the TMA kernel: per-lane bulk copies are bound by the TMA engine's operation rate
+  // (~1 op / 40 cycles / SM measured), so they only pay with long chunks, and a long chunk's slots allow two warps per SM --
+  // enough for batches of up to 2 x 32 x #SM trajectories (C4: 8 192 per GPU, 0.187 -> 0.151 ms); larger batches (C3: 16 384)
+  // stay on the register-prefetch kernel (0.100 vs 0.139 ms).
+  int pdp_dev = 0, pdp_sms = 0;
+  cudaGetDevice(&pdp_dev);
+  cudaDeviceGetAttribute(&pdp_sms, cudaDevAttrMultiProcessorCount, pdp_dev);
+  if (fb_gains == nullptr && (B + PDP_TB - 1) / PDP_TB <= 2 * pdp_sms) {
+    const size_t smem_t = (size_t)PDP_TB * PDP_TSTRIDE * sizeof(double);
+    cudaError_t et = pdp_opt_in_smem((const void*)pdp_k_rollout_costate_tma, smem_t);
+    if (et != cudaSuccess) return (int)et;
+    pdp_k_rollout_costate_tma<<<(B + PDP_TB - 1) / PDP_TB, PDP_TB, smem_t, st>>>(B, H, x0, theta, theta_stride, U, X, Lam, cost, dHu, status);
+    return (int)cudaGetLastError();
+  }
+'''
+
+
+def rollout_tma_launcher(launch_common_text):
+    old = "  pdp_k_rollout_costate<<<(B + 127) / 128, 128, 0, st>>>("
+    assert launch_common_text.count(old) == 1
+    return launch_common_text.replace(old, K_LAUNCH_ROLLOUT_TMA_BRANCH + old)
+
+
 K_AUX_LQR = r'''
 // =====================================================================================================
 // Kernels 3a/3b: fused getAuxSys + LQR.lqrSolver (PDP.py:272-314 + 446-615), ONE WARP PER TRAJECTORY.

@@ -52,7 +52,7 @@ def test_b200_arm_json_contract():
     assert x["matches_device_path"] is True and x["d2h_bytes_per_step"] > 1024 * 51 * 13 * 9 * 8
 
 
-@pytest.mark.parametrize("cfg,launches,kernel", [("c5", 2, "pdp_k_sens_fwd"), ("c4", 1, "pdp_k_rollout_costate"),
+@pytest.mark.parametrize("cfg,launches,kernel", [("c5", 2, "pdp_k_sens_fwd"), ("c4", 1, "pdp_k_rollout_costate_tma"),
                                                  ("c2", 1, "pdp_k_sens_fwd")])
 def test_secondary_config_arms_json_contract(cfg, launches, kernel):
     """bench.py --config c2|c4|c5: the same contract line for the other BASELINE configs (H = 100 for C4 / C5)."""

@@ -29,7 +29,8 @@ def _variant(base, **kw):
     cfg = dict(chunk=base.chunk, warps_per_block=base.wpb, min_blocks=base.min_blocks, fwd_warps_per_block=base.wpbf,
                fwd_min_blocks=base.min_blocks_f, keep_fg=base.keep_fg, fast_rcp=base.fast_rcp,
                early_solve=base.early_solve, fwd_pack=base.fwd_pack, fwd_chunk=base.fwd_chunk, bwd_pack=base.bwd_pack)
-    cfg.update(fwd_vec=base.fwd_vec, prefetch=base.prefetch, prefetch_dist=base.prefetch_dist, h_group=base.h_group)
+    cfg.update(fwd_vec=base.fwd_vec, prefetch=base.prefetch, prefetch_dist=base.prefetch_dist, h_group=base.h_group,
+               rollout_tma=base.rollout_tma, tma_chunk=base.tma_chunk)
     cfg.update(kw)
     return codegen.OCModuleSource(base.x, base.u, base.th, base.dyn, base.c, base.h, **cfg)
 
@@ -329,3 +330,29 @@ def test_emulator_detects_a_missing_barrier():
     assert np.array_equal(good, again)                       # the intact kernel is deterministic
     bad, _ = warp_emu.Emulator(broken).backward(X, U, L, th)
     assert not np.allclose(np.nan_to_num(bad), good, rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("env,B,H,chunk", [("quadrotor", 37, 9, 3), ("quadrotor", 3, 1, 3), ("rocket", 5, 7, 4), ("pendulum", 34, 21, 2),
+                                           ("cartpole", 3, 8, 8)])
+def test_emulated_tma_rollout_kernel_equals_the_register_prefetch_kernel(env, B, H, chunk):
+    """pdp_k_rollout_costate_tma (the open-loop kernel for small batches: rows moved by thread-private 1-D bulk copies; in the emulator a bulk
+    copy is an immediate memcpy, so this checks slot layout, the 0 / 8-byte parity shifts of loads and stores -- rows of
+    13 / 3 / 1 doubles --, the head / tail elements of the stores, chunk tails and the end-of-tensor guard): bit-identical
+    to the register-prefetch kernel, with and without dH/du."""
+    from pontryagin_differentiable_programming_b200 import systems
+    base = systems.OC_BUILDERS[env](0.1).src
+    src = _variant(base, rollout_tma=1, tma_chunk=chunk)
+    assert "pdp_k_rollout_costate_tma" in src.source() and "#define PDP_TC %d\n" % chunk in src.source()
+    assert "pdp_k_rollout_costate_tma" not in _variant(base, rollout_tma=0).source()
+    rng = np.random.default_rng(6)
+    x0 = 0.3 * rng.standard_normal((B, src.n))
+    if env in ("quadrotor", "rocket"):
+        x0[:, 6] += 1.0
+    theta = 1.0 + 0.2 * rng.uniform(-1, 1, (B, src.r))
+    U = 0.5 * rng.standard_normal((B, H, src.m)) + (2.5 if env == "quadrotor" else 0.0)
+    emu = warp_emu.Emulator(src)
+    for want in (True, False):
+        ref = emu.rollout(x0, theta, U, want_dHu=want)
+        got = emu.rollout(x0, theta, U, want_dHu=want, tma=True)
+        for a, b_ in zip(ref, got):
+            assert (a is None and b_ is None) or np.array_equal(a, b_)

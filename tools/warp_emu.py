@@ -135,6 +135,17 @@ extern "C" void emu_rollout(int B, int H, const double* x0, const double* theta,
   }
 }
 #endif
+#ifdef PDP_TSTRIDE
+// TMA rollout kernel: thread-private shared slots, no inter-thread synchronisation -> the threads run one after the other
+// (bulk copies are immediate memcpy's, mbarriers / fences are no-ops)
+extern "C" void emu_rollout_tma(int B, int H, const double* x0, const double* theta, int theta_stride, const double* U,
+                                double* X, double* Lam, double* cost, double* dHu, int* status) {
+  for (int b = 0; b < B; ++b) {
+    threadIdx.x = b % PDP_TB; blockIdx.x = b / PDP_TB; blockDim.x = PDP_TB;
+    pdp_k_rollout_costate_tma(B, H, x0, theta, theta_stride, U, X, Lam, cost, dHu, status);
+  }
+}
+#endif
 '''
 
 _RCP = re.compile(r'asm\("rcp\.approx\.ftz\.f64 %0, %1;" : "=d"\((\w+)\) : "d"\((\w+)\)\);')
@@ -187,7 +198,7 @@ class Emulator:
     def _p(a):
         return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
-    def rollout(self, x0, theta, U, want_dHu=False, feedback=None):
+    def rollout(self, x0, theta, U, want_dHu=False, feedback=None, tma=False):
         """pdp_k_rollout_costate -> X, Lam, cost[, dHu].  ``feedback`` = dict(gains[Bs,H,(n+1)*m], X[Bs,H+1,n], alpha[B],
         group): closed-loop mode (B = group * Bs candidates); then the applied controls are returned as a fifth item."""
         x0, U = (np.ascontiguousarray(a, dtype=np.float64) for a in (x0, U))
@@ -205,6 +216,10 @@ class Emulator:
         if feedback:
             fg, fx, fa = (np.ascontiguousarray(feedback[k], dtype=np.float64) for k in ("gains", "X", "alpha"))
             Uout = np.full((B, H, self.m), np.nan)
+        if tma:      # modules generated with rollout_tma=1: the open-loop kernel with bulk-copy row traffic
+            self.lib.emu_rollout_tma(B, H, self._p(x0), self._p(theta), ts, self._p(U), self._p(X), self._p(Lam), self._p(cost),
+                                     self._p(dHu), self._p(status))
+            return X, Lam, cost, dHu
         self.lib.emu_rollout(B, H, self._p(x0), self._p(theta), ts, self._p(U), self._p(X), self._p(Lam), self._p(cost),
                              self._p(dHu), self._p(status), self._p(fg), self._p(fx), self._p(fa), self._p(Uout), group)
         return (X, Lam, cost, dHu, Uout) if feedback else (X, Lam, cost, dHu)
