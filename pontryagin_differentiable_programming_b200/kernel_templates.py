@@ -55,6 +55,101 @@ __device__ __forceinline__ void pdp_row_load(double* x, const double* g) {
 
 '''
 
+K_TMA_PRIMS = r'''
+// ---- TMA (1-D bulk async copy) and mbarrier primitives; in the CPU emulator a bulk copy is an immediate memcpy ----------
+__device__ __forceinline__ unsigned pdp_smem_u32(const void* p) {
+#ifdef __CUDACC__
+  return (unsigned)__cvta_generic_to_shared(p);
+#else
+  return 0u;
+#endif
+}
+__device__ __forceinline__ void pdp_mbar_init(double* mbar) {
+#ifdef __CUDACC__
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(pdp_smem_u32(mbar)) : "memory");
+#endif
+}
+__device__ __forceinline__ void pdp_mbar_init_fence() {
+#ifdef __CUDACC__
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdp_mbar_expect(double* mbar, unsigned bytes) {
+#ifdef __CUDACC__
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(pdp_smem_u32(mbar)), "r"(bytes) : "memory");
+#endif
+}
+__device__ __forceinline__ void pdp_mbar_wait(double* mbar, unsigned phase) {
+#ifdef __CUDACC__
+  unsigned done = 0;
+  const unsigned a = pdp_smem_u32(mbar);
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(a), "r"(phase) : "memory");
+  } while (!done);
+#endif
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void pdp_bulk_g2s(double* dst_shared, const void* src, unsigned bytes, double* mbar) {
+#ifdef __CUDACC__
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(pdp_smem_u32(dst_shared)), "l"(src), "r"(bytes), "r"(pdp_smem_u32(mbar)) : "memory");
+#else
+  memcpy(dst_shared, src, bytes);        /* CPU emulation: immediate copy */
+#endif
+}
+__device__ __forceinline__ void pdp_bulk_s2g(void* dst, const double* src_shared, unsigned bytes) {
+#ifdef __CUDACC__
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"(pdp_smem_u32(src_shared)), "r"(bytes) : "memory");
+#else
+  memcpy(dst, src_shared, bytes);
+#endif
+}
+__device__ __forceinline__ void pdp_bulk_store_fence() {     // generic-proxy writes to shared memory -> visible to the bulk store
+#ifdef __CUDACC__
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdp_bulk_commit() {
+#ifdef __CUDACC__
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdp_bulk_wait_read() {       // the committed stores have finished READING shared memory
+#ifdef __CUDACC__
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#endif
+}
+// A planned load of `count` doubles starting at g (8-byte aligned) into a 16-byte aligned slot: the copy starts at the aligned
+// address at or below g, so the data sits `off` (0 or 1) doubles into the slot.  A copy that would read past `end` (the end of
+// the tensor) is shortened by 16 bytes; the one or two doubles it leaves out are fetched with plain loads at issue time.
+struct pdp_tma_plan { const double* src; unsigned bytes; int off, total; };
+__device__ __forceinline__ pdp_tma_plan pdp_tma_plan_load(const double* g, int count, const double* end) {
+  pdp_tma_plan p;
+  p.off = (int)((reinterpret_cast<uintptr_t>(g) >> 3) & 1);
+  p.src = g - p.off;
+  p.total = p.off + count;
+  p.bytes = (unsigned)((p.total * 8 + 15) & ~15);
+  if (p.src + p.bytes / 8 > end) p.bytes -= 16;
+  return p;
+}
+__device__ __forceinline__ void pdp_tma_issue_load(double* slot, const pdp_tma_plan& p, double* mbar) {
+  for (int e = (int)(p.bytes / 8); e < p.total; ++e) slot[e] = p.src[e];       // only at the very end of a tensor
+  if (p.bytes) pdp_bulk_g2s(slot, p.src, p.bytes, mbar);
+}
+// Send `count` doubles that sit in `slot` at offset `off` (= parity of g) to g: aligned middle as one bulk copy, the
+// possible first / last element with plain stores.
+__device__ __forceinline__ void pdp_tma_send(const double* slot, int off, double* g, int count) {
+  int first = 0;
+  if (off) { g[0] = slot[off]; first = 1; }
+  const int mid = (count - first) & ~1;
+  if (mid > 0) pdp_bulk_s2g(g + first, slot + off + first, (unsigned)mid * 8);
+  if (first + mid < count) g[count - 1] = slot[off + count - 1];
+}
+
+'''
+
 K_ROLLOUT_AUXEVAL = r'''
 // =====================================================================================================
 // Kernel 1: forward rollout + cost + costate recursion (+ optional dH/du), one thread per trajectory.
@@ -248,97 +343,6 @@ K_ROLLOUT_TMA = r'''
 //   doubles): a load starts at the aligned address below the chunk (the data then sits 0 or 8 bytes into its slot), a
 //   store sends the aligned middle as a bulk copy and the possible first / last element with plain stores.
 // =====================================================================================================
-__device__ __forceinline__ unsigned pdp_smem_u32(const void* p) {
-#ifdef __CUDACC__
-  return (unsigned)__cvta_generic_to_shared(p);
-#else
-  return 0u;
-#endif
-}
-__device__ __forceinline__ void pdp_mbar_init(double* mbar) {
-#ifdef __CUDACC__
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(pdp_smem_u32(mbar)) : "memory");
-#endif
-}
-__device__ __forceinline__ void pdp_mbar_init_fence() {
-#ifdef __CUDACC__
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#endif
-}
-__device__ __forceinline__ void pdp_mbar_expect(double* mbar, unsigned bytes) {
-#ifdef __CUDACC__
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(pdp_smem_u32(mbar)), "r"(bytes) : "memory");
-#endif
-}
-__device__ __forceinline__ void pdp_mbar_wait(double* mbar, unsigned phase) {
-#ifdef __CUDACC__
-  unsigned done = 0;
-  const unsigned a = pdp_smem_u32(mbar);
-  do {
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                 : "=r"(done) : "r"(a), "r"(phase) : "memory");
-  } while (!done);
-#endif
-}
-// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned
-__device__ __forceinline__ void pdp_bulk_g2s(double* dst_shared, const void* src, unsigned bytes, double* mbar) {
-#ifdef __CUDACC__
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               :: "r"(pdp_smem_u32(dst_shared)), "l"(src), "r"(bytes), "r"(pdp_smem_u32(mbar)) : "memory");
-#else
-  memcpy(dst_shared, src, bytes);        /* CPU emulation: immediate copy */
-#endif
-}
-__device__ __forceinline__ void pdp_bulk_s2g(void* dst, const double* src_shared, unsigned bytes) {
-#ifdef __CUDACC__
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"(pdp_smem_u32(src_shared)), "r"(bytes) : "memory");
-#else
-  memcpy(dst, src_shared, bytes);
-#endif
-}
-__device__ __forceinline__ void pdp_bulk_store_fence() {     // generic-proxy writes to shared memory -> visible to the bulk store
-#ifdef __CUDACC__
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#endif
-}
-__device__ __forceinline__ void pdp_bulk_commit() {
-#ifdef __CUDACC__
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-#endif
-}
-__device__ __forceinline__ void pdp_bulk_wait_read() {       // the committed stores have finished READING shared memory
-#ifdef __CUDACC__
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-#endif
-}
-// A planned load of `count` doubles starting at g (8-byte aligned) into a 16-byte aligned slot: the copy starts at the aligned
-// address at or below g, so the data sits `off` (0 or 1) doubles into the slot.  A copy that would read past `end` (the end of
-// the tensor) is shortened by 16 bytes; the one or two doubles it leaves out are fetched with plain loads at issue time.
-struct pdp_tma_plan { const double* src; unsigned bytes; int off, total; };
-__device__ __forceinline__ pdp_tma_plan pdp_tma_plan_load(const double* g, int count, const double* end) {
-  pdp_tma_plan p;
-  p.off = (int)((reinterpret_cast<uintptr_t>(g) >> 3) & 1);
-  p.src = g - p.off;
-  p.total = p.off + count;
-  p.bytes = (unsigned)((p.total * 8 + 15) & ~15);
-  if (p.src + p.bytes / 8 > end) p.bytes -= 16;
-  return p;
-}
-__device__ __forceinline__ void pdp_tma_issue_load(double* slot, const pdp_tma_plan& p, double* mbar) {
-  for (int e = (int)(p.bytes / 8); e < p.total; ++e) slot[e] = p.src[e];       // only at the very end of a tensor
-  if (p.bytes) pdp_bulk_g2s(slot, p.src, p.bytes, mbar);
-}
-// Send `count` doubles that sit in `slot` at offset `off` (= parity of g) to g: aligned middle as one bulk copy, the
-// possible first / last element with plain stores.
-__device__ __forceinline__ void pdp_tma_send(const double* slot, int off, double* g, int count) {
-  int first = 0;
-  if (off) { g[0] = slot[off]; first = 1; }
-  const int mid = (count - first) & ~1;
-  if (mid > 0) pdp_bulk_s2g(g + first, slot + off + first, (unsigned)mid * 8);
-  if (first + mid < count) g[count - 1] = slot[off + count - 1];
-}
-
 extern "C" __global__ void __launch_bounds__(PDP_TB)
 pdp_k_rollout_costate_tma(int B, int H, const double* __restrict__ x0, const double* __restrict__ theta, int theta_stride,
                           const double* __restrict__ U, double* __restrict__ X, double* __restrict__ Lam,
@@ -647,6 +651,51 @@ pdp_k_aux_lqr_fwd(int B, int H, const double* __restrict__ X, const double* __re
 @@X0STORE@@
   }
   const bool fused = (loss_dp != nullptr) && (Xref != nullptr);
+#if PDP_FTMA
+  // The rows the chunk evaluation needs (x_t, u_t and, for the fused loss, xref_t, uref_t of PDP_CHF steps) are contiguous
+  // per trajectory: lane 0 brings them in with one bulk async copy per array and trajectory, ONE CHUNK AHEAD (issued right
+  // after the previous evaluation has consumed the slots), completion on the warp's mbarrier -- the evaluation's loads were
+  // this kernel's long-scoreboard stalls (16 % of its samples).  Slots: [x | u | xref | uref] at PDP_FOFF_IN of each
+  // trajectory's region; a chunk that starts 8 bytes off a 16-byte boundary sits one double into its slot.
+  double* FMB = wbase + PDP_FG * PDP_FTS;
+  unsigned fphase = 0;
+  if (lane == 0) pdp_mbar_init(FMB);
+  pdp_mbar_init_fence();
+  __syncwarp();
+  auto f_issue = [&](const int tcn) {
+    const int nn = H - tcn < PDP_CHF ? H - tcn : PDP_CHF;
+    pdp_tma_plan pl[PDP_FG * 4];
+    unsigned tx = 0;
+    #pragma unroll
+    for (int gq = 0; gq < PDP_FG; ++gq) {
+      const size_t bb = (size_t)((b0 + gq < B) ? b0 + gq : B - 1);
+      pl[4 * gq + 0] = pdp_tma_plan_load(X + (bb * (H + 1) + tcn) * PDP_N, nn * PDP_N, X + (size_t)B * (H + 1) * PDP_N);
+      pl[4 * gq + 1] = pdp_tma_plan_load(U + (bb * H + tcn) * PDP_M, nn * PDP_M, U + (size_t)B * H * PDP_M);
+      tx += pl[4 * gq].bytes + pl[4 * gq + 1].bytes;
+      if (fused) {
+        pl[4 * gq + 2] = pdp_tma_plan_load(Xref + (bb * (H + 1) + tcn) * PDP_N, nn * PDP_N, Xref + (size_t)B * (H + 1) * PDP_N);
+        tx += pl[4 * gq + 2].bytes;
+        if (Uref) {
+          pl[4 * gq + 3] = pdp_tma_plan_load(Uref + (bb * H + tcn) * PDP_M, nn * PDP_M, Uref + (size_t)B * H * PDP_M);
+          tx += pl[4 * gq + 3].bytes;
+        }
+      }
+    }
+    pdp_mbar_expect(FMB, tx);
+    #pragma unroll
+    for (int gq = 0; gq < PDP_FG; ++gq) {
+      double* fin = wbase + gq * PDP_FTS + PDP_FOFF_IN;
+      pdp_tma_issue_load(fin, pl[4 * gq + 0], FMB);
+      pdp_tma_issue_load(fin + PDP_FXS, pl[4 * gq + 1], FMB);
+      if (fused) {
+        pdp_tma_issue_load(fin + PDP_FXS + PDP_FUS, pl[4 * gq + 2], FMB);
+        if (Uref) pdp_tma_issue_load(fin + 2 * PDP_FXS + PDP_FUS, pl[4 * gq + 3], FMB);
+      }
+    }
+  };
+  if (lane == 0) f_issue(0);
+  __syncwarp();       // (only the CPU emulator needs it: there the copy is lane 0's memcpy, and mbarrier waits are no-ops)
+#endif
   double dpacc = 0.0, lossacc = 0.0;
   double lacc[PDP_FG];
   #pragma unroll
@@ -663,6 +712,10 @@ pdp_k_aux_lqr_fwd(int B, int H, const double* __restrict__ X, const double* __re
   for (int tc = 0; tc < H; tc += PDP_CHF) {
     const int nst = (tc + PDP_CHF < H ? PDP_CHF : H - tc);
     (void)nst;
+#if PDP_FTMA
+    pdp_mbar_wait(FMB, fphase);          // this chunk's rows were requested one chunk ago
+    fphase ^= 1;
+#endif
 @@EVAL_DYN_COOP@@
     {
       const int te = tc + se;
@@ -670,11 +723,27 @@ pdp_k_aux_lqr_fwd(int B, int H, const double* __restrict__ X, const double* __re
         double* eo = ereg + se * PDP_FLD;
         const double* the = ereg + PDP_FOFF_TH;
         (void)the; (void)eo;
+#if PDP_FTMA
+        // staged rows of step te: the chunk of trajectory `be` starts at row tc of its arrays
+        const double* fin = ereg + PDP_FOFF_IN;
+        const double* fin_x = fin + ((reinterpret_cast<uintptr_t>(X + ((size_t)be * (H + 1) + tc) * PDP_N) >> 3) & 1) + se * PDP_N;
+        const double* fin_u = fin + PDP_FXS + ((reinterpret_cast<uintptr_t>(U + ((size_t)be * H + tc) * PDP_M) >> 3) & 1) + se * PDP_M;
+        (void)fin_x; (void)fin_u;
+#endif
 @@EVAL_DYN@@
         if (fused) {
           // loss / chain rule of the IRL scripts (reference Examples/IRL/quadrotor/uav_PDP.py:67-75), per evaluation lane
+#if PDP_FTMA
+          const double* xe = fin_x;
+          const double* xr = fin + PDP_FXS + PDP_FUS + ((reinterpret_cast<uintptr_t>(Xref + ((size_t)be * (H + 1) + tc) * PDP_N) >> 3) & 1) + se * PDP_N;
+          const double* ue = fin_u;
+          const double* ur = Uref ? fin + 2 * PDP_FXS + PDP_FUS + ((reinterpret_cast<uintptr_t>(Uref + ((size_t)be * H + tc) * PDP_M) >> 3) & 1) + se * PDP_M : fin_u;
+#else
           const double* xe = X + ((size_t)be * (H + 1) + te) * PDP_N;
           const double* xr = Xref + ((size_t)be * (H + 1) + te) * PDP_N;
+          const double* ue = U + ((size_t)be * H + te) * PDP_M;
+          const double* ur = Uref ? Uref + ((size_t)be * H + te) * PDP_M : ue;
+#endif
           #pragma unroll
           for (int i = 0; i < PDP_N; ++i) {
             const double d = xe[i] - xr[i];
@@ -682,14 +751,19 @@ pdp_k_aux_lqr_fwd(int B, int H, const double* __restrict__ X, const double* __re
           }
           #pragma unroll
           for (int i = 0; i < PDP_M; ++i) {
-            const double d = Uref ? U[((size_t)be * H + te) * PDP_M + i] - Uref[((size_t)be * H + te) * PDP_M + i] : 0.0;
+            const double d = Uref ? ue[i] - ur[i] : 0.0;
             ereg[PDP_FOFF_DU + se * PDP_M + i] = d; lossacc = fma(d, d, lossacc);
           }
         }
       }
     }
+#if !PDP_FTMA
 @@PREFETCH_DYN_CHUNK@@
+#endif
     __syncwarp();
+#if PDP_FTMA
+    if (lane == 0 && tc + PDP_CHF < H) f_issue(tc + PDP_CHF);     // every lane has consumed the slots: refill them for the next chunk
+#endif
     const int tend = tc + PDP_CHF < H ? tc + PDP_CHF : H;
     #pragma unroll 1
     for (int t = tc; t < tend; ++t) {
