@@ -207,10 +207,9 @@ class OCModuleSource:
                  chunk: int = 8, warps_per_block: int = 4, min_blocks: int = 1, fwd_warps_per_block: int = 4,
                  fwd_min_blocks: int = 1, keep_fg: bool = True, fast_rcp: bool = False, early_solve: bool = False,
                  fwd_pack: int = 0, fwd_chunk: int = 0, bwd_pack: int = 1, fwd_vec: int = -1, prefetch: int = 2,
-                 prefetch_dist: int = 2, inline_eval: int = -1, h_group: int = 1, prefetch_l1_lead: int = 0, rollout_tma: int = 1, tma_chunk: int = 0, fwd_tma: int = 1):
+                 prefetch_dist: int = 2, inline_eval: int = -1, h_group: int = 1, prefetch_l1_lead: int = 0, rollout_tma: int = 1, tma_chunk: int = 0):
         self.keep_fg = bool(keep_fg)
         self.rollout_tma, self.tma_chunk = int(rollout_tma), max(0, int(tma_chunk))
-        self.fwd_tma = int(fwd_tma)
         self.prefetch_l1_lead = int(prefetch_l1_lead)
         self.h_group = int(h_group)
         self.inline_eval = int(inline_eval)
@@ -252,8 +251,6 @@ class OCModuleSource:
         self.ns = self.n + self.m + self.r
         if self.bwd_pack == 2 and not (self.n <= 16 and self.m + self.r <= 16):
             self.bwd_pack = 1          # the two-rows-per-lane layout needs n <= 16 and m + r <= 16
-        if type(self)._eval_macros is not OCModuleSource._eval_macros:
-            self.fwd_tma = 0                      # only modules that evaluate their own slots stage chunk rows
         if self.bwd_pack == 2:
             self.chunk = min(self.chunk, 16)
         elif self.ns > WARP:
@@ -829,7 +826,7 @@ class OCModuleSource:
         fg = max(1, min(fg, WARP // gs, WARP))
         ch = getattr(self, "fwd_chunk", 0)
         if not ch:
-            per_step = _pad_ld(self.nvar_s) + self.n + self.m + (2 * (self.n + self.m) if getattr(self, "fwd_tma", 0) else 0)
+            per_step = _pad_ld(self.nvar_s) + self.n + self.m
             fit = (self.fwd_smem_budget // (8 * fg) - self.n * self.m - max(self._nthx(), 1) - 16) // per_step
             ch = min(WARP // fg if fg > 1 else self.chunk, max(fit, 1))
         ch = max(1, min(ch, WARP // fg))
@@ -945,17 +942,14 @@ class OCModuleSource:
         foff_th = foff_ks + _even(n * m)
         foff_dl = foff_th + _even(max(self._nthx(), 1))           # residuals x - xref [CHF*n], u - uref [CHF*m]
         foff_du = foff_dl + chf * n
-        ftma = getattr(self, "fwd_tma", 0)
-        foff_in = _even(foff_du + chf * m)
-        fxs, fus = _even(chf * n + 2), _even(chf * m + 2)       # staged chunk rows: [x | u | xref | uref], +2: parity shift / rounding
-        fts = _pad_ld(foff_in + 2 * (fxs + fus)) if ftma else _pad_ld(foff_du + chf * m)
-        fwarp_doubles = max(fg * fts, WARP) + (2 if ftma else 0)      # + the warp's mbarrier
+        fts = _pad_ld(foff_du + chf * m)
+        fwarp_doubles = max(fg * fts, WARP)
         defs = {
             "N": n, "M": m, "R": r, "NS": ns, "NM": nm, "NVAR": self.nvar, "NVAR_S": self.nvar_s,
             "AUXLD": self.auxld, "CH": self.chunk, "WPB": self.wpb, "LDZ": self.ldz,
             "LDK": self.ldk, "OFF_ZT": off_zt, "OFF_KS": off_ks, "OFF_QUU": off_quu, "OFF_TH": off_th,
             "FLD": fld, "FOFF_KS": foff_ks, "FOFF_TH": foff_th, "FOFF_DL": foff_dl, "FG": fg, "CHF": chf, "FTS": fts,
-            "FOFF_DU": foff_du, "FGS": self._fwd_group_stride(), "FTMA": 1 if ftma else 0, "FOFF_IN": foff_in, "FXS": fxs, "FUS": fus,
+            "FOFF_DU": foff_du, "FGS": self._fwd_group_stride(),
             "FWARP_DOUBLES": fwarp_doubles, "WPBF": getattr(self, "wpbf", 4), "MINBF": getattr(self, "min_blocks_f", 1),
             "WARP_DOUBLES": warp_doubles, "NTH": self.nth, "NRCP": self._nthx() - self.nth, "NTHX": max(self._nthx(), 1), "MINB": getattr(self, "min_blocks", 1), "GREC": (n + r) * m,
             "NDENSE": n * n + n * m + n * r + n * n + n * m + n * r + m * n + m * m + m * r,
@@ -1096,8 +1090,7 @@ class OCModuleSource:
       if (%(el)s < PDP_CH && te < H)
         pdp_f_aux_slots(Xb + (size_t)te * PDP_N, Ub + (size_t)te * PDP_M, Lb + (size_t)te * PDP_N, TH, auxc + %(el)s * PDP_AUXLD);
     }""" % {"el": el},
-            "@@EVAL_DYN@@": ("        pdp_f_dyn_slots(fin_x, fin_u, the, eo);" if getattr(self, "fwd_tma", 0) else
-                             "        pdp_f_dyn_slots(X + ((size_t)be * (H + 1) + te) * PDP_N, U + ((size_t)be * H + te) * PDP_M, the, eo);"),
+            "@@EVAL_DYN@@": "        pdp_f_dyn_slots(X + ((size_t)be * (H + 1) + te) * PDP_N, U + ((size_t)be * H + te) * PDP_M, the, eo);",
             "@@EVAL_DYN_COOP@@": "",
             "@@PREFETCH_AUX_CHUNK@@": "",      # measured: no gain (two-trajectory kernel) / a loss (one-trajectory kernel)
             "@@PREFETCH_DYN_CHUNK@@": """#if PDP_PF

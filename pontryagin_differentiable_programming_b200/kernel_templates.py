@@ -651,51 +651,6 @@ pdp_k_aux_lqr_fwd(int B, int H, const double* __restrict__ X, const double* __re
 @@X0STORE@@
   }
   const bool fused = (loss_dp != nullptr) && (Xref != nullptr);
-#if PDP_FTMA
-  // The rows the chunk evaluation needs (x_t, u_t and, for the fused loss, xref_t, uref_t of PDP_CHF steps) are contiguous
-  // per trajectory: lane 0 brings them in with one bulk async copy per array and trajectory, ONE CHUNK AHEAD (issued right
-  // after the previous evaluation has consumed the slots), completion on the warp's mbarrier -- the evaluation's loads were
-  // this kernel's long-scoreboard stalls (16 % of its samples).  Slots: [x | u | xref | uref] at PDP_FOFF_IN of each
-  // trajectory's region; a chunk that starts 8 bytes off a 16-byte boundary sits one double into its slot.
-  double* FMB = wbase + PDP_FG * PDP_FTS;
-  unsigned fphase = 0;
-  if (lane == 0) pdp_mbar_init(FMB);
-  pdp_mbar_init_fence();
-  __syncwarp();
-  auto f_issue = [&](const int tcn) {
-    const int nn = H - tcn < PDP_CHF ? H - tcn : PDP_CHF;
-    pdp_tma_plan pl[PDP_FG * 4];
-    unsigned tx = 0;
-    #pragma unroll
-    for (int gq = 0; gq < PDP_FG; ++gq) {
-      const size_t bb = (size_t)((b0 + gq < B) ? b0 + gq : B - 1);
-      pl[4 * gq + 0] = pdp_tma_plan_load(X + (bb * (H + 1) + tcn) * PDP_N, nn * PDP_N, X + (size_t)B * (H + 1) * PDP_N);
-      pl[4 * gq + 1] = pdp_tma_plan_load(U + (bb * H + tcn) * PDP_M, nn * PDP_M, U + (size_t)B * H * PDP_M);
-      tx += pl[4 * gq].bytes + pl[4 * gq + 1].bytes;
-      if (fused) {
-        pl[4 * gq + 2] = pdp_tma_plan_load(Xref + (bb * (H + 1) + tcn) * PDP_N, nn * PDP_N, Xref + (size_t)B * (H + 1) * PDP_N);
-        tx += pl[4 * gq + 2].bytes;
-        if (Uref) {
-          pl[4 * gq + 3] = pdp_tma_plan_load(Uref + (bb * H + tcn) * PDP_M, nn * PDP_M, Uref + (size_t)B * H * PDP_M);
-          tx += pl[4 * gq + 3].bytes;
-        }
-      }
-    }
-    pdp_mbar_expect(FMB, tx);
-    #pragma unroll
-    for (int gq = 0; gq < PDP_FG; ++gq) {
-      double* fin = wbase + gq * PDP_FTS + PDP_FOFF_IN;
-      pdp_tma_issue_load(fin, pl[4 * gq + 0], FMB);
-      pdp_tma_issue_load(fin + PDP_FXS, pl[4 * gq + 1], FMB);
-      if (fused) {
-        pdp_tma_issue_load(fin + PDP_FXS + PDP_FUS, pl[4 * gq + 2], FMB);
-        if (Uref) pdp_tma_issue_load(fin + 2 * PDP_FXS + PDP_FUS, pl[4 * gq + 3], FMB);
-      }
-    }
-  };
-  if (lane == 0) f_issue(0);
-  __syncwarp();       // (only the CPU emulator needs it: there the copy is lane 0's memcpy, and mbarrier waits are no-ops)
-#endif
   double dpacc = 0.0, lossacc = 0.0;
   double lacc[PDP_FG];
   #pragma unroll
@@ -712,10 +667,6 @@ pdp_k_aux_lqr_fwd(int B, int H, const double* __restrict__ X, const double* __re
   for (int tc = 0; tc < H; tc += PDP_CHF) {
     const int nst = (tc + PDP_CHF < H ? PDP_CHF : H - tc);
     (void)nst;
-#if PDP_FTMA
-    pdp_mbar_wait(FMB, fphase);          // this chunk's rows were requested one chunk ago
-    fphase ^= 1;
-#endif
 @@EVAL_DYN_COOP@@
     {
       const int te = tc + se;
@@ -723,27 +674,13 @@ pdp_k_aux_lqr_fwd(int B, int H, const double* __restrict__ X, const double* __re
         double* eo = ereg + se * PDP_FLD;
         const double* the = ereg + PDP_FOFF_TH;
         (void)the; (void)eo;
-#if PDP_FTMA
-        // staged rows of step te: the chunk of trajectory `be` starts at row tc of its arrays
-        const double* fin = ereg + PDP_FOFF_IN;
-        const double* fin_x = fin + ((reinterpret_cast<uintptr_t>(X + ((size_t)be * (H + 1) + tc) * PDP_N) >> 3) & 1) + se * PDP_N;
-        const double* fin_u = fin + PDP_FXS + ((reinterpret_cast<uintptr_t>(U + ((size_t)be * H + tc) * PDP_M) >> 3) & 1) + se * PDP_M;
-        (void)fin_x; (void)fin_u;
-#endif
 @@EVAL_DYN@@
         if (fused) {
           // loss / chain rule of the IRL scripts (reference Examples/IRL/quadrotor/uav_PDP.py:67-75), per evaluation lane
-#if PDP_FTMA
-          const double* xe = fin_x;
-          const double* xr = fin + PDP_FXS + PDP_FUS + ((reinterpret_cast<uintptr_t>(Xref + ((size_t)be * (H + 1) + tc) * PDP_N) >> 3) & 1) + se * PDP_N;
-          const double* ue = fin_u;
-          const double* ur = Uref ? fin + 2 * PDP_FXS + PDP_FUS + ((reinterpret_cast<uintptr_t>(Uref + ((size_t)be * H + tc) * PDP_M) >> 3) & 1) + se * PDP_M : fin_u;
-#else
           const double* xe = X + ((size_t)be * (H + 1) + te) * PDP_N;
           const double* xr = Xref + ((size_t)be * (H + 1) + te) * PDP_N;
           const double* ue = U + ((size_t)be * H + te) * PDP_M;
           const double* ur = Uref ? Uref + ((size_t)be * H + te) * PDP_M : ue;
-#endif
           #pragma unroll
           for (int i = 0; i < PDP_N; ++i) {
             const double d = xe[i] - xr[i];
@@ -757,13 +694,8 @@ pdp_k_aux_lqr_fwd(int B, int H, const double* __restrict__ X, const double* __re
         }
       }
     }
-#if !PDP_FTMA
 @@PREFETCH_DYN_CHUNK@@
-#endif
     __syncwarp();
-#if PDP_FTMA
-    if (lane == 0 && tc + PDP_CHF < H) f_issue(tc + PDP_CHF);     // every lane has consumed the slots: refill them for the next chunk
-#endif
     const int tend = tc + PDP_CHF < H ? tc + PDP_CHF : H;
     #pragma unroll 1
     for (int t = tc; t < tend; ++t) {

@@ -15,12 +15,11 @@ sys.path.insert(0, ROOT)
 # every variant: keyword overrides of BASE (= the shipped configuration of engine.OCSystem)
 BASE = dict(chunk=8, warps_per_block=1, min_blocks=8, fwd_warps_per_block=1, fwd_min_blocks=8, keep_fg=True,
             fast_rcp=True, early_solve=True, fwd_pack=3, fwd_chunk=10, bwd_pack=2, fwd_vec=-1, prefetch=2, prefetch_dist=2,
-            inline_eval=-1, h_group=1, prefetch_l1_lead=0, fwd_tma=1)
+            inline_eval=-1, h_group=1, prefetch_l1_lead=0)
 V1 = dict(bwd_pack=1, chunk=17, warps_per_block=4, min_blocks=3, keep_fg=True)     # one trajectory per warp
 VARIANTS = [
     V1,
     {},                                                                    # shipped: two trajectories per warp
-    dict(fwd_tma=0),                                                       # forward kernel without TMA-staged chunk rows
 ]
 # Measured and removed in round 2 (profiles/r2a_tune_pending_variants.json, B200, C3 at 16 384 trajectories; shipped path
 # rollout 0.101 / bwd 0.650 / fwd 0.403 ms): cp.async staging of the backward kernel's chunk rows (bwd 0.757), of the
@@ -31,8 +30,10 @@ VARIANTS = [
 # the staging tile, [F|G] re-read from the chunk buffer) -- 0.667 ms at the same 8 warps per SM (+40 shared-memory wavefronts
 # per step), and SLOWER with every extra resident warp the smaller register budget allows: 10 warps/SM 0.770, 12: 0.957,
 # 14: 1.232, 16: 1.369 ms.
-# TMA-staged chunk rows (profiles/r2t_tune_tma_staged_chunk_rows.json): forward kernel 0.3975 -> 0.3805 ms (adopted, default);
-# the same for the backward kernel: 0.6058 -> 0.6054 ms (no gain: its evaluator's loads are not a limiter; removed).  The kernel is not latency-bound: two warps per scheduler already saturate what the shared-memory
+# TMA-staged chunk rows (lane 0 brings the evaluation's rows in with one cp.async.bulk per array and trajectory, one chunk
+# ahead; profiles/r2t_tune_tma_staged_chunk_rows.json, r2w_sweep_pipeline_fwd_variants.json): forward kernel alone 0.3975 ->
+# 0.3805 ms, but its slots (+8 KB per warp) cost the co-residency the pipelined sweep lives on: whole sweep 1.068 -> 1.082 ms;
+# backward kernel 0.6058 -> 0.6054 ms (its evaluator's loads are not a limiter).  Both removed.  The kernel is not latency-bound: two warps per scheduler already saturate what the shared-memory
 # data path and the FP64 pipe deliver together; more warps only shrink the chunk (fewer evaluation lanes) and add spills.
 
 
