@@ -220,13 +220,21 @@ class OCSys:
             control_init = _dev_tensor(numpy.asarray(control_init, dtype=numpy.float64).reshape(1, horizon, self.n_control), dev)
         sol = self.ocSolver_batched(x0, horizon, theta, control_init=control_init, n_starts=n_starts,
                                     verbose=print_level > 0)
+        converged = bool(sol["converged"][0].item()) if "converged" in sol else True
+        if not converged:
+            # the reference never looks at IPOPT's return status (PDP.py:182-183); here a solve that stopped short of a
+            # stationary point is at least announced: the auxiliary-system gradient is only meaningful at dH/du = 0
+            import warnings
+            warnings.warn("OCSys.ocSolver: the Newton/DDP solve did not reach the stationarity tolerance "
+                          "(max |dH/du| = %.3g); try control_init= or n_starts=" % float(sol["grad_norm"][0].item()), RuntimeWarning)
         return {"state_traj_opt": sol["X"][0].cpu().numpy(),
                 "control_traj_opt": sol["U"][0].cpu().numpy(),
                 "costate_traj_opt": sol["Lam"][0].cpu().numpy(),
                 'auxvar_value': auxvar_value,
                 "time": numpy.arange(horizon + 1),
                 "horizon": horizon,
-                "cost": sol["cost"][0:1].cpu().numpy().reshape(1, 1)}
+                "cost": sol["cost"][0:1].cpu().numpy().reshape(1, 1),
+                "converged": converged}        # additive key (not in the reference's dict)
 
     def getAuxSys(self, state_traj_opt, control_traj_opt, costate_traj_opt, auxvar_value=1):
         """Matrices of the auxiliary control system along a trajectory (reference PDP.py:272-314), evaluated
