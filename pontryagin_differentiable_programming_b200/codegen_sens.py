@@ -19,7 +19,8 @@ dimension (``blockIdx.x``), so the groups of one block of trajectories are sched
 second group's reads of the shared input rows hit L2 instead of HBM (measured round 2: the round-1 order
 ``(trajectory block, group)`` read everything once per group from DRAM, 1.86x the algorithmic bytes at C5; C5
 0.321 -> 0.300 ms).  Measured and rejected in round 2 (profiles/r2d_*, r2e_*, r2f_*): fetching the next step's rows into
-registers (spills: 0.381 ms), cache-hint prefetches (0.415 ms), rows as 16-byte pairs (0.314 ms) and a
+registers (spills: 0.381 ms), cache-hint prefetches (0.415 ms), rows as 16-byte pairs (0.314 ms), register caps for more
+resident warps (168 / 128 registers: 0.70 / 1.16 ms -- the spills cost far more than the occupancy gives) and a
 warp-cooperative staged variant with shared tiles (0.47 ms).
 """
 from __future__ import annotations

@@ -18,7 +18,7 @@ from pontryagin_differentiable_programming_b200 import systems  # noqa: E402
 from tools.tune_aux_lqr import make  # noqa: E402
 
 # module variants to put through the pipelined sweep (keyword overrides of tune_aux_lqr.BASE); {} = the shipped module
-VARIANTS = [dict(), dict(fwd_min_blocks=9), dict(fwd_min_blocks=10), dict(fwd_min_blocks=12), dict(fwd_min_blocks=10, min_blocks=7), dict(min_blocks=7)]
+VARIANTS = [dict()]
 
 
 def main():
@@ -31,7 +31,7 @@ def main():
     rows, ref = [], None
     for var in VARIANTS:
         s = make(**var)
-        for parts in (2, 4):
+        for parts in (1, 2, 3, 4, 5, 6, 8):
             s.set_sweep_parts(parts)
             fn = lambda: s.sweep(d[0], d[1], d[2], Xref=d[3], Uref=d[4], out=out)
             for _ in range(3):

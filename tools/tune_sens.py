@@ -11,7 +11,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-SYSID_VARIANTS = [dict(max_group_cols=3), dict(max_group_cols=2), dict(max_group_cols=5), dict(max_group_cols=3, block=32)]
+SYSID_VARIANTS = [dict(max_group_cols=3), dict(max_group_cols=2), dict(max_group_cols=5)]
 CP_VARIANTS = [dict(max_group_cols=12), dict(max_group_cols=3)]
 
 
