@@ -16,8 +16,10 @@
 A "step" = one pass of that path over the per-rank batch.  Inputs are synthetic (seeded, float64).
 `value` times the step with inputs resident in HBM; `e2e` times the C-ABI host-buffer call (pinned host inputs -> H2D ->
 kernels -> D2H of the step's result) of the same step; `roofline` is for the step's dominant kernel, timed live with CUDA
-events on the launching stream; `cpu_baseline` / `--impl reference` time the oracle port (reference-shaped NumPy loops,
-`oracle/`) on the box's host cores.  A parity subset is checked against the oracle in every run.
+events on the launching stream; `cpu_baseline` / `--impl reference` time the path on the box's host cores: the reference's
+own NumPy half (unmodified `LQR.lqrSolver` / `integrateAuxSys`, staged under `oracle/_ref` by `oracle/stage_reference.py`,
+kind "reference") fed by the oracle's restatement of the CasADi half, or the oracle alone (kind "port") where that copy is
+absent or the path has no NumPy half (C4).  A parity subset is checked against the oracle in every run.
 """
 import argparse
 import json
@@ -246,34 +248,86 @@ def _oracle(kind):
     return _ORACLE[kind]
 
 
+def _ref_loader():
+    """oracle/ref_loader when the unmodified reference PDP.py is reachable (build container, or staged under oracle/_ref by
+    oracle/stage_reference.py), else None: the CPU arms then time the oracle's restatement of the NumPy half as well."""
+    from oracle import ref_loader
+    return ref_loader if ref_loader.reference_available() else None
+
+
+def cpu_kind(kind):
+    """'reference' = the reference's own NumPy half (LQR.lqrSolver / SysID.integrateAuxSys / ControlPlanning.integrateAuxSys,
+    unmodified) fed by the oracle's restatement of the CasADi half; 'port' = oracle only.  C4's reference
+    path (recmat) is one CasADi function with no NumPy half."""
+    return "reference" if kind != "c4" and _ref_loader() is not None else "port"
+
+
+def _asmat(fn, shape, *a):
+    return np.asarray(fn(*a), dtype=np.float64).reshape(shape)
+
+
 def _cpu_worker(job):
     kind, H, idx, cores, data = job
+    if cores > 1:                                   # one process per core: keep each worker's BLAS on its own core
+        try:                                        # (SURVEY 8(d): pool over trajectories with OMP_NUM_THREADS=1)
+            from threadpoolctl import threadpool_limits
+            threadpool_limits(1)
+        except ImportError:
+            pass
     obj, po = _oracle(kind)
+    rl = _ref_loader() if cpu_kind(kind) == "reference" else None
     t0 = time.perf_counter()
     if kind == "c3":
         x0, theta, U, _, _ = data
         for b in range(x0.shape[0]):
-            po.pdp_sweep(obj, x0[b], U[b], theta[b])
+            if rl is None:
+                po.pdp_sweep(obj, x0[b], U[b], theta[b])
+            else:                                   # Examples/IRL/quadrotor/uav_PDP.py:52-65 with ocSolver's outputs given
+                X, _ = obj.rollout(x0[b], U[b], theta[b])
+                L = obj.costate(X, U[b], theta[b])
+                rl.reference_lqr_solver(obj.getAuxSys(X, U[b], L, theta[b]), np.zeros((obj.n, obj.r)), H)
     elif kind == "c5":
         inputs, states, theta = data
-        obj.step(list(inputs), list(states), theta)
+        if rl is None:
+            obj.step(list(inputs), list(states), theta)
+        else:                                       # PDP.py:1261-1296 with the reference's own integrateAuxSys
+            sid, n, r = rl.load_reference_pdp().SysID(), obj.n, obj.r
+            for u, obs in zip(inputs, states):
+                X = obj.integrateDyn(obs[0], u, theta)
+                F = [_asmat(obj.dfx_fn, (n, n), X[t], u[t], theta) for t in range(H)]
+                E = [_asmat(obj.dfe_fn, (n, r), X[t], u[t], theta) for t in range(H)]
+                S = sid.integrateAuxSys(F, E, np.zeros((n, r)))["state_traj"]
+                d, dp = X - obs, np.zeros(r)
+                for t in range(H + 1):
+                    dp += d[t] @ S[t]
     elif kind == "c4":
         x0, U = data
         for b in range(x0.shape[0]):
             obj.adjoint_grad(x0[b], U[b])
     elif kind == "c2":
         x0, theta = data
+        if rl is not None:
+            cpr, n, m, r = rl.load_reference_pdp().ControlPlanning(), obj.n, obj.m, obj.r
         for b in range(x0.shape[0]):
-            obj.step(x0[b], H, theta[b])
+            if rl is None:
+                obj.step(x0[b], H, theta[b])
+            else:                                   # PDP.py:850-878 with the reference's own integrateAuxSys
+                X, U, _ = obj.integrateSys(x0[b], H, theta[b])
+                F = [_asmat(obj.dfx_fn, (n, n), X[t], U[t]) for t in range(H)]
+                G = [_asmat(obj.dfu_fn, (n, m), X[t], U[t]) for t in range(H)]
+                Ux = [_asmat(obj.dpolicy_dx_fn, (m, n), [t], X[t], theta[b]) for t in range(H)]
+                Ue = [_asmat(obj.dpolicy_de_fn, (m, r), [t], X[t], theta[b]) for t in range(H)]
+                aux = cpr.integrateAuxSys(F, G, Ux, Ue, np.zeros((n, r)))
+                g = np.zeros(r)
+                for t in range(H):
+                    g += (_asmat(obj.dcx_fn, (1, n), X[t], U[t]) @ aux["state_traj"][t] +
+                          _asmat(obj.dcu_fn, (1, m), X[t], U[t]) @ aux["control_traj"][t]).ravel()
+                g += (_asmat(obj.dhx_fn, (1, n), X[H]) @ aux["state_traj"][H]).ravel()
     return time.perf_counter() - t0
 
 
-def cpu_sweeps_per_s(kind, H, per_core, cores):
-    """Oracle port (reference-shaped per-step NumPy / lambdified loops), one process per host core, ``per_core``
-    trajectories of the config's workload each."""
-    import multiprocessing as mp
-    obj, po = _oracle(kind)                      # build before forking so the children inherit the lambdified functions
-    n = per_core * cores
+def _cpu_jobs(kind, obj, n, H, cores):
+    """``n`` trajectories of the config's synthetic workload dealt over ``cores`` workers."""
     if kind == "c3":
         data = synth_quadrotor(n, H, seed=1)
         jobs = [tuple(a[i::cores] for a in data) for i in range(cores)]
@@ -290,6 +344,19 @@ def cpu_sweeps_per_s(kind, H, per_core, cores):
     else:
         x0, theta = synth_cartpole(n, obj.r, seed=1)
         jobs = [(x0[i::cores], theta[i::cores]) for i in range(cores)]
+    return jobs
+
+
+def cpu_sweeps_per_s(kind, H, per_core, cores):
+    """Oracle port (reference-shaped per-step NumPy / lambdified loops), one process per host core, ``per_core``
+    trajectories of the config's workload each."""
+    import multiprocessing as mp
+    obj, po = _oracle(kind)                      # build before forking so the children inherit the lambdified functions
+    if cpu_kind(kind) == "reference":
+        _ref_loader().load_reference_pdp()       # likewise the imported reference module
+    _cpu_worker((kind, H, 0, 1, _cpu_jobs(kind, obj, 1, H, 1)[0]))       # one-off costs (lazy imports, BLAS start-up) untimed
+    n = per_core * cores
+    jobs = _cpu_jobs(kind, obj, n, H, cores)
     jobs = [(kind, H, i, cores, j) for i, j in enumerate(jobs)]
     t0 = time.perf_counter()
     if cores == 1:
@@ -301,6 +368,8 @@ def cpu_sweeps_per_s(kind, H, per_core, cores):
     return n / wall, wall
 
 
+CPU_KIND_NOTE = {"reference": "unmodified reference NumPy half (oracle/_ref/PDP.py) + oracle restatement of the CasADi half",
+                 "port": "oracle port"}
 CPU_PER_CORE = {"c3": 48, "c5": 24, "c4": 24, "c2": 48}     # ~1-2 s of oracle work per core and step
 
 
@@ -320,14 +389,15 @@ def run_reference(args, cfg):
         vals.append(v)
     total = time.perf_counter() - t_all
     value = float(np.mean(vals))
-    sample = "%d trajectories of the %s workload per step (%d per core x %d cores), oracle port" % (
-        per_core * cores, args.config.upper(), per_core, cores)
+    sample = "%d trajectories of the %s workload per step (%d per core x %d cores), %s" % (
+        per_core * cores, args.config.upper(), per_core, cores, CPU_KIND_NOTE[cpu_kind(args.config)])
     print(json.dumps({
         "impl": "reference", "metric": cfg["metric"], "value": value, "unit": "sweeps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": cfg["workload"], "batch_per_step": per_core * cores},
-        "cpu_baseline": {"value": value, "unit": "sweeps/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "sweeps/s", "cores": cores, "kind": cpu_kind(args.config),
+                         "sample": sample},
         "e2e": {"value": value, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
@@ -926,9 +996,9 @@ def run_gpu(args, cfg):
             cores = os.cpu_count() or 1
             per_core = args.ref_per_core or CPU_PER_CORE[args.config]
             v, wall = cpu_sweeps_per_s(args.config, H, per_core, cores)
-            line["cpu_baseline"] = {"value": v, "unit": "sweeps/s", "cores": cores, "kind": "port",
-                                    "sample": "%d trajectories of the same workload (%d per core), %.1f s wall"
-                                              % (per_core * cores, per_core, wall)}
+            line["cpu_baseline"] = {"value": v, "unit": "sweeps/s", "cores": cores, "kind": cpu_kind(args.config),
+                                    "sample": "%d trajectories of the same workload (%d per core), %.1f s wall, %s"
+                                              % (per_core * cores, per_core, wall, CPU_KIND_NOTE[cpu_kind(args.config)])}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

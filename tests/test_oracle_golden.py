@@ -121,6 +121,33 @@ def test_k6_live_reference_lqr_and_sensitivity_recursions():
     assert np.allclose(np.stack(sid["state_traj"]), g["fs_sysid_X"], rtol=0, atol=1e-13)
 
 
+@pytest.mark.skipif(not ref_loader.reference_available(), reason="reference PDP.py neither mounted nor staged")
+def test_k6_live_reference_lqr_solver_matches_the_restatement_on_a_quadrotor_sweep():
+    """The CPU arm's 'reference' kind (bench.py): the unmodified LQR.lqrSolver fed by the oracle's getAuxSys gives the
+    restated lqr_solve's trajectories (1e-10 relative)."""
+    oc = pdp_oracle.build_oc(envs.quadrotor(c=0.01, wthrust=0.1), 0.1)
+    oc.diffPMP()
+    rng = np.random.default_rng(5)
+    x0 = np.concatenate([rng.uniform(-3, 3, 3), np.zeros(3), [1, 0, 0, 0], np.zeros(3)])
+    theta = np.array([1, 1, 1, 1, 0.4, 1, 1, 5, 1.0]) + rng.uniform(-0.2, 0.2, 9)
+    U = 2.5 + 0.3 * rng.standard_normal((12, 4))
+    X, _ = oc.rollout(x0, U, theta)
+    aux = oc.getAuxSys(X, U, oc.costate(X, U, theta), theta)
+    ours = pdp_oracle.lqr_solve(aux, np.zeros((13, 9)), 12)
+    ref = ref_loader.reference_lqr_solver(aux, np.zeros((13, 9)), 12)
+    for k in ("state_traj_opt", "control_traj_opt", "costate_traj_opt"):
+        a, b = np.stack(ours[k]), np.stack(ref[k])
+        assert np.max(np.abs(a - b)) <= 1e-10 * np.max(np.abs(b)), k
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/PDP/PDP.py"), reason="build container only")
+def test_staged_reference_copy_is_byte_identical():
+    import filecmp
+    from oracle import stage_reference
+    assert stage_reference.stage(verbose=False)
+    assert filecmp.cmp(stage_reference.SRC, stage_reference.DST, shallow=False)
+
+
 @pytest.mark.parametrize("env,demo", [("pendulum", 0), ("pendulum", 3), ("quadrotor", 0), ("robotarm", 1), ("cartpole", 2)])
 def test_k2_oracle_oc_solver_reproduces_shipped_ipopt_demos(env, demo):
     """The oracle's OC solve from the cold start U = 0 lands on the demo IPOPT found (K2)."""
