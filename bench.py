@@ -17,7 +17,7 @@ A "step" = one pass of that path over the per-rank batch.  Inputs are synthetic 
 `value` times the step with inputs resident in HBM; `e2e` times the C-ABI host-buffer call (pinned host inputs -> H2D ->
 kernels -> D2H of the step's result) of the same step; `roofline` is for the step's dominant kernel, timed live with CUDA
 events on the launching stream; `cpu_baseline` / `--impl reference` time the path on the box's host cores: the reference's
-own NumPy half (unmodified `LQR.lqrSolver` / `integrateAuxSys`, staged under `oracle/_ref` by `oracle/stage_reference.py`,
+own NumPy half (unmodified `LQR.lqrSolver` / `integrateAuxSys`, staged under `baseline/_ref/reference_src` by `oracle/stage_reference.py`,
 kind "reference") fed by the oracle's restatement of the CasADi half, or the oracle alone (kind "port") where that copy is
 absent or the path has no NumPy half (C4).  A parity subset is checked against the oracle in every run.
 """
@@ -249,7 +249,7 @@ def _oracle(kind):
 
 
 def _ref_loader():
-    """oracle/ref_loader when the unmodified reference PDP.py is reachable (build container, or staged under oracle/_ref by
+    """oracle/ref_loader when the unmodified reference PDP.py is reachable (build container, or staged under baseline/_ref/reference_src by
     oracle/stage_reference.py), else None: the CPU arms then time the oracle's restatement of the NumPy half as well."""
     from oracle import ref_loader
     return ref_loader if ref_loader.reference_available() else None
@@ -368,7 +368,7 @@ def cpu_sweeps_per_s(kind, H, per_core, cores):
     return n / wall, wall
 
 
-CPU_KIND_NOTE = {"reference": "unmodified reference NumPy half (oracle/_ref/PDP.py) + oracle restatement of the CasADi half",
+CPU_KIND_NOTE = {"reference": "unmodified reference NumPy half (baseline/_ref/reference_src/PDP.py) + oracle restatement of the CasADi half",
                  "port": "oracle port"}
 CPU_PER_CORE = {"c3": 48, "c5": 24, "c4": 24, "c2": 48}     # ~1-2 s of oracle work per core and step
 

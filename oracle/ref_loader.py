@@ -1,7 +1,7 @@
 """Import the UNMODIFIED reference ``PDP/PDP.py`` under a stub ``casadi`` (TEST INFRASTRUCTURE).
 
 Source of the file, in this order: ``/root/reference/PDP/PDP.py`` (the build container) or the byte-identical copy that
-``oracle/stage_reference.py`` (the committed recipe, run by ``__graft_entry__.build()``) puts under ``oracle/_ref/`` --
+``oracle/stage_reference.py`` (the committed recipe, run by ``__graft_entry__.build()``) puts under ``baseline/_ref/reference_src/`` (next to the staged Examples scripts) --
 git-ignored, so no reference source enters the history, but it travels to the GPU box with the snapshot so that
 ``bench.py``'s CPU arms can time the reference's OWN NumPy half there (``cpu_baseline.kind`` "reference").
 The stub makes ``from casadi import *`` succeed so the pure-NumPy half of the
@@ -16,7 +16,7 @@ import sys
 import types
 
 REFERENCE_ROOT = "/root/reference"
-STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "PDP.py")
+STAGED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "reference_src", "PDP.py")
 _MOD = None
 
 

@@ -1,5 +1,5 @@
-"""Recipe that stages the UNMODIFIED reference ``PDP/PDP.py`` under ``oracle/_ref/`` (TEST INFRASTRUCTURE, build container
-only -- needs /root/reference).  ``oracle/_ref/`` is git-ignored (no reference source in the history) but not
+"""Recipe that stages the UNMODIFIED reference ``PDP/PDP.py`` under ``baseline/_ref/reference_src/`` (TEST INFRASTRUCTURE, build container
+only -- needs /root/reference).  ``baseline/_ref/`` is git-ignored (no reference source in the history) but not
 gpurun-ignored, so the copy travels to the GPU box, where ``oracle/ref_loader.py`` imports it under a ``casadi`` stub and
 ``bench.py``'s CPU arms time the reference's own NumPy half (``LQR.lqrSolver`` PDP.py:446-615, ``SysID.integrateAuxSys``
 :1241-1259, ``ControlPlanning.integrateAuxSys`` :813-838) next to the oracle's restatement of the CasADi half.
@@ -11,7 +11,7 @@ import os
 import shutil
 
 SRC = "/root/reference/PDP/PDP.py"
-DST = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "PDP.py")
+DST = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "reference_src", "PDP.py")
 
 
 def stage(verbose=True):

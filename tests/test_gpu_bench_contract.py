@@ -66,5 +66,5 @@ def test_reference_arm_json_contract():
     d = _run("--impl", "reference", "--gpus", "1", "--steps", "1", "--warmup", "1", "--ref-per-core", "1")
     assert d["impl"] == "reference" and d["unit"] == "sweeps/s" and d["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    staged = os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "PDP.py"))       # oracle/stage_reference.py ran in build()
+    staged = os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "reference_src", "PDP.py"))       # oracle/stage_reference.py ran in build()
     assert d["cpu_baseline"]["kind"] == ("reference" if staged else "port") and d["gpu_launches"] == 0
