@@ -78,6 +78,9 @@ def build_all(verbose=False):
         out[name] = fn().module_path
         if verbose:
             print("built", name, out[name])
+    out["oc_rocket_adjoint"] = rocket_oc_adjoint().module_path          # C4 (bench.py --config c4, tests/test_gpu_configs.py)
+    if verbose:
+        print("built rocket_adjoint", out["oc_rocket_adjoint"])
     # Newton (ocSolver) variants, generic dense-LQR sizes used by the drop-in LQR class on the shipped examples
     from . import ocsolver
     for name, fn in OC_BUILDERS.items():
