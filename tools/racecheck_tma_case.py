@@ -10,7 +10,8 @@ from pontryagin_differentiable_programming_b200 import systems
 
 dev = torch.device("cuda:0")
 t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
-x0, U = bench.synth_rocket(3, 19, seed=3)
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 3      # B = 1: one active lane per warp, nothing for the tool to mis-attribute
+x0, U = bench.synth_rocket(B, 19, seed=3)
 ro = systems.rocket_oc_adjoint(0.1)
 o = ro.rollout_costate(t(x0), torch.zeros((1, 1), dtype=torch.float64, device=dev), t(U), want_dHu=True)
 torch.cuda.synchronize()
