@@ -18,6 +18,7 @@ Nothing here is copied from CasADi or from the reference; it is a from-scratch e
 """
 from __future__ import annotations
 
+import hashlib
 import math
 import numbers
 from typing import Dict, Iterable, List, Sequence, Tuple
@@ -42,13 +43,15 @@ inf = math.inf
 class Node:
     """One vertex of the expression DAG (immutable, hash-consed)."""
 
-    __slots__ = ("op", "args", "val", "uid")
+    __slots__ = ("op", "args", "val", "uid", "skey", "height")
 
-    def __init__(self, op, args, val, uid):
+    def __init__(self, op, args, val, uid, skey):
         self.op = op
         self.args = args
         self.val = val
         self.uid = uid
+        self.skey = skey          # structural key: depends on the expression's content only, never on creation order
+        self.height = 1 + max(a.height for a in args) if args else 0
 
     def __repr__(self):
         return _fmt(self)
@@ -60,12 +63,24 @@ _SYM_COUNTER = [0]
 
 
 
+def _skey(op, args, val) -> int:
+    """64-bit content hash of a node: operator, the operands' keys, and the constant value or the symbol NAME (not its
+    creation index).  Stable across processes (no use of Python's randomised ``hash``)."""
+    if op == "sym":
+        text = "sym:%s" % (val[0],)
+    elif op == "const":
+        text = "const:%r" % (val,)
+    else:
+        text = "%s:%s:%r" % (op, ",".join("%x" % a.skey for a in args), val)
+    return int.from_bytes(hashlib.blake2b(text.encode(), digest_size=8).digest(), "big")
+
+
 def _mk(op, args=(), val=None):
     key = (op, tuple(a.uid for a in args), val)
     node = _TABLE.get(key)
     if node is None:
         _COUNTER[0] += 1
-        node = Node(op, tuple(args), val, _COUNTER[0])
+        node = Node(op, tuple(args), val, _COUNTER[0], _skey(op, args, val))
         _TABLE[key] = node
     return node
 
@@ -94,13 +109,16 @@ def _isc(n: Node) -> bool:
 
 
 def _swap(a: Node, b: Node) -> bool:
-    """Canonical operand order of commutative ops: constants first, then creation order.  Constants
-    are shared between systems built in one process, so ordering them by uid would make the
-    generated source (and its cache key) depend on what else was built earlier."""
+    """Canonical operand order of commutative ops: constants first, then the shallower operand (height in the DAG: it is
+    ready earlier, which is also what creation order tended to give), then the STRUCTURAL key; creation order only breaks
+    ties between distinct symbols of the same name.  Measured on B200 (profiles/r2f_order_ab.txt): identical kernel times
+    to creation order; ordering by the content hash alone cost the latency-bound C2 / C4 kernels 7-14 %.  Ordering by creation index made the generated source -- and with it
+    the module cache key -- depend on what else had been built from the same symbols earlier in the process (e.g.
+    ``OCSys.diffPMP()`` before the first sweep): same mathematics, different operand order, a needless recompile."""
     ca, cb = a.op == "const", b.op == "const"
     if ca != cb:
         return cb
-    return a.uid > b.uid
+    return (a.height, a.skey, a.uid) > (b.height, b.skey, b.uid)
 
 
 def add(a: Node, b: Node) -> Node:

@@ -310,3 +310,31 @@ def test_ocsolver_refuses_finite_bounds():
     oc.setFinalCost(env.final_cost)
     with pytest.raises(NotImplementedError, match="control_lb"):
         oc.ocSolver([0, 0], 10)
+
+
+def test_generated_source_does_not_depend_on_what_was_built_before():
+    """The module cache key is a hash of the generated source: calling the drop-in ``diffPMP()`` (which differentiates the
+    same symbols in its own order) or building the Newton variant before the first sweep must not change the text."""
+    from PDP import PDP
+    from JinEnv import JinEnv
+    from casadi import vertcat
+    from pontryagin_differentiable_programming_b200 import ocsolver
+
+    def make():
+        e = JinEnv.CartPole(); e.initDyn(); e.initCost(wu=0.1)
+        oc = PDP.OCSys()
+        oc.setAuxvarVariable(vertcat(e.dyn_auxvar, e.cost_auxvar))
+        oc.setControlVariable(e.U)
+        oc.setStateVariable(e.X)
+        oc.setDyn(e.X + 0.1 * e.f)
+        oc.setPathCost(e.path_cost)
+        oc.setFinalCost(e.final_cost)
+        return oc
+
+    plain = make()._system().src.source()
+    a = make()
+    a.diffPMP()
+    assert a._system().src.source() == plain
+    b = make()
+    ocsolver.newton_system(b._system()).src.source()
+    assert b._system().src.source() == plain
