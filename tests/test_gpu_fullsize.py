@@ -41,7 +41,7 @@ def test_c3_full_size_batch_independence_and_chain_rule():
     loss = (dlx ** 2).sum(dim=(1, 2)) + (dlu ** 2).sum(dim=(1, 2))
     dp = torch.einsum("bti,btir->br", dlx, full["dX"]) + torch.einsum("bta,btar->br", dlu, full["dU"])
     ok = torch.isfinite(full["loss_dp"]).all(dim=1) & torch.isfinite(dp).all(dim=1)
-    assert ok.float().mean() > 0.9
+    assert bool(ok.all())          # the oracle finds no non-finite row on these seeded batches (max |dX/dtheta| 1e7)
     scale = dp[ok].abs().amax(dim=1, keepdim=True).clamp_min(1e-300)
     assert ((full["loss_dp"][ok, 1:] - dp[ok]).abs() / scale).max() < 1e-9
     assert ((full["loss_dp"][ok, 0] - loss[ok]).abs() / loss[ok]).max() < 1e-12
@@ -187,7 +187,7 @@ def test_c5_full_size_zero_residual_batch_independence_and_chain_rule():
     Xobs = sid.step(inputs, None, th_true, x0=x0, want_traj=True)["X"]
     zero = sid.step(inputs, Xobs, th_true)["loss_dp"]
     fin = torch.isfinite(Xobs).all(dim=(1, 2))
-    assert fin.float().mean() > 0.9 and bool((zero[fin] == 0).all())
+    assert bool(fin.all()) and bool((zero == 0).all())
     full = sid.step(inputs, Xobs, theta, want_traj=True, want_sens=True)
     again = sid.step(inputs, Xobs, theta)
     assert torch.equal(full["loss_dp"], again["loss_dp"])
@@ -199,7 +199,7 @@ def test_c5_full_size_zero_residual_batch_independence_and_chain_rule():
     loss = (d ** 2).sum(dim=(1, 2))
     dp = torch.einsum("bti,btir->br", d, full["dX"])
     ok = torch.isfinite(full["loss_dp"]).all(dim=1) & torch.isfinite(dp).all(dim=1) & (loss > 0)
-    assert ok.float().mean() > 0.9
+    assert bool(ok.all())          # the oracle finds no non-finite row on these seeded batches (max |dX/dtheta| 1e7)
     scale = dp[ok].abs().amax(dim=1, keepdim=True).clamp_min(1e-300)
     assert ((full["loss_dp"][ok, 1:] - dp[ok]).abs() / scale).max() < 1e-9
     assert ((full["loss_dp"][ok, 0] - loss[ok]).abs() / loss[ok]).max() < 1e-12
@@ -234,7 +234,7 @@ def test_c4_full_size_both_rollout_kernels_agree_and_gradient_matches_finite_dif
     fd = (Jp - Jm) / (2 * eps)
     an = (big["dHu"] * D).sum(dim=(1, 2))
     ok = torch.isfinite(fd) & torch.isfinite(an)
-    assert ok.float().mean() > 0.99
+    assert bool(ok.all())
     # scaled by |dJ/dU| |D| (Cauchy-Schwarz), not by the directional derivative itself, which can be ~0 by chance; the CPU
     # oracle gives 1e-11 on this scale at eps = 1e-5
     scale = big["dHu"].flatten(1).norm(dim=1) * D.flatten(1).norm(dim=1)
